@@ -1,0 +1,134 @@
+// common.cuh -- shared declarations for libannb.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/annb.h"
+
+#define ANNB_API extern "C" __attribute__((visibility("default")))
+
+namespace annb {
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+constexpr int kMaxAnchors = 64;
+
+void set_error(const char *fmt, ...);
+extern int64_t g_launches;
+
+#define ANNB_CUDA(expr)                                                                  \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess) {                                                         \
+            annb::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,                \
+                            cudaGetErrorString(_e));                                     \
+            return _e == cudaErrorMemoryAllocation ? ANNB_ENOMEM : ANNB_ECUDA;           \
+        }                                                                                \
+    } while (0)
+
+#define ANNB_TRY(expr)              \
+    do {                            \
+        int _r = (expr);            \
+        if (_r != ANNB_OK) return _r; \
+    } while (0)
+
+#define ANNB_REQUIRE(cond, code, ...)    \
+    do {                                 \
+        if (!(cond)) {                   \
+            annb::set_error(__VA_ARGS__); \
+            return (code);               \
+        }                                \
+    } while (0)
+
+// every kernel launch goes through this so gpu_launches can be reported
+#define ANNB_LAUNCH(kernel, grid, block, smem, stream, ...)                       \
+    do {                                                                          \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);               \
+        ++annb::g_launches;                                                       \
+        ANNB_CUDA(cudaGetLastError());                                            \
+    } while (0)
+
+// Device buffer with grow-only reuse (avoids cudaMalloc on the hot path).
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return ANNB_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + (bytes >> 3) + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            e = cudaMalloc(&p, bytes);
+            want = bytes;
+        }
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+            p = nullptr;
+            return ANNB_ENOMEM;
+        }
+        cap = want;
+        return ANNB_OK;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+}  // namespace annb
+
+struct annb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int num_sms = annb::kNumSMs;
+    size_t l2_bytes = 0;
+    // scratch reused by the host-pointer entry points
+    annb::DevBuf s_in[6], s_out[3];
+    void *pinned = nullptr;
+    size_t pinned_cap = 0;
+};
+
+enum annb_ds_kind { ANNB_DS_DENSE = 0, ANNB_DS_STRINGS = 1, ANNB_DS_HIST = 2 };
+
+struct annb_dataset {
+    annb_ctx *ctx = nullptr;
+    int kind = 0;
+    int dtype = 0;  // ANNB_F32 / ANNB_F64 for dense
+    int64_t n = 0;
+    int64_t d = 0;        // dense: dims; hist: bins; strings: max length
+    int64_t ld = 0;       // dense/hist: row pitch in elements
+    void *data = nullptr; // dense rows / hist CDFs (double) / string symbols (uint8, 16B-aligned rows)
+    int64_t *offs = nullptr;  // strings: device start offset per string (n+1, 16B aligned starts)
+    int32_t *lens = nullptr;  // strings: device length per string
+    int sigma = 0;            // strings: alphabet size after remap
+    int64_t max_len = 0;
+};
+
+namespace annb {
+
+// ---- internal device-pointer entry points shared between translation units ----
+// All pointers are device pointers; work is enqueued on ctx->stream.
+
+// out[p] = metric(X[i[p]], X[j[p]]), float64 out
+int pair_dists_f64(annb_ctx *ctx, const annb_dataset *ds, int metric, const int32_t *i,
+                   const int32_t *j, int64_t n, double *out);
+// distances from one item (index read from device memory *anchor) to all n items
+int anchor_row_f64(annb_ctx *ctx, const annb_dataset *ds, int metric, const int32_t *anchor_dev,
+                   double *row);
+
+int check_metric(const annb_dataset *ds, int metric);
+
+}  // namespace annb
