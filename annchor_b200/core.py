@@ -1,0 +1,178 @@
+"""Contexts, datasets and the metric-evaluation plug (get_exact_ijs) over libannb.so."""
+import ctypes as C
+import weakref
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, ptr, as_c
+
+
+class Context:
+    """One CUDA device + stream (annb_ctx).  Not thread safe, like the reference's fit()."""
+
+    def __init__(self, device=0):
+        L = _lib.load()
+        h = C.c_void_p()
+        check(L.annb_ctx_create(int(device), C.byref(h)))
+        self.handle = h
+        self.device = int(device)
+        self._L = L
+
+    def sync(self):
+        check(self._L.annb_sync(self.handle))
+
+    def stream(self):
+        s = C.c_uint64()
+        check(self._L.annb_ctx_stream(self.handle, C.byref(s)))
+        return s.value
+
+    def timer_start(self):
+        check(self._L.annb_timer_start(self.handle))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        check(self._L.annb_timer_stop(self.handle, C.byref(ms)))
+        return ms.value
+
+    def close(self):
+        if self.handle:
+            self._L.annb_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default = {}
+
+
+def default_context(device=0):
+    if device not in _default:
+        _default[device] = Context(device)
+    return _default[device]
+
+
+def launch_count():
+    return int(_lib.load().annb_launch_count())
+
+
+def pack_strings(X):
+    """Sequence of str -> (uint8 code units, int64 offsets[n+1]); one byte per code point."""
+    try:
+        enc = [s.encode("latin-1") for s in X]
+    except UnicodeEncodeError as e:
+        raise ValueError("levenshtein on device needs code points < 256 "
+                         "(got %r); wider alphabets are not supported yet" % (e.object[e.start],))
+    offs = np.zeros(len(enc) + 1, dtype=np.int64)
+    np.cumsum([len(e) for e in enc], out=offs[1:])
+    chars = np.frombuffer(b"".join(enc) or b"\0", dtype=np.uint8).copy()
+    return chars, offs
+
+
+class Dataset:
+    """Device-resident copy of X for one metric family (annb_dataset)."""
+
+    def __init__(self, ctx, X, metric, cost_matrix=None):
+        L = _lib.load()
+        self.ctx = ctx
+        self._L = L
+        self.metric = metric if isinstance(metric, int) else _lib.METRIC_IDS[metric]
+        h = C.c_void_p()
+        if self.metric in (_lib.EUCLIDEAN, _lib.COSINE):
+            X = np.asarray(X)
+            if X.ndim != 2:
+                raise ValueError("dense metrics need a 2-D array, got shape %r" % (X.shape,))
+            if X.dtype == np.float32:
+                Xc, dt = as_c(X, np.float32), _lib.F32
+            else:
+                Xc, dt = as_c(X, np.float64), _lib.F64
+            check(L.annb_dataset_dense(ctx.handle, ptr(Xc), Xc.shape[0], Xc.shape[1], dt, 0,
+                                       C.byref(h)))
+            self.n = Xc.shape[0]
+        elif self.metric == _lib.LEVENSHTEIN:
+            chars, offs = pack_strings(X)
+            check(L.annb_dataset_strings(ctx.handle, ptr(chars), ptr(offs), len(offs) - 1,
+                                         C.byref(h)))
+            self.n = len(offs) - 1
+        elif self.metric == _lib.WASSERSTEIN1D:
+            X = np.asarray(X)
+            if X.ndim != 2:
+                raise ValueError("wasserstein needs a 2-D array of histograms")
+            if cost_matrix is not None:
+                M = np.asarray(cost_matrix, dtype=np.float64)
+                nb = X.shape[1]
+                ref = np.abs(np.arange(nb)[:, None] - np.arange(nb)[None, :])
+                if M.shape != (nb, nb) or not np.array_equal(M, ref):
+                    raise NotImplementedError(
+                        "device 'wasserstein' implements the 1-D ground cost |a-b| only "
+                        "(annchor/utils.py:75-86 with a general cost matrix is exact OT by network "
+                        "simplex, which is not on the device path); no CPU fallback is provided")
+            if X.dtype == np.uint8:
+                Xc, dt = as_c(X, np.uint8), _lib.U8
+            elif X.dtype == np.float32:
+                Xc, dt = as_c(X, np.float32), _lib.F32
+            else:
+                Xc, dt = as_c(X, np.float64), _lib.F64
+            check(L.annb_dataset_hist(ctx.handle, ptr(Xc), Xc.shape[0], Xc.shape[1], dt, C.byref(h)))
+            self.n = Xc.shape[0]
+        else:
+            raise ValueError("unknown metric %r" % (metric,))
+        self.handle = h
+
+    def pair_dists(self, IJ):
+        """out[p] = metric(X[i_p], X[j_p]) -- the get_exact_ijs contract (annchor/utils.py:110-177)."""
+        IJ = as_c(IJ, np.int64).reshape(-1, 2)
+        out = np.empty(IJ.shape[0], dtype=np.float64)
+        check(self._L.annb_pair_dists(self.ctx.handle, self.handle, self.metric, ptr(IJ), IJ.shape[0],
+                                      ptr(out)))
+        return out
+
+    def maxmin_anchors(self, n_anchors, first):
+        """MaxMinAnchorPicker core (annchor/pickers.py:18-52) -> (A int64[na], D float64 (n, na))."""
+        A = np.empty(n_anchors, dtype=np.int64)
+        D = np.empty((self.n, n_anchors), dtype=np.float64)
+        check(self._L.annb_maxmin_anchors(self.ctx.handle, self.handle, self.metric, n_anchors,
+                                          int(first), ptr(A), ptr(D)))
+        return A, D
+
+    def anchor_dists(self, A):
+        A = as_c(A, np.int64)
+        D = np.empty((self.n, A.shape[0]), dtype=np.float64)
+        check(self._L.annb_anchor_dists(self.ctx.handle, self.handle, self.metric, ptr(A), A.shape[0],
+                                        ptr(D)))
+        return D
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self._L.annb_dataset_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class GpuExactIJs:
+    """Drop-in for the reference's ``get_exact_ijs(f, X, IJ)`` plug (annchor/annchor.py:77-82,
+    doc/parallelisation.rst:14-32) that evaluates a bundled metric on the B200.  ``f`` is ignored
+    (the metric is fixed at construction); X is uploaded once and cached by identity."""
+
+    def __init__(self, metric, ctx=None, cost_matrix=None):
+        self.metric = metric
+        self.ctx = ctx or default_context()
+        self.cost_matrix = cost_matrix
+        self._cache = None
+
+    def dataset(self, X):
+        if self._cache is None or self._cache[0] is not X:
+            self._cache = (X, Dataset(self.ctx, X, self.metric, self.cost_matrix))
+        return self._cache[1]
+
+    def __call__(self, f, X, IJ):
+        return self.dataset(X).pair_dists(IJ)

@@ -1,0 +1,69 @@
+"""Stage-operator parity: the explicit-list CUDA operators (C ABI) vs vectors produced by the
+reference's own numba functions (tests/golden/kat.npz, euclid_small.npz) and vs the oracle."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def test_bounds_dad_update_probs_leaf_vectors(gpu_ctx):
+    from annchor_b200 import ops
+    k = load_golden("kat")
+    assert np.array_equal(ops.get_bounds_njit_ijs(k["leaf_IJ"], k["leaf_D"], gpu_ctx), k["leaf_bounds"])
+    assert np.array_equal(ops.get_dad_ijs(k["leaf_IJ"], k["leaf_D"], gpu_ctx), k["leaf_dad"])
+    got = ops.update_bounds(k["leaf_IJ"], k["ub_kptr"], k["ub_kids"], k["ub_kds"], gpu_ctx)
+    assert np.array_equal(got, k["ub_out"])
+    errs = np.split(k["pr_errs"], np.cumsum(k["pr_len"])[:-1])
+    assert np.array_equal(ops.get_probs(k["pr_p"], k["pr_lab"], errs, gpu_ctx), k["pr_out"])
+
+
+def test_stage_chain_on_reference_capture(gpu_ctx):
+    """features -> predict/clip -> labels -> thresh -> get_nn on the arrays the unmodified
+    reference produced for the euclid_small config."""
+    from annchor_b200 import ops
+    import oracle.pipeline as P
+    from oracle import OracleAnnchor
+    g = load_golden("euclid_small")
+    IJs = g["IJs"].astype(np.int64)
+    f0 = g["features0"]
+    assert np.array_equal(ops.get_bounds_njit_ijs(IJs, g["D"], gpu_ctx), f0[:, :2])
+    assert np.array_equal(ops.get_dad_ijs(IJs, g["D"], gpu_ctx), f0[:, 2])
+    raw, clp = ops.predict_stratified(f0, g["sample_bins0"], g["coef0"], g["icpt0"], gpu_ctx)
+    np.testing.assert_allclose(clp, g["pred0"], rtol=1e-12, atol=1e-12)
+    assert np.array_equal(ops.error_labels(f0[:, 2], g["sample_bins0"], gpu_ctx), g["labels0"])
+    # row structure from the oracle (same IJs as the reference: checked in test_oracle)
+    na, nn, ns, pw, seed, niters = g["params"]
+    o = OracleAnnchor(g["X"], "euclidean", n_anchors=int(na), n_neighbors=int(nn), n_samples=int(ns),
+                      p_work=float(pw))
+    o.get_anchors(); o.get_locality()
+    assert np.array_equal(o.IJs, IJs)
+    th = ops.row_kth(g["RA_pre0"], o.row_ptr, o.row_pairs, int(nn), gpu_ctx)
+    assert np.array_equal(th, g["thresh0"])
+    th1 = ops.row_kth(g["RA_pre1"], o.row_ptr, o.row_pairs, int(nn), gpu_ctx)
+    assert np.array_equal(th1, g["thresh1"])
+    # final graph from the oracle's end state
+    o = OracleAnnchor(g["X"], "euclidean", n_anchors=int(na), n_neighbors=int(nn), n_samples=int(ns),
+                      p_work=float(pw)).fit()
+    ngi, ngd = ops.get_nn(o.nx, int(nn), o.RefineApprox, o.IJs, o.row_ptr, o.row_pairs,
+                          o.not_computed_mask, gpu_ctx)
+    assert np.array_equal(ngd, g["ng_dist"][:, 1:])
+    assert np.array_equal(ngi, g["ng_idx"][:, 1:])
+
+
+def test_row_kth_and_get_nn_edge_cases(gpu_ctx):
+    from annchor_b200 import ops
+    import oracle.pipeline as P
+    rng = np.random.default_rng(0)
+    nx = 50
+    lens = rng.integers(1, 400, size=nx)
+    lens[3] = 1
+    row_ptr = np.zeros(nx + 1, dtype=np.int64); np.cumsum(lens, out=row_ptr[1:])
+    P_ = 3000
+    row_pairs = rng.integers(0, P_, size=row_ptr[-1]).astype(np.int64)
+    RA = np.round(rng.normal(size=P_), 1)  # heavy ties, negative values
+    RA[:10] = -1.0
+    for k in (0, 5, 16):
+        assert np.array_equal(ops.row_kth(RA, row_ptr, row_pairs, k, gpu_ctx),
+                              P.row_kth(RA, row_ptr, row_pairs, k))
