@@ -48,7 +48,11 @@ def test_stage_chain_on_reference_capture(gpu_ctx):
                       p_work=float(pw)).fit()
     ngi, ngd = ops.get_nn(o.nx, int(nn), o.RefineApprox, o.IJs, o.row_ptr, o.row_pairs,
                           o.not_computed_mask, gpu_ctx)
-    assert np.array_equal(ngd, g["ng_dist"][:, 1:])
+    # bit-identical to the oracle on identical inputs; the reference capture differs from the
+    # oracle state only by float64 rounding of D (~1e-15)
+    assert np.array_equal(ngd, o.neighbor_graph[1][:, 1:])
+    assert np.array_equal(ngi, o.neighbor_graph[0][:, 1:])
+    np.testing.assert_allclose(ngd, g["ng_dist"][:, 1:], rtol=1e-12, atol=1e-12)
     assert np.array_equal(ngi, g["ng_idx"][:, 1:])
 
 
