@@ -1,0 +1,343 @@
+"""``Annchor(X, distance, ...).fit()`` / ``.neighbor_graph`` on the B200 -- the host-side mirror
+of annchor/annchor.py:21-623 over the streaming device index (include/annb.h, annb_index_*).
+
+Same constructor keywords, same stage order, same attribute names after ``fit()``
+(``neighbor_graph``, ``A``, ``D``, ``evals``, ``n_samples``, ``p_work`` ...).  What differs, by
+design, is that nothing Theta(N^2) is materialised: ``IJs``, ``features``, ``RefineApprox`` and
+``not_computed_mask`` do not exist; the plug-ins see the protocols in ``annchor_b200.plugins``.
+"""
+import ctypes as C
+import time
+from collections import Counter
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, ptr, as_c
+from .core import Dataset, GpuExactIJs, default_context
+from . import plugins
+from .plugins import (FEATURE_NAMES, NothingToSample, MaxMinAnchorPicker, SimpleStratifiedSampler,
+                      SimpleStratifiedLinearRegression, SimpleStratifiedErrorRegression,
+                      regression_device_spec, error_device_spec)
+
+
+class Index:
+    """Thin wrapper over annb_index_* (one per fit)."""
+
+    def __init__(self, ctx, dataset, n_anchors, n_neighbors, locality, loc_thresh, loc_min,
+                 is_metric=True, rank=0, world=1):
+        self._L = _lib.load()
+        self.ctx = ctx
+        self.dataset = dataset
+        self.n = dataset.n
+        self.na = n_anchors
+        self.nn = n_neighbors
+        p = _lib.IndexParams(n_anchors, n_neighbors, locality, loc_thresh, int(loc_min),
+                             1 if is_metric else 0, rank, world)
+        h = C.c_void_p()
+        check(self._L.annb_index_create(ctx.handle, dataset.handle, dataset.metric, C.byref(p), C.byref(h)))
+        self.handle = h
+        self._n_nc = None
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self._L.annb_index_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def maxmin(self, first):
+        A = np.empty(self.na, dtype=np.int64)
+        check(self._L.annb_index_maxmin(self.handle, int(first), ptr(A)))
+        return A
+
+    def set_anchors(self, A, D):
+        A = as_c(A, np.int64)
+        D = as_c(D, np.float64)
+        if D.shape != (self.n, self.na):
+            raise ValueError("D must have shape (nx, n_anchors) = %r, got %r" % ((self.n, self.na), D.shape))
+        check(self._L.annb_index_set_anchors(self.handle, ptr(A), A.shape[0], ptr(D)))
+
+    def get_D(self):
+        D = np.empty((self.n, self.na), dtype=np.float64)
+        check(self._L.annb_index_get_D(self.handle, ptr(D)))
+        return D
+
+    def locality(self):
+        nc, nr = C.c_int64(), C.c_int64()
+        check(self._L.annb_index_locality(self.handle, C.byref(nc), C.byref(nr)))
+        return nc.value, nr.value
+
+    def sample_pool(self, seed, max_pool):
+        """-> (n_pool, n_not_computed, exact)"""
+        n, nc, ex = C.c_int64(), C.c_int64(), C.c_int()
+        check(self._L.annb_index_sample_pool(self.handle, int(seed) & 0xFFFFFFFFFFFFFFFF, int(max_pool),
+                                             C.byref(n), C.byref(nc), C.byref(ex)))
+        self._n_pool = n.value
+        return n.value, nc.value, bool(ex.value)
+
+    def get_pool(self):
+        ij = np.empty((self._n_pool, 2), dtype=np.int64)
+        dad = np.empty(self._n_pool, dtype=np.float64)
+        check(self._L.annb_index_get_pool(self.handle, ptr(ij), ptr(dad)))
+        return ij, dad
+
+    def pair_features(self, ij):
+        ij = as_c(ij, np.int64).reshape(-1, 2)
+        feat = np.empty((ij.shape[0], 3), dtype=np.float64)
+        check(self._L.annb_index_pair_features(self.handle, ptr(ij), ij.shape[0], ptr(feat)))
+        return feat
+
+    def add_known(self, ij, d):
+        ij, d = as_c(ij, np.int64).reshape(-1, 2), as_c(d, np.float64)
+        check(self._L.annb_index_add_known(self.handle, ptr(ij), ptr(d), ij.shape[0]))
+
+    def eval_pairs(self, ij):
+        ij = as_c(ij, np.int64).reshape(-1, 2)
+        d = np.empty(ij.shape[0], dtype=np.float64)
+        check(self._L.annb_index_eval_pairs(self.handle, ptr(ij), ij.shape[0], ptr(d)))
+        return d
+
+    def set_model(self, bins, coef, icpt, errs=None, eptr=None):
+        bins, coef, icpt = as_c(bins, np.float64), as_c(coef, np.float64), as_c(icpt, np.float64)
+        if errs is not None:
+            errs, eptr = as_c(errs, np.float64), as_c(eptr, np.int64)
+        check(self._L.annb_index_set_model(self.handle, ptr(bins), ptr(coef), ptr(icpt), bins.shape[0] - 1,
+                                           ptr(errs), ptr(eptr)))
+
+    def row_thresh(self):
+        th = np.empty(self.n, dtype=np.float64)
+        check(self._L.annb_index_row_thresh(self.handle, ptr(th)))
+        return th
+
+    def guarantee_nmin(self, nmin):
+        nf = C.c_int64()
+        check(self._L.annb_index_guarantee_nmin(self.handle, int(nmin), C.byref(nf)))
+        return nf.value
+
+    def select(self, n_refine, lookahead):
+        a, b = C.c_int64(), C.c_int64()
+        check(self._L.annb_index_select(self.handle, int(n_refine), int(lookahead), C.byref(a), C.byref(b)))
+        self._sel = (a.value, b.value)
+        return a.value, b.value
+
+    def get_selected(self):
+        ns, nx = self._sel
+        s, x = np.empty((ns, 2), dtype=np.int64), np.empty((nx, 2), dtype=np.int64)
+        check(self._L.annb_index_get_selected(self.handle, ptr(s), ptr(x)))
+        return s, x
+
+    def refine_selected(self):
+        n = C.c_int64()
+        check(self._L.annb_index_refine_selected(self.handle, C.byref(n)))
+        return n.value
+
+    def update_bounds(self):
+        n = C.c_int64()
+        check(self._L.annb_index_update_bounds(self.handle, C.byref(n)))
+        return n.value
+
+    def neighbor_graph(self):
+        idx = np.empty((self.n, self.nn), dtype=np.int64)
+        dist = np.empty((self.n, self.nn), dtype=np.float64)
+        check(self._L.annb_index_neighbor_graph(self.handle, ptr(idx), ptr(dist)))
+        return idx, dist
+
+    def stats(self):
+        out = np.zeros(8, dtype=np.int64)
+        check(self._L.annb_index_stats(self.handle, ptr(out), 8))
+        return dict(zip(["pairs_swept", "n_known", "n_tight", "sweeps", "n_candidates", "hash_capacity",
+                         "n_anchor_pairs", "n_not_computed"], out.tolist()))
+
+    def last_sweep(self):
+        ms, pairs = C.c_float(), C.c_int64()
+        check(self._L.annb_index_last_sweep(self.handle, C.byref(ms), C.byref(pairs)))
+        return ms.value, pairs.value
+
+
+class Annchor:
+    """Quickly computes the approximate k-NN graph for slow metrics -- on a B200.
+
+    Parameters are those of the reference class (annchor/annchor.py:27-88).  ``func`` must be one
+    of the bundled metric names ('euclidean', 'cosine', 'levenshtein', 'wasserstein' with a 1-D
+    ``cost_matrix``): arbitrary Python callables cannot run on the device and there is no CPU
+    fallback.  ``backend`` and ``get_exact_ijs`` are accepted for signature compatibility;
+    the metric is always evaluated by the CUDA kernels.
+    """
+
+    def __init__(self, X, func, func_kwargs=None, n_anchors=20, n_neighbors=15, n_samples=5000,
+                 p_work=0.1, anchor_picker=None, sampler=None, regression=None, error_predictor=None,
+                 random_seed=42, locality=5, loc_thresh=1, loc_min=None, verbose=False, is_metric=True,
+                 get_exact_ijs=None, backend="loky", niters=2, lookahead=5, device=0, ctx=None,
+                 _dataset=None):
+        if not isinstance(func, str):
+            raise NotImplementedError(
+                "annchor_b200 evaluates metrics on the GPU; pass one of 'euclidean', 'cosine', "
+                "'levenshtein', 'wasserstein' (got a callable).  There is no CPU fallback.")
+        if func not in _lib.METRIC_IDS:
+            raise AssertionError("Error: The string must be one of %s" % sorted(_lib.METRIC_IDS))
+        cost = None
+        if func == "wasserstein":
+            assert func_kwargs is not None and "cost_matrix" in func_kwargs, \
+                "Error: wassetstein metric requires cost_function kwarg"
+            cost = func_kwargs["cost_matrix"]
+        assert backend in ["loky", "multiprocessing"]
+        self.X = X
+        self.nx = len(X)
+        self.N = (self.nx * (self.nx - 1)) // 2
+        self.f = func
+        self.evals = 0
+        self.n_anchors = n_anchors
+        self.na = int(np.sum([self.nx - j for j in range(1, self.n_anchors + 1)]))
+        self.n_neighbors = n_neighbors
+        self.p_work = p_work
+        self.n_samples = n_samples
+        # annchor/annchor.py:132-148
+        if self.p_work > 1:
+            print("Warning: p_work should not exceed 1.  Setting it to 1.")
+            self.p_work = 1.0
+        min_p_work = (2 * (self.na + self.n_samples) + 1) / self.N
+        min_p_work = 1 if min_p_work > 1 else min_p_work
+        if self.p_work < min_p_work:
+            print("Warning: Too many anchors/samples for specified p_work.")
+            print("Increasing p_work to %5.3f." % min_p_work)
+            self.p_work = min_p_work
+        if self.p_work > 0.75:
+            print("Warning: High Value of p_work.")
+            print("Think about decreasing n_anchors or n_samples, or using BruteForce.")
+        self.anchor_picker = anchor_picker or MaxMinAnchorPicker()
+        self.sampler = sampler or SimpleStratifiedSampler()
+        self.regression = regression or SimpleStratifiedLinearRegression()
+        self.error_predictor = error_predictor or SimpleStratifiedErrorRegression()
+        if not hasattr(self.sampler, "sample_index"):
+            raise NotImplementedError(
+                "samplers must implement sample_index(ann) (see annchor_b200.plugins): the reference "
+                "protocol sample(features, ...) needs the materialised Theta(N^2) feature array")
+        self.random_seed = random_seed
+        self.verbose = verbose
+        self.locality = locality
+        self.loc_thresh = loc_thresh
+        self.loc_min = 10 * self.n_neighbors if loc_min is None else loc_min
+        self.loc_min = int(np.clip(self.loc_min, 0, self.nx - 1))
+        self.is_metric = is_metric
+        self.niters = niters
+        self.lookahead = lookahead
+        self.backend = backend
+        self.feature_names = list(FEATURE_NAMES)
+        self.ctx = ctx or default_context(device)
+        # _dataset: an already-uploaded annchor_b200.Dataset of X (skips the host-to-device copy)
+        self._dataset = _dataset if _dataset is not None else Dataset(self.ctx, X, func, cost_matrix=cost)
+        self._plug = GpuExactIJs(func, self.ctx, cost)
+        self._plug._cache = (X, self._dataset)
+        self.get_exact_ijs = self._plug  # same call contract as annchor/annchor.py:77-82
+        self._index = Index(self.ctx, self._dataset, n_anchors, n_neighbors, locality, loc_thresh,
+                            self.loc_min, is_metric)
+        self._D = None
+        self.stage_times = {}
+
+    # -- stage 1 -----------------------------------------------------------------------------
+    def get_anchors(self):
+        A, D, evals = self.anchor_picker.get_anchors(self)
+        self.A = np.asarray(A)
+        if D is not None:  # host picker (reference protocol): hand its distances to the index
+            self._index.set_anchors(self.A.astype(np.int64) if self.A.size else np.zeros(0, np.int64),
+                                    np.asarray(D, dtype=np.float64))
+        self.evals += evals
+
+    @property
+    def D(self):
+        if self._D is None:
+            self._D = self._index.get_D()
+        return self._D
+
+    def get_locality(self):
+        self.n_candidates, self.n_relaxed = self._index.locality()
+
+    # -- sample / model ----------------------------------------------------------------------
+    def get_sample(self):
+        ijs, feats, bins = self.sampler.sample_index(self)
+        self.sample_ijs = ijs
+        self.sample_bins = bins
+        self.n_samples = ijs.shape[0]
+        self.sample_features = np.hstack([feats, np.zeros((feats.shape[0], 1))])
+        self.sample_y = self._index.eval_pairs(ijs)  # evaluates the metric and marks the pairs computed
+        self.evals += self.sample_y.shape[0]
+
+    def fit_predict_regression(self):
+        self.regression.fit(self.sample_features, self.feature_names, self.sample_y,
+                            sample_bins=self.sample_bins)
+        self.sample_predict = self.regression.predict(self.sample_features, self.feature_names)
+
+    def fit_predict_errors(self):
+        self.error_predictor.fit(self.sample_features, self.feature_names,
+                                 self.sample_y - self.sample_predict, sample_bins=self.sample_bins)
+        bins, coef, icpt = regression_device_spec(self.regression, self.feature_names)
+        errs, eptr = error_device_spec(self.error_predictor)
+        self._index.set_model(bins, coef, icpt, errs, eptr)
+
+    # -- select / refine ---------------------------------------------------------------------
+    def select_refine_candidate_pairs(self, w=0.5, it=0):
+        nn = self.n_neighbors
+        if it == 0:
+            self.n_forced = self._index.guarantee_nmin(3 * nn // 2)  # also computes thresh
+        else:
+            self._index.row_thresh()
+        n_refine = int((self.p_work * self.N - self.na - self.n_samples) * w) + 1
+        n_refine = 0 if n_refine < 0 else n_refine
+        self.n_refine = n_refine
+        self._index.select(n_refine, self.lookahead)
+        self.evals += self._index.refine_selected()
+
+    def update_anchor_points(self):
+        self.n_tightened = self._index.update_bounds()
+
+    def get_ann(self):
+        self.neighbor_graph = self._index.neighbor_graph()
+
+    def fit(self):
+        """Computes the approx nearest neighbour graph (annchor/annchor.py:532-623)."""
+        origin = time.time()
+
+        def stage(name, fn, *a, **k):
+            t = time.time()
+            r = fn(*a, **k)
+            self.ctx.sync()
+            dt = time.time() - t
+            self.stage_times[name] = self.stage_times.get(name, 0.0) + dt
+            if self.verbose:
+                print("%40s: %6.3f | %6.3f" % (name, dt, time.time() - origin))
+            return r
+
+        stage("get_anchors", self.get_anchors)
+        stage("get_locality", self.get_locality)
+        niters = self.niters
+        for it in range(niters):
+            try:
+                stage("get_sample", self.get_sample)
+            except NothingToSample as err:
+                if it == 0:
+                    raise ValueError("Sampler raised NothingToSample on first iteration.") from err
+                print("Warning: main loop terminated early with nothing left to sample.")
+                break
+            stage("fit_predict_regression", self.fit_predict_regression)
+            stage("fit_predict_errors", self.fit_predict_errors)
+            stage("select_refine_candidate_pairs", self.select_refine_candidate_pairs, w=1 / niters, it=it)
+            if it < niters - 1:
+                stage("update_anchor_points", self.update_anchor_points)
+        stage("get_ann", self.get_ann)
+        return self
+
+
+def compare_neighbor_graphs(nng_1, nng_2, n_neighbors):
+    """Tie-aware number of incorrect NN pairs (annchor/annchor.py:1026-1066): per row the multiset
+    difference of the first n_neighbors distances rounded to 3 decimals."""
+    err = 0
+    for ix in range(nng_1[0].shape[0]):
+        a = Counter(np.round(nng_1[1][ix][:n_neighbors], 3).astype(np.float32))
+        b = Counter(np.round(nng_2[1][ix][:n_neighbors], 3).astype(np.float32))
+        err += len(a - b)
+    return int(err)

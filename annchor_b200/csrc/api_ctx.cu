@@ -7,6 +7,7 @@ namespace annb {
 
 static thread_local char g_err[1024] = "";
 int64_t g_launches = 0;
+bool g_debug_sync = getenv("ANNB_DEBUG_SYNC") != nullptr;
 
 void set_error(const char *fmt, ...)
 {
@@ -94,6 +95,8 @@ ANNB_API int annb_ctx_create(int device, annb_ctx **out)
     ANNB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     ANNB_CUDA(cudaEventCreate(&c->ev0));
     ANNB_CUDA(cudaEventCreate(&c->ev1));
+    ANNB_CUDA(cudaEventCreate(&c->uev0));
+    ANNB_CUDA(cudaEventCreate(&c->uev1));
     *out = c;
     return ANNB_OK;
 }
@@ -108,6 +111,8 @@ ANNB_API int annb_ctx_destroy(annb_ctx *c)
     if (c->pinned) cudaFreeHost(c->pinned);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
+    cudaEventDestroy(c->uev0);
+    cudaEventDestroy(c->uev1);
     cudaStreamDestroy(c->stream);
     delete c;
     return ANNB_OK;
@@ -130,16 +135,16 @@ ANNB_API int annb_ctx_stream(annb_ctx *c, uint64_t *stream)
 ANNB_API int annb_timer_start(annb_ctx *c)
 {
     ANNB_REQUIRE(c != nullptr, ANNB_EINVAL, "ctx is NULL");
-    ANNB_CUDA(cudaEventRecord(c->ev0, c->stream));
+    ANNB_CUDA(cudaEventRecord(c->uev0, c->stream));
     return ANNB_OK;
 }
 
 ANNB_API int annb_timer_stop(annb_ctx *c, float *ms)
 {
     ANNB_REQUIRE(c && ms, ANNB_EINVAL, "NULL argument");
-    ANNB_CUDA(cudaEventRecord(c->ev1, c->stream));
-    ANNB_CUDA(cudaEventSynchronize(c->ev1));
-    ANNB_CUDA(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    ANNB_CUDA(cudaEventRecord(c->uev1, c->stream));
+    ANNB_CUDA(cudaEventSynchronize(c->uev1));
+    ANNB_CUDA(cudaEventElapsedTime(ms, c->uev0, c->uev1));
     return ANNB_OK;
 }
 

@@ -20,6 +20,7 @@ constexpr int kMaxAnchors = 64;
 
 void set_error(const char *fmt, ...);
 extern int64_t g_launches;
+extern bool g_debug_sync;
 
 #define ANNB_CUDA(expr)                                                                  \
     do {                                                                                 \
@@ -51,6 +52,14 @@ extern int64_t g_launches;
         kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);               \
         ++annb::g_launches;                                                       \
         ANNB_CUDA(cudaGetLastError());                                            \
+        if (annb::g_debug_sync) { /* ANNB_DEBUG_SYNC=1: localise asynchronous faults */ \
+            cudaError_t _s = cudaStreamSynchronize(stream);                       \
+            if (_s != cudaSuccess) {                                              \
+                annb::set_error("%s:%d: kernel %s failed: %s", __FILE__, __LINE__, #kernel, \
+                                cudaGetErrorString(_s));                          \
+                return ANNB_ECUDA;                                                \
+            }                                                                     \
+        }                                                                         \
     } while (0)
 
 // Device buffer with grow-only reuse (avoids cudaMalloc on the hot path).
@@ -92,7 +101,8 @@ struct DevBuf {
 struct annb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // internal per-sweep timing
+    cudaEvent_t uev0 = nullptr, uev1 = nullptr;  // annb_timer_start / stop
     int num_sms = annb::kNumSMs;
     size_t l2_bytes = 0;
     // scratch reused by the host-pointer entry points

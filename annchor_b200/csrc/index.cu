@@ -1,0 +1,1732 @@
+// index.cu -- the streaming index: Annchor.fit() (annchor/annchor.py:532-623) without any
+// Theta(N^2) array.  Host-side orchestration of the sweeps in sweep_*.cu plus the small kernels
+// around them (point metadata, candidate counting, known-pair hash map, selection, top-k).
+#include <algorithm>
+#include <cmath>
+#include <unordered_map>
+#include <unordered_set>
+
+#include "sweep.cuh"
+#include "sweep_args.cuh"
+
+namespace annb {
+
+// ---- declarations from the other translation units -------------------------------------------
+int maxmin_device(annb_ctx *c, const annb_dataset *ds, int metric, int na, int32_t *A_dev,
+                  double *Dam, DevBuf &scratch);
+int transpose_D(annb_ctx *c, const double *Dam, int64_t n, int na, double *Dpm);
+int pair_dists_f32_perm(annb_ctx *c, const annb_dataset *ds, int metric, const int32_t *I,
+                        const int32_t *J, const int32_t *perm, int64_t n, float *out);
+
+// ---------------------------------------------------------------------------------------------
+// small kernels
+// ---------------------------------------------------------------------------------------------
+
+// D (na, n) float64 anchor-major -> float32 (na, npad) + per-point metadata
+__global__ void build_meta_kernel(const double *__restrict__ D64, int64_t n, int64_t npad, int na,
+                                  int locality, int loc_thresh, float *__restrict__ D32,
+                                  PointMeta *__restrict__ meta)
+{
+    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < npad;
+         j += (int64_t)gridDim.x * blockDim.x) {
+        PointMeta m;
+        m.amask = 0;
+        m.cA = 0;
+        m.loc_t = (int8_t)loc_thresh;
+        m.slot = -1;
+        m.pad = 0;
+        if (j < n) {
+            double best = INFINITY;
+            for (int a = 0; a < na; ++a) {
+                const double v = D64[(int64_t)a * n + j];
+                D32[(int64_t)a * npad + j] = (float)v;
+                if (v < best) {  // first minimum (np.argmin)
+                    best = v;
+                    m.cA = a;
+                }
+            }
+            // `locality` nearest anchors, ties to the lower anchor index (stable argsort, annchor.py:235)
+            for (int l = 0; l < locality && l < na; ++l) {
+                double bv = INFINITY;
+                int ba = -1;
+                for (int a = 0; a < na; ++a) {
+                    if ((m.amask >> a) & 1ull) continue;
+                    const double v = D64[(int64_t)a * n + j];
+                    if (ba < 0 || v < bv) {
+                        bv = v;
+                        ba = a;
+                    }
+                }
+                m.amask |= 1ull << ba;
+            }
+        } else {
+            for (int a = 0; a < na; ++a) D32[(int64_t)a * npad + j] = 0.0f;
+            m.loc_t = 127;  // padding rows are never candidates
+        }
+        meta[j] = m;
+    }
+}
+
+__global__ void set_slots_kernel(const int32_t *__restrict__ A, int nA, PointMeta *__restrict__ meta)
+{
+    // serial so that duplicated anchors resolve like the reference's loop (last one wins)
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (int k = 0; k < nA; ++k) meta[A[k]].slot = (int8_t)k;
+}
+
+// per row: histogram of min(shared-anchor count, loc_thresh) over all points (get_check,
+// utils.py:470-473), or (pass 2) the number of candidates under the relaxed thresholds
+__global__ void __launch_bounds__(256)
+locality_count_kernel(const PointMeta *__restrict__ meta, int64_t n, int loc_thresh, int pass,
+                      int32_t *__restrict__ out /* pass 1: [n][8]; pass 2: [n] */)
+{
+    __shared__ uint64_t s_mask[1024];
+    __shared__ int8_t s_t[1024];
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const bool live = i < n;
+    const PointMeta mi = live ? meta[i] : PointMeta{0, 0, 127, -1, 0};
+    int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int64_t j0 = 0; j0 < n; j0 += 1024) {
+        __syncthreads();
+        for (int k = threadIdx.x; k < 1024; k += blockDim.x) {
+            const int64_t j = j0 + k;
+            s_mask[k] = j < n ? meta[j].amask : 0ull;
+            s_t[k] = j < n ? meta[j].loc_t : 127;
+        }
+        __syncthreads();
+        const int lim = (int)min((int64_t)1024, n - j0);
+        for (int k = 0; k < lim; ++k) {
+            const int c = __popcll(mi.amask & s_mask[k]);
+            if (pass == 1) {
+                const int cc = c < loc_thresh ? c : loc_thresh;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) cnt[q] += (cc == q);
+            } else {
+                const int t = mi.loc_t < s_t[k] ? mi.loc_t : s_t[k];
+                cnt[0] += (c >= t) && (j0 + k != i);
+            }
+        }
+    }
+    if (!live) return;
+    if (pass == 1) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) out[i * 8 + q] = cnt[q];
+    } else {
+        out[i] = cnt[0];
+    }
+}
+
+__global__ void set_loc_t_kernel(PointMeta *__restrict__ meta, const int8_t *__restrict__ t, int64_t n)
+{
+    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n;
+         j += (int64_t)gridDim.x * blockDim.x)
+        meta[j].loc_t = t[j];
+}
+
+__global__ void fill_u64_kernel(uint64_t *p, int64_t n, uint64_t v)
+{
+    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n;
+         j += (int64_t)gridDim.x * blockDim.x)
+        p[j] = v;
+}
+
+// insert / overwrite entries of the known-pair hash map and raise their flag bits
+__global__ void hash_insert_kernel(HashSlot *__restrict__ htab, uint64_t hmask,
+                                   uint32_t *__restrict__ bitmap, int T,
+                                   const int32_t *__restrict__ I, const int32_t *__restrict__ J,
+                                   const float *__restrict__ a, const float *__restrict__ b,
+                                   uint32_t kind, int64_t m)
+{
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < m;
+         p += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t i = (uint32_t)I[p], j = (uint32_t)J[p];
+        if (i == j) continue;
+        const uint32_t lo = i < j ? i : j, hi = i < j ? j : i;
+        const uint64_t key = pair_key(lo, hi);
+        const uint64_t stored = key | kind_bits(kind);
+        uint64_t h = mix64(key) & hmask;
+        for (;;) {
+            unsigned long long *kp = reinterpret_cast<unsigned long long *>(&htab[h].key);
+            const uint64_t prev = atomicCAS(kp, HKEY_EMPTY, stored);
+            if (prev == HKEY_EMPTY) {
+                htab[h].a = a ? a[p] : 0.0f;
+                htab[h].b = b ? b[p] : 0.0f;
+                break;
+            }
+            if ((prev & HKEY_MASK) == key) {
+                if (kind != KIND_KNOWN && kind_of(prev) == KIND_KNOWN) break;  // never downgrade
+                atomicExch(kp, stored);
+                htab[h].a = a ? a[p] : 0.0f;
+                htab[h].b = b ? b[p] : 0.0f;
+                break;
+            }
+            h = (h + 1) & hmask;
+        }
+        const int64_t t = tile_index((int)(lo >> 7), (int)(hi >> 7), T);
+        const int r = lo & 127, c = hi & 127;
+        atomicOr(&bitmap[t * BITMAP_WORDS + r * 4 + (c >> 5)], 1u << (c & 31));
+    }
+}
+
+__global__ void hash_rehash_kernel(const HashSlot *__restrict__ otab, uint64_t ocap,
+                                   HashSlot *__restrict__ htab, uint64_t hmask)
+{
+    for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s < ocap;
+         s += (uint64_t)gridDim.x * blockDim.x) {
+        const HashSlot e = otab[s];
+        if (e.key == HKEY_EMPTY) continue;
+        uint64_t h = mix64(e.key & HKEY_MASK) & hmask;
+        for (;;) {
+            const uint64_t prev = atomicCAS(reinterpret_cast<unsigned long long *>(&htab[h].key),
+                                            HKEY_EMPTY, e.key);
+            if (prev == HKEY_EMPTY) {
+                htab[h].a = e.a;
+                htab[h].b = e.b;
+                break;
+            }
+            h = (h + 1) & hmask;
+        }
+    }
+}
+
+// retire the transient FORCED marks after the iteration-0 selection (annchor.py:374-379 overwrites
+// every not-computed RefineApprox on the next iteration)
+__global__ void hash_retire_forced_kernel(HashSlot *__restrict__ htab, uint64_t cap)
+{
+    for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s < cap;
+         s += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t k = htab[s].key;
+        if (k != HKEY_EMPTY && kind_of(k) == KIND_FORCED) htab[s].key = k & HKEY_MASK;  // KIND_NONE
+    }
+}
+
+// number of anchors that are candidates of each point (those pairs are "computed" from the start,
+// annchor.py:286-301)
+__global__ void anchor_cand_kernel(const PointMeta *__restrict__ meta, int64_t n,
+                                   const int32_t *__restrict__ A, int nA, int32_t *__restrict__ out)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const PointMeta mi = meta[i];
+        int cnt = 0;
+        for (int k = 0; k < nA; ++k) {
+            const int a = A[k];
+            const PointMeta ma = meta[a];
+            if (a != i && ma.slot == k && __popcll(mi.amask & ma.amask) >= (mi.loc_t < ma.loc_t ? mi.loc_t : ma.loc_t))
+                ++cnt;
+        }
+        out[i] = cnt;
+    }
+}
+
+__global__ void split_ij32_kernel(const int64_t *__restrict__ ij, const double *__restrict__ d,
+                                  int64_t n, int32_t *__restrict__ I, int32_t *__restrict__ J,
+                                  float *__restrict__ df)
+{
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n;
+         p += (int64_t)gridDim.x * blockDim.x) {
+        I[p] = (int32_t)ij[2 * p];
+        J[p] = (int32_t)ij[2 * p + 1];
+        if (d) df[p] = (float)d[p];
+    }
+}
+
+// features [lb, ub, dad] of explicit pairs in the sweep's float32 arithmetic (sampler output)
+__global__ void pair_features_kernel(View V, const int32_t *__restrict__ I,
+                                     const int32_t *__restrict__ J, int64_t m,
+                                     float *__restrict__ feat /* (m,3) */)
+{
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < m;
+         p += (int64_t)gridDim.x * blockDim.x) {
+        const int i = I[p], j = J[p];
+        float lb = 0.0f, ub = INFINITY;
+        for (int a = 0; a < V.na; ++a) {
+            const float x = V.D32[(int64_t)a * V.npad + i], y = V.D32[(int64_t)a * V.npad + j];
+            lb = fmaxf(lb, fabsf(x - y));
+            ub = fminf(ub, x + y);
+        }
+        const PointMeta mi = V.meta[i], mj = V.meta[j];
+        const float dad = 0.5f * (V.D32[(int64_t)mj.cA * V.npad + i] + V.D32[(int64_t)mi.cA * V.npad + j]);
+        const uint32_t lo = i < j ? i : j, hi = i < j ? j : i;
+        float ta = 0.0f, tb = 0.0f;
+        if (hash_lookup(V, pair_key(lo, hi), ta, tb) == KIND_TIGHT) {
+            lb = fmaxf(lb, ta);
+            ub = fminf(ub, tb);
+        }
+        feat[3 * p] = lb;
+        feat[3 * p + 1] = ub;
+        feat[3 * p + 2] = dad;
+    }
+}
+
+// ---- selection over the emitted list -----------------------------------------------------------
+// digit histogram of the mixed pair keys at one level (deterministic tie-break at the cut)
+__global__ void tie_hist_kernel(const uint64_t *__restrict__ keys, const uint16_t *__restrict__ lvl,
+                                int64_t E, int level, uint64_t prefix, int shift /* bits below digit */,
+                                uint32_t *__restrict__ hist /* 65536 */)
+{
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < E;
+         p += (int64_t)gridDim.x * blockDim.x) {
+        if (lvl[p] != level) continue;
+        const uint64_t mk = mix64(keys[p]);
+        if (shift < 48 && (mk >> (shift + 16)) != prefix) continue;
+        atomicAdd(&hist[(mk >> shift) & 0xffff], 1u);
+    }
+}
+
+// selected: lvl > c1 or (lvl == c1 and mix <= thr1); next: not selected and (lvl > c2 or
+// (lvl == c2 and mix <= thr2))
+__global__ void partition_emitted_kernel(const uint64_t *__restrict__ keys,
+                                         const uint16_t *__restrict__ lvl, int64_t E, int c1,
+                                         uint64_t thr1, int c2, uint64_t thr2,
+                                         int32_t *__restrict__ sel_i, int32_t *__restrict__ sel_j,
+                                         int32_t *__restrict__ nxt_i, int32_t *__restrict__ nxt_j,
+                                         unsigned long long *__restrict__ cnt /* [0] sel, [1] next */,
+                                         int64_t cap_sel, int64_t cap_next)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t b0 = warp * 32; b0 < E; b0 += nwarps * 32) {  // warp-uniform trip count
+        const int64_t p = b0 + lane;
+        const bool live = p < E;
+        const int l = live ? lvl[p] : -1;
+        const uint64_t key = live ? keys[p] : 0ull;
+        const uint64_t mk = mix64(key);
+        const bool sel = live && (l > c1 || (l == c1 && mk <= thr1));
+        const bool nxt = live && !sel && (l > c2 || (l == c2 && mk <= thr2));
+        const unsigned ms = __ballot_sync(0xffffffffu, sel), mn = __ballot_sync(0xffffffffu, nxt);
+        unsigned long long bs = 0, bn = 0;
+        if (lane == 0) {
+            if (ms) bs = atomicAdd(&cnt[0], (unsigned long long)__popc(ms));
+            if (mn) bn = atomicAdd(&cnt[1], (unsigned long long)__popc(mn));
+        }
+        bs = __shfl_sync(0xffffffffu, bs, 0);
+        bn = __shfl_sync(0xffffffffu, bn, 0);
+        if (sel) {
+            const unsigned long long s = bs + __popc(ms & ((1u << lane) - 1));
+            if ((int64_t)s < cap_sel) {
+                sel_i[s] = (int32_t)(key >> 32);
+                sel_j[s] = (int32_t)(key & 0xffffffffu);
+            }
+        } else if (nxt) {
+            const unsigned long long s = bn + __popc(mn & ((1u << lane) - 1));
+            if ((int64_t)s < cap_next) {
+                nxt_i[s] = (int32_t)(key >> 32);
+                nxt_j[s] = (int32_t)(key & 0xffffffffu);
+            }
+        }
+    }
+}
+
+// ---- CSR of exactly-known pairs ---------------------------------------------------------------
+__global__ void known_degree_kernel(const HashSlot *__restrict__ htab, uint64_t cap,
+                                    int32_t *__restrict__ deg)
+{
+    for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s < cap;
+         s += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t k = htab[s].key;
+        if (k == HKEY_EMPTY || kind_of(k) != KIND_KNOWN) continue;
+        const uint64_t key = k & HKEY_MASK;
+        atomicAdd(&deg[(uint32_t)(key >> 32)], 1);
+        atomicAdd(&deg[(uint32_t)(key & 0xffffffffu)], 1);
+    }
+}
+
+// single-block exclusive scan (n up to a few million; one-off per iteration)
+__global__ void __launch_bounds__(1024) exclusive_scan_kernel(const int32_t *__restrict__ in,
+                                                              int64_t *__restrict__ out, int64_t n)
+{
+    __shared__ int64_t s_warp[32];
+    __shared__ int64_t s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int64_t base = 0; base < n; base += 1024) {
+        const int64_t idx = base + threadIdx.x;
+        int64_t v = idx < n ? in[idx] : 0;
+        int64_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int64_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) s_warp[w] = x;
+        __syncthreads();
+        if (w == 0) {
+            int64_t t = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int64_t y = __shfl_up_sync(0xffffffffu, t, o);
+                if (lane >= o) t += y;
+            }
+            s_warp[lane] = t;
+        }
+        __syncthreads();
+        const int64_t incl = x + (w > 0 ? s_warp[w - 1] : 0) + s_carry;
+        if (idx < n) out[idx] = incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[n] = s_carry;
+}
+
+__global__ void known_fill_kernel(const HashSlot *__restrict__ htab, uint64_t cap,
+                                  const int64_t *__restrict__ ptr, int32_t *__restrict__ cursor,
+                                  int32_t *__restrict__ ids, float *__restrict__ ds)
+{
+    for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s < cap;
+         s += (uint64_t)gridDim.x * blockDim.x) {
+        const HashSlot e = htab[s];
+        if (e.key == HKEY_EMPTY || kind_of(e.key) != KIND_KNOWN) continue;
+        const uint64_t key = e.key & HKEY_MASK;
+        const uint32_t i = (uint32_t)(key >> 32), j = (uint32_t)(key & 0xffffffffu);
+        const float d = e.a;
+        int64_t p = ptr[i] + atomicAdd(&cursor[i], 1);
+        ids[p] = (int32_t)j;
+        ds[p] = d;
+        p = ptr[j] + atomicAdd(&cursor[j], 1);
+        ids[p] = (int32_t)i;
+        ds[p] = d;
+    }
+}
+
+// sort every CSR row by id: bitonic network, one block per row, in shared memory when the
+// row fits (<= 4096 entries) else directly in global memory
+__global__ void __launch_bounds__(256)
+sort_rows_kernel(const int64_t *__restrict__ ptr, int64_t n, int32_t *__restrict__ ids,
+                 float *__restrict__ ds)
+{
+    __shared__ int32_t s_id[4096];
+    __shared__ float s_d[4096];
+    for (int64_t row = blockIdx.x; row < n; row += gridDim.x) {
+        const int64_t beg = ptr[row];
+        const int m = (int)(ptr[row + 1] - beg);
+        if (m <= 1) continue;
+        int P2 = 1;
+        while (P2 < m) P2 <<= 1;
+        const bool in_smem = P2 <= 4096;
+        __syncthreads();
+        if (in_smem) {
+            for (int k = threadIdx.x; k < P2; k += blockDim.x) {
+                s_id[k] = k < m ? ids[beg + k] : INT32_MAX;
+                s_d[k] = k < m ? ds[beg + k] : 0.0f;
+            }
+        }
+        __syncthreads();
+        for (int size = 2; size <= P2; size <<= 1)
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int k = threadIdx.x; k < P2 / 2; k += blockDim.x) {
+                    const int lo = 2 * k - (k & (stride - 1));
+                    const int hi = lo + stride;
+                    const bool up = (lo & size) == 0;
+                    if (in_smem) {
+                        const int32_t a = s_id[lo], b = s_id[hi];
+                        if ((a > b) == up) {
+                            s_id[lo] = b;
+                            s_id[hi] = a;
+                            const float t = s_d[lo];
+                            s_d[lo] = s_d[hi];
+                            s_d[hi] = t;
+                        }
+                    } else {
+                        const int32_t a = lo < m ? ids[beg + lo] : INT32_MAX;
+                        const int32_t b = hi < m ? ids[beg + hi] : INT32_MAX;
+                        if ((a > b) == up && lo < m) {
+                            // hi >= m can only hold padding, which never needs to move left of real data
+                            if (hi < m) {
+                                ids[beg + lo] = b;
+                                ids[beg + hi] = a;
+                                const float t = ds[beg + lo];
+                                ds[beg + lo] = ds[beg + hi];
+                                ds[beg + hi] = t;
+                            }
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        if (in_smem)
+            for (int k = threadIdx.x; k < m; k += blockDim.x) {
+                ids[beg + k] = s_id[k];
+                ds[beg + k] = s_d[k];
+            }
+    }
+}
+
+// update_bounds (utils.py:304-352) for the look-ahead pairs: one warp per pair; the shorter
+// list is streamed coalesced, each lane binary-searches the longer one.
+__global__ void __launch_bounds__(256)
+tighten_kernel(View V, const int64_t *__restrict__ ptr, const int32_t *__restrict__ ids,
+               const float *__restrict__ ds, const int32_t *__restrict__ I,
+               const int32_t *__restrict__ J, int64_t m, float *__restrict__ out_lb,
+               float *__restrict__ out_ub, uint8_t *__restrict__ improved)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t p = warp; p < m; p += nwarps) {
+        int i = I[p], j = J[p];
+        int64_t bi = ptr[i], bj = ptr[j];
+        int mi = (int)(ptr[i + 1] - bi), mj = (int)(ptr[j + 1] - bj);
+        if (mi > mj) {  // stream the shorter list
+            const int64_t tb = bi; bi = bj; bj = tb;
+            const int tm = mi; mi = mj; mj = tm;
+        }
+        float lb = 0.0f, ub = INFINITY;
+        for (int k = lane; k < mi; k += 32) {
+            const int32_t id = ids[bi + k];
+            int lo = 0, hi = mj;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (ids[bj + mid] < id) lo = mid + 1;
+                else hi = mid;
+            }
+            if (lo < mj && ids[bj + lo] == id) {
+                const float x = ds[bi + k], y = ds[bj + lo];
+                lb = fmaxf(lb, fabsf(x - y));
+                ub = fminf(ub, x + y);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lb = fmaxf(lb, __shfl_xor_sync(0xffffffffu, lb, o));
+            ub = fminf(ub, __shfl_xor_sync(0xffffffffu, ub, o));
+        }
+        if (lane == 0) {
+            // combine with what the pair already has (anchor bounds and any earlier tightening)
+            i = I[p];
+            j = J[p];
+            float l0 = 0.0f, u0 = INFINITY;
+            for (int a = 0; a < V.na; ++a) {
+                const float x = V.D32[(int64_t)a * V.npad + i], y = V.D32[(int64_t)a * V.npad + j];
+                l0 = fmaxf(l0, fabsf(x - y));
+                u0 = fminf(u0, x + y);
+            }
+            const uint32_t lo = i < j ? i : j, hi = i < j ? j : i;
+            float ta = 0.0f, tb = 0.0f;
+            if (hash_lookup(V, pair_key(lo, hi), ta, tb) == KIND_TIGHT) {
+                l0 = fmaxf(l0, ta);
+                u0 = fminf(u0, tb);
+            }
+            const bool imp = lb > l0 || ub < u0;
+            out_lb[p] = fmaxf(lb, l0);
+            out_ub[p] = fminf(ub, u0);
+            improved[p] = imp ? 1 : 0;
+        }
+    }
+}
+
+__global__ void compact_improved_kernel(const int32_t *__restrict__ I, const int32_t *__restrict__ J,
+                                        const float *__restrict__ lb, const float *__restrict__ ub,
+                                        const uint8_t *__restrict__ improved, int64_t m,
+                                        int32_t *__restrict__ oI, int32_t *__restrict__ oJ,
+                                        float *__restrict__ olb, float *__restrict__ oub,
+                                        unsigned long long *__restrict__ cnt)
+{
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < m;
+         p += (int64_t)gridDim.x * blockDim.x) {
+        if (!improved[p]) continue;
+        const unsigned long long s = atomicAdd(cnt, 1ull);
+        oI[s] = I[p];
+        oJ[s] = J[p];
+        olb[s] = lb[p];
+        oub[s] = ub[p];
+    }
+}
+
+// get_nn (utils.py:383-429) over the computed pairs of each row: CSR known entries + anchor
+// distances.  One block per row; nn-1 extract-min rounds ordered by (distance, neighbour id).
+__global__ void __launch_bounds__(256)
+neighbor_graph_kernel(View V, const double *__restrict__ D64, const int32_t *__restrict__ A, int nA,
+                      const int64_t *__restrict__ ptr, const int32_t *__restrict__ ids,
+                      const float *__restrict__ ds, int64_t *__restrict__ out_idx,
+                      double *__restrict__ out_d, int32_t *__restrict__ deficient)
+{
+    __shared__ double s_d[8];
+    __shared__ int s_id[8];
+    __shared__ double s_pd;
+    __shared__ int s_pid;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int nn = V.nn;
+    for (int64_t row = blockIdx.x; row < V.n; row += gridDim.x) {
+        const PointMeta mr = V.meta[row];
+        const int64_t beg = ptr[row];
+        const int mk = (int)(ptr[row + 1] - beg);
+        if (threadIdx.x == 0) {
+            s_pd = -INFINITY;
+            s_pid = -1;
+            out_idx[row * nn] = row;
+            out_d[row * nn] = 0.0;
+        }
+        __syncthreads();
+        for (int r = 0; r < nn - 1; ++r) {
+            const double pd = s_pd;
+            const int pid = s_pid;
+            double bd = INFINITY;
+            int bid = INT32_MAX;
+            auto offer = [&](double d, int id) {
+                const bool after = d > pd || (d == pd && id > pid);
+                if (after && (d < bd || (d == bd && id < bid))) {
+                    bd = d;
+                    bid = id;
+                }
+            };
+            for (int k = threadIdx.x; k < mk; k += blockDim.x) offer((double)ds[beg + k], ids[beg + k]);
+            if (mr.slot >= 0) {
+                // anchor row: every candidate pair is computed (annchor.py:288-289)
+                for (int64_t j = threadIdx.x; j < V.n; j += blockDim.x)
+                    if (j != row && is_candidate(mr, V.meta[j]))
+                        offer(D64[(int64_t)mr.slot * V.n + j], (int)j);
+            } else {
+                for (int k = threadIdx.x; k < nA; k += blockDim.x) {
+                    const int a = A[k];
+                    if (V.meta[a].slot == k && a != row && is_candidate(mr, V.meta[a]))
+                        offer(D64[(int64_t)k * V.n + row], a);
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double yd = __shfl_xor_sync(0xffffffffu, bd, o);
+                const int yi = __shfl_xor_sync(0xffffffffu, bid, o);
+                if (yd < bd || (yd == bd && yi < bid)) {
+                    bd = yd;
+                    bid = yi;
+                }
+            }
+            if (lane == 0) {
+                s_d[w] = bd;
+                s_id[w] = bid;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                for (int q = 1; q < 8; ++q)
+                    if (s_d[q] < bd || (s_d[q] == bd && s_id[q] < bid)) {
+                        bd = s_d[q];
+                        bid = s_id[q];
+                    }
+                s_pd = bd;
+                s_pid = bid;
+                if (bid == INT32_MAX) {
+                    out_idx[row * nn + 1 + r] = -1;
+                    out_d[row * nn + 1 + r] = INFINITY;
+                    atomicAdd(deficient, 1);
+                    s_pd = INFINITY;
+                } else {
+                    out_idx[row * nn + 1 + r] = bid;
+                    out_d[row * nn + 1 + r] = bd;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+}  // namespace annb
+
+using namespace annb;
+
+namespace annb {
+
+// mixed keys of the emitted entries at one level (ties at a selection cut)
+__global__ void compact_level_kernel(const uint64_t *__restrict__ keys, const uint16_t *__restrict__ lvl,
+                                     int64_t E, int level, uint64_t *__restrict__ out,
+                                     unsigned long long *__restrict__ cnt)
+{
+    // warp-uniform trip count: every ballot / shuffle below is executed by all 32 lanes
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t b0 = warp * 32; b0 < E; b0 += nwarps * 32) {
+        const int64_t p = b0 + lane;
+        const bool hit = p < E && lvl[p] == level;
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (!m) continue;
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(cnt, (unsigned long long)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (hit) out[base + __popc(m & ((1u << lane) - 1))] = mix64(keys[p]);
+    }
+}
+
+// 16-bit digit histogram of 64-bit keys that share `prefix` above the digit
+__global__ void digit_hist_kernel(const uint64_t *__restrict__ keys, int64_t m, uint64_t prefix, int shift,
+                                  uint32_t *__restrict__ hist /* 65536 */)
+{
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < m;
+         p += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t k = keys[p];
+        if (shift < 48 && (k >> (shift + 16)) != prefix) continue;
+        atomicAdd(&hist[(k >> shift) & 0xffff], 1u);
+    }
+}
+
+__global__ void max_f32_kernel(const float *__restrict__ x, int64_t n, unsigned int *__restrict__ out)
+{
+    float m = 0.0f;
+    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n;
+         j += (int64_t)gridDim.x * blockDim.x)
+        m = fmaxf(m, x[j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));  // non-negative floats order as uints
+}
+
+}  // namespace annb
+
+// ---------------------------------------------------------------------------------------------
+// the index object
+// ---------------------------------------------------------------------------------------------
+struct annb_index {
+    annb_ctx *ctx = nullptr;
+    const annb_dataset *ds = nullptr;
+    int metric = 0;
+    annb_index_params P;
+    int64_t n = 0, npad = 0;
+    int na = 0, T = 0;
+    int64_t NT = 0;  // upper-triangular tiles
+    bool have_anchors = false, have_locality = false, have_model = false, have_thresh = false;
+    bool has_forced = false;
+    std::vector<int32_t> A_host;
+    DevBuf A_dev, D64, D32, meta, scratch;
+    // known-pair store
+    DevBuf htab, bitmap;
+    uint64_t hcap = 0;
+    int64_t hcount_ub = 0;  // upper bound on occupied slots
+    // model
+    Model model;
+    std::vector<float> errs_host;
+    std::vector<uint16_t> rank_host;
+    DevBuf errs_dev, rank_dev;
+    int nlevels = 0;
+    // candidate-set statistics (host copies, from annb_index_locality)
+    std::vector<int32_t> ncand_host, anc_cand_host;
+    int64_t n_candidates = 0, n_anchor_pairs = 0;
+    // thresholds and row lists
+    DevBuf thresh, l2val, l2id;
+    // selection
+    DevBuf hist, counters, emit_key, emit_lvl, sel_i, sel_j, nxt_i, nxt_j, tiehist, tiekeys;
+    int64_t n_sel = 0, n_next = 0;
+    // sampler pool
+    DevBuf pool_key, pool_dad;
+    int64_t n_pool = 0;
+    // temporaries
+    DevBuf t0, t1, t2, t3, t4, t5, t6;
+    // CSR of known pairs
+    DevBuf kptr, kids, kds, kdeg;
+    int64_t csr_entries = 0;
+    // stats
+    int64_t pairs_swept = 0, sweeps = 0, n_tight = 0, n_known = 0;
+    float last_sweep_ms = 0;
+    int64_t last_sweep_pairs = 0;
+
+    View view() const
+    {
+        View V;
+        V.n = n;
+        V.npad = npad;
+        V.na = na;
+        V.T = T;
+        V.nn = P.n_neighbors;
+        V.is_metric = P.is_metric;
+        V.D32 = D32.as<float>();
+        V.meta = meta.as<PointMeta>();
+        V.htab = htab.as<HashSlot>();
+        V.hmask = hcap - 1;
+        V.bitmap = bitmap.as<uint32_t>();
+        return V;
+    }
+    int64_t n_not_computed() const { return n_candidates - n_anchor_pairs - n_known; }
+};
+
+static int grid_for_n(const annb_ctx *c, int64_t n, int per_block = 256)
+{
+    int64_t g = (n + per_block - 1) / per_block;
+    const int64_t cap = (int64_t)c->num_sms * 16;
+    return (int)(g < 1 ? 1 : (g < cap ? g : cap));
+}
+
+static int hash_alloc(annb_index *ix, uint64_t cap)
+{
+    annb_ctx *c = ix->ctx;
+    ANNB_TRY(ix->htab.ensure(cap * sizeof(HashSlot)));
+    ANNB_CUDA(cudaMemsetAsync(ix->htab.p, 0xff, cap * sizeof(HashSlot), c->stream));  // key = HKEY_EMPTY
+    ix->hcap = cap;
+    return ANNB_OK;
+}
+
+// make room for `extra` more entries (load factor <= 0.5)
+static int hash_reserve(annb_index *ix, int64_t extra)
+{
+    annb_ctx *c = ix->ctx;
+    const uint64_t need = (uint64_t)(ix->hcount_ub + extra) * 2 + 1024;
+    if (need <= ix->hcap) return ANNB_OK;
+    uint64_t cap = ix->hcap ? ix->hcap : 1024;
+    while (cap < need) cap <<= 1;
+    DevBuf otab = ix->htab;
+    const uint64_t ocap = ix->hcap;
+    ix->htab = DevBuf();
+    ANNB_TRY(hash_alloc(ix, cap));
+    if (ocap)
+        ANNB_LAUNCH(hash_rehash_kernel, grid_for_n(c, (int64_t)ocap), 256, 0, c->stream,
+                    otab.as<HashSlot>(), ocap, ix->htab.as<HashSlot>(), cap - 1);
+    ANNB_CUDA(cudaStreamSynchronize(c->stream));
+    otab.release();
+    return ANNB_OK;
+}
+
+// insert device-resident (I, J, a, b) with the given kind
+static int hash_insert(annb_index *ix, const int32_t *I, const int32_t *J, const float *a,
+                       const float *b, uint32_t kind, int64_t m)
+{
+    if (m == 0) return ANNB_OK;
+    annb_ctx *c = ix->ctx;
+    ANNB_TRY(hash_reserve(ix, m));
+    ANNB_LAUNCH(hash_insert_kernel, grid_for_n(c, m), 256, 0, c->stream, ix->htab.as<HashSlot>(),
+                ix->hcap - 1, ix->bitmap.as<uint32_t>(), ix->T, I, J, a, b, kind, m);
+    ix->hcount_ub += m;
+    return ANNB_OK;
+}
+
+static int finish_anchors(annb_index *ix)
+{
+    annb_ctx *c = ix->ctx;
+    ANNB_LAUNCH(build_meta_kernel, grid_for_n(c, ix->npad), 256, 0, c->stream, ix->D64.as<double>(),
+                ix->n, ix->npad, ix->na, ix->P.locality, ix->P.loc_thresh, ix->D32.as<float>(),
+                ix->meta.as<PointMeta>());
+    if (!ix->A_host.empty())
+        ANNB_LAUNCH(set_slots_kernel, 1, 32, 0, c->stream, ix->A_dev.as<int32_t>(),
+                    (int)ix->A_host.size(), ix->meta.as<PointMeta>());
+    ix->have_anchors = true;
+    ix->have_locality = false;
+    return ANNB_OK;
+}
+
+ANNB_API int annb_index_create(annb_ctx *c, const annb_dataset *ds, int metric,
+                               const annb_index_params *P, annb_index **out)
+{
+    ANNB_REQUIRE(c && ds && P && out, ANNB_EINVAL, "NULL argument");
+    ANNB_TRY(check_metric(ds, metric));
+    ANNB_REQUIRE(P->n_anchors > 0 && P->n_anchors <= kMaxAnchors, ANNB_ERANGE,
+                 "n_anchors=%d outside [1,%d]", P->n_anchors, kMaxAnchors);
+    ANNB_REQUIRE(P->n_neighbors >= 2 && P->n_neighbors + 1 <= MAX_LIST, ANNB_ERANGE,
+                 "n_neighbors=%d outside [2,%d]", P->n_neighbors, MAX_LIST - 1);
+    ANNB_REQUIRE(P->locality >= 1 && P->loc_thresh >= 0 && P->loc_thresh <= 7, ANNB_ERANGE,
+                 "locality=%d / loc_thresh=%d unsupported (loc_thresh must be <= 7)", P->locality,
+                 P->loc_thresh);
+    ANNB_REQUIRE(P->world >= 1 && P->rank >= 0 && P->rank < P->world, ANNB_EINVAL, "bad rank/world");
+    ANNB_CUDA(cudaSetDevice(c->device));
+    annb_index *ix = new annb_index();
+    ix->ctx = c;
+    ix->ds = ds;
+    ix->metric = metric;
+    ix->P = *P;
+    ix->n = ds->n;
+    ix->na = P->n_anchors;
+    ix->T = (int)((ds->n + TILE - 1) / TILE);
+    ix->npad = (int64_t)ix->T * TILE;
+    ix->NT = (int64_t)ix->T * (ix->T + 1) / 2;
+    int rc = ANNB_OK;
+    do {
+        if ((rc = ix->A_dev.ensure((size_t)ix->na * 4))) break;
+        if ((rc = ix->D64.ensure((size_t)ix->na * ix->n * 8))) break;
+        if ((rc = ix->D32.ensure((size_t)ix->na * ix->npad * 4))) break;
+        if ((rc = ix->meta.ensure((size_t)ix->npad * sizeof(PointMeta)))) break;
+        if ((rc = ix->bitmap.ensure((size_t)ix->NT * BITMAP_WORDS * 4))) break;
+        if ((rc = ix->thresh.ensure((size_t)ix->npad * 4))) break;
+        if ((rc = ix->counters.ensure(256))) break;
+        if ((rc = ix->tiehist.ensure(65536 * 4))) break;
+    } while (0);
+    if (rc) {
+        annb_index_destroy(ix);
+        return rc;
+    }
+    ANNB_CUDA(cudaMemsetAsync(ix->bitmap.p, 0, (size_t)ix->NT * BITMAP_WORDS * 4, c->stream));
+    ANNB_TRY(hash_alloc(ix, 1 << 16));
+    *out = ix;
+    return ANNB_OK;
+}
+
+ANNB_API int annb_index_destroy(annb_index *ix)
+{
+    if (!ix) return ANNB_OK;
+    cudaSetDevice(ix->ctx->device);
+    cudaStreamSynchronize(ix->ctx->stream);
+    DevBuf *all[] = {&ix->A_dev, &ix->D64, &ix->D32, &ix->meta, &ix->scratch, &ix->htab, &ix->bitmap,
+                     &ix->errs_dev, &ix->rank_dev, &ix->thresh, &ix->l2val, &ix->l2id, &ix->hist,
+                     &ix->counters, &ix->emit_key, &ix->emit_lvl, &ix->sel_i, &ix->sel_j, &ix->nxt_i,
+                     &ix->nxt_j, &ix->tiehist, &ix->tiekeys, &ix->pool_key, &ix->pool_dad, &ix->t0,
+                     &ix->t1, &ix->t2, &ix->t3, &ix->t4, &ix->t5, &ix->t6, &ix->kptr, &ix->kids,
+                     &ix->kds, &ix->kdeg};
+    for (DevBuf *b : all) b->release();
+    delete ix;
+    return ANNB_OK;
+}
+
+ANNB_API int annb_index_maxmin(annb_index *ix, int64_t first, int64_t *A)
+{
+    ANNB_REQUIRE(ix != nullptr, ANNB_EINVAL, "index is NULL");
+    ANNB_REQUIRE(first >= 0 && first < ix->n, ANNB_EINVAL, "first anchor out of range");
+    annb_ctx *c = ix->ctx;
+    ANNB_CUDA(cudaSetDevice(c->device));
+    const int32_t f = (int32_t)first;
+    ANNB_CUDA(cudaMemcpyAsync(ix->A_dev.p, &f, 4, cudaMemcpyHostToDevice, c->stream));
+    ANNB_TRY(maxmin_device(c, ix->ds, ix->metric, ix->na, ix->A_dev.as<int32_t>(),
+                           ix->D64.as<double>(), ix->scratch));
+    ix->A_host.resize(ix->na);
+    ANNB_CUDA(cudaMemcpyAsync(ix->A_host.data(), ix->A_dev.p, (size_t)ix->na * 4,
+                              cudaMemcpyDeviceToHost, c->stream));
+    ANNB_CUDA(cudaStreamSynchronize(c->stream));
+    if (A)
+        for (int k = 0; k < ix->na; ++k) A[k] = ix->A_host[k];
+    return finish_anchors(ix);
+}
+
+ANNB_API int annb_index_set_anchors(annb_index *ix, const int64_t *A, int64_t nA, const double *D)
+{
+    ANNB_REQUIRE(ix && D, ANNB_EINVAL, "NULL argument");
+    ANNB_REQUIRE(nA == 0 || nA == ix->na, ANNB_EINVAL, "A must be empty or have n_anchors entries");
+    annb_ctx *c = ix->ctx;
+    ANNB_CUDA(cudaSetDevice(c->device));
+    // D arrives (n, na) row-major (the reference's D.T); store anchor-major
+    std::vector<double> Dam((size_t)ix->na * ix->n);
+    for (int64_t j = 0; j < ix->n; ++j)
+        for (int a = 0; a < ix->na; ++a) Dam[(size_t)a * ix->n + j] = D[j * ix->na + a];
+    ANNB_CUDA(cudaMemcpyAsync(ix->D64.p, Dam.data(), Dam.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    ix->A_host.clear();
+    for (int64_t k = 0; k < nA; ++k) {
+        ANNB_REQUIRE(A[k] >= 0 && A[k] < ix->n, ANNB_EINVAL, "anchor id out of range");
+        ix->A_host.push_back((int32_t)A[k]);
+    }
+    if (nA)
+        ANNB_CUDA(cudaMemcpyAsync(ix->A_dev.p, ix->A_host.data(), (size_t)nA * 4,
+                                  cudaMemcpyHostToDevice, c->stream));
+    ANNB_CUDA(cudaStreamSynchronize(c->stream));
+    return finish_anchors(ix);
+}
+
+ANNB_API int annb_index_get_D(annb_index *ix, double *D)
+{
+    ANNB_REQUIRE(ix && D, ANNB_EINVAL, "NULL argument");
+    ANNB_REQUIRE(ix->have_anchors, ANNB_ESTATE, "anchors not computed yet");
+    annb_ctx *c = ix->ctx;
+    ANNB_CUDA(cudaSetDevice(c->device));
+    ANNB_TRY(ix->t0.ensure((size_t)ix->na * ix->n * 8));
+    ANNB_TRY(transpose_D(c, ix->D64.as<double>(), ix->n, ix->na, ix->t0.as<double>()));
+    ANNB_CUDA(cudaMemcpyAsync(D, ix->t0.p, (size_t)ix->na * ix->n * 8, cudaMemcpyDeviceToHost, c->stream));
+    ANNB_CUDA(cudaStreamSynchronize(c->stream));
+    return ANNB_OK;
+}
+
+ANNB_API int annb_index_locality(annb_index *ix, int64_t *n_candidates, int64_t *n_relaxed)
+{
+    ANNB_REQUIRE(ix != nullptr, ANNB_EINVAL, "index is NULL");
+    ANNB_REQUIRE(ix->have_anchors, ANNB_ESTATE, "anchors not computed yet");
+    annb_ctx *c = ix->ctx;
+    ANNB_CUDA(cudaSetDevice(c->device));
+    const int64_t n = ix->n;
+    const int lt = ix->P.loc_thresh;
+    ANNB_TRY(ix->t0.ensure((size_t)n * 8 * 4));
+    const int grid = (int)((n + 255) / 256);
+    ANNB_LAUNCH(locality_count_kernel, grid, 256, 0, c->stream, ix->meta.as<PointMeta>(), n, lt, 1,
+                ix->t0.as<int32_t>());
+    std::vector<int32_t> h((size_t)n * 8);
+    ANNB_CUDA(cudaMemcpyAsync(h.data(), ix->t0.p, h.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+    ANNB_CUDA(cudaStreamSynchronize(c->stream));
+    // t_i = min(loc_thresh, (loc_min+1)-th largest shared count)   (utils.py:472-480)
+    const int64_t want = std::min<int64_t>(ix->P.loc_min, n - 1) + 1;
+    std::vector<int8_t> t(n);
+    int64_t relaxed = 0, total = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        int64_t cum = 0;
+        int ti = 0;
+        for (int cval = lt; cval >= 0; --cval) {
+            cum += h[i * 8 + cval];
+            if (cum >= want) {
+                ti = cval;
+                break;
+            }
+        }
+        t[i] = (int8_t)ti;
+        if (ti < lt) ++relaxed;
+    }
+    std::vector<int32_t> &ncand = ix->ncand_host;
+    ncand.assign(n, 0);
+    if (relaxed) {
+        ANNB_TRY(ix->t1.ensure((size_t)n));
+        ANNB_CUDA(cudaMemcpyAsync(ix->t1.p, t.data(), (size_t)n, cudaMemcpyHostToDevice, c->stream));
+        ANNB_LAUNCH(set_loc_t_kernel, grid_for_n(c, n), 256, 0, c->stream, ix->meta.as<PointMeta>(),
+                    ix->t1.as<int8_t>(), n);
+        ANNB_LAUNCH(locality_count_kernel, grid, 256, 0, c->stream, ix->meta.as<PointMeta>(), n, lt, 2,
+                    ix->t0.as<int32_t>());
+        ANNB_CUDA(cudaMemcpyAsync(ncand.data(), ix->t0.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+        ANNB_CUDA(cudaStreamSynchronize(c->stream));
+    } else {
+        for (int64_t i = 0; i < n; ++i) ncand[i] = h[i * 8 + lt] - 1;  // minus self
+    }
+    int64_t minc = INT64_MAX;
+    for (int64_t i = 0; i < n; ++i) {
+        total += ncand[i];
+        minc = std::min<int64_t>(minc, ncand[i]);
+    }
+    // candidate pairs that touch an anchor: computed from the start (annchor.py:286-301)
+    ix->anc_cand_host.assign(n, 0);
+    ix->n_anchor_pairs = 0;
+    if (!ix->A_host.empty()) {
+        ANNB_LAUNCH(anchor_cand_kernel, grid_for_n(c, n), 256, 0, c->stream, ix->meta.as<PointMeta>(), n,
+                    ix->A_dev.as<int32_t>(), (int)ix->A_host.size(), ix->t0.as<int32_t>());
+        ANNB_CUDA(cudaMemcpyAsync(ix->anc_cand_host.data(), ix->t0.p, (size_t)n * 4, cudaMemcpyDeviceToHost,
+                                  c->stream));
+        ANNB_CUDA(cudaStreamSynchronize(c->stream));
+        std::vector<char> is_anchor(n, 0);
+        for (size_t k = 0; k < ix->A_host.size(); ++k) is_anchor[ix->A_host[k]] = 1;
+        int64_t mixed = 0, both = 0;
+        for (int64_t i = 0; i < n; ++i) {
+            if (is_anchor[i]) {
+                mixed += ncand[i] - ix->anc_cand_host[i];  // (anchor, non-anchor) pairs
+                both += ix->anc_cand_host[i];              // (anchor, anchor) pairs, counted twice
+            }
+        }
+        ix->n_anchor_pairs = mixed + both / 2;
+    }
+    ix->n_candidates = total / 2;
+    ix->have_locality = true;
+    if (n_candidates) *n_candidates = total / 2;
+    if (n_relaxed) *n_relaxed = relaxed;
+    // check_locality_size (utils.py:592-597, annchor.py:252-256)
+    ANNB_REQUIRE(minc >= ix->P.n_neighbors, ANNB_ESTATE,
+                 "Error: Not enough candidates in pool for all indices. Try again with higher locality.");
+    return ANNB_OK;
+}
+
+static int upload_pairs(annb_index *ix, const int64_t *ij, const double *d, int64_t m)
+{
+    annb_ctx *c = ix->ctx;
+    for (int64_t p = 0; p < 2 * m; ++p)
+        ANNB_REQUIRE(ij[p] >= 0 && ij[p] < ix->n, ANNB_EINVAL, "pair index out of range");
+    ANNB_TRY(ix->t0.ensure((size_t)m * 16));
+    ANNB_TRY(ix->t1.ensure((size_t)m * 4));
+    ANNB_TRY(ix->t2.ensure((size_t)m * 4));
+    ANNB_TRY(ix->t3.ensure((size_t)m * 4));
+    ANNB_CUDA(cudaMemcpyAsync(ix->t0.p, ij, (size_t)m * 16, cudaMemcpyHostToDevice, c->stream));
+    double *dd = nullptr;
+    if (d) {
+        ANNB_TRY(ix->t4.ensure((size_t)m * 8));
+        ANNB_CUDA(cudaMemcpyAsync(ix->t4.p, d, (size_t)m * 8, cudaMemcpyHostToDevice, c->stream));
+        dd = ix->t4.as<double>();
+    }
+    ANNB_LAUNCH(split_ij32_kernel, grid_for_n(c, m), 256, 0, c->stream, ix->t0.as<int64_t>(), dd, m,
+                ix->t1.as<int32_t>(), ix->t2.as<int32_t>(), ix->t3.as<float>());
+    return ANNB_OK;
+}
+
+ANNB_API int annb_index_add_known(annb_index *ix, const int64_t *ij, const double *d, int64_t m)
+{
+    ANNB_REQUIRE(ix && (m == 0 || (ij && d)), ANNB_EINVAL, "NULL argument");
+    if (m == 0) return ANNB_OK;
+    ANNB_CUDA(cudaSetDevice(ix->ctx->device));
+    ANNB_TRY(upload_pairs(ix, ij, d, m));
+    ANNB_TRY(hash_insert(ix, ix->t1.as<int32_t>(), ix->t2.as<int32_t>(), ix->t3.as<float>(), nullptr,
+                         KIND_KNOWN, m));
+    ix->n_known += m;
+    return ANNB_OK;
+}
+
+ANNB_API int annb_index_eval_pairs(annb_index *ix, const int64_t *ij, int64_t m, double *d)
+{
+    ANNB_REQUIRE(ix && (m == 0 || ij), ANNB_EINVAL, "NULL argument");
+    if (m == 0) return ANNB_OK;
+    annb_ctx *c = ix->ctx;
+    ANNB_CUDA(cudaSetDevice(c->device));
+    ANNB_TRY(upload_pairs(ix, ij, nullptr, m));
+    ANNB_TRY(pair_dists_f32_perm(c, ix->ds, ix->metric, ix->t1.as<int32_t>(), ix->t2.as<int32_t>(),
+                                 nullptr, m, ix->t3.as<float>()));
+    ANNB_TRY(hash_insert(ix, ix->t1.as<int32_t>(), ix->t2.as<int32_t>(), ix->t3.as<float>(), nullptr,
+                         KIND_KNOWN, m));
+    ix->n_known += m;
+    if (d) {
+        ANNB_TRY(ix->t4.ensure((size_t)m * 8));
+        ANNB_TRY(pair_dists_f64(c, ix->ds, ix->metric, ix->t1.as<int32_t>(), ix->t2.as<int32_t>(), m,
+                                ix->t4.as<double>()));
+        ANNB_CUDA(cudaMemcpyAsync(d, ix->t4.p, (size_t)m * 8, cudaMemcpyDeviceToHost, c->stream));
+        ANNB_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    return ANNB_OK;
+}
+
+ANNB_API int annb_index_pair_features(annb_index *ix, const int64_t *ij, int64_t m, double *feat)
+{
+    ANNB_REQUIRE(ix && (m == 0 || (ij && feat)), ANNB_EINVAL, "NULL argument");
+    ANNB_REQUIRE(ix->have_anchors, ANNB_ESTATE, "anchors not computed yet");
+    if (m == 0) return ANNB_OK;
+    annb_ctx *c = ix->ctx;
+    ANNB_CUDA(cudaSetDevice(c->device));
+    ANNB_TRY(upload_pairs(ix, ij, nullptr, m));
+    ANNB_TRY(ix->t4.ensure((size_t)m * 12));
+    ANNB_LAUNCH(pair_features_kernel, grid_for_n(c, m), 256, 0, c->stream, ix->view(),
+                ix->t1.as<int32_t>(), ix->t2.as<int32_t>(), m, ix->t4.as<float>());
+    std::vector<float> f((size_t)m * 3);
+    ANNB_CUDA(cudaMemcpyAsync(f.data(), ix->t4.p, f.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+    ANNB_CUDA(cudaStreamSynchronize(c->stream));
+    for (size_t k = 0; k < f.size(); ++k) feat[k] = f[k];
+    return ANNB_OK;
+}
+
+ANNB_API int annb_index_set_model(annb_index *ix, const double *bins, const double *coef,
+                                  const double *icpt, int64_t nb, const double *errs,
+                                  const int64_t *eptr)
+{
+    ANNB_REQUIRE(ix && bins && coef && icpt, ANNB_EINVAL, "NULL argument");
+    ANNB_REQUIRE(nb >= 1 && nb <= MAX_BINS, ANNB_ERANGE, "n_partitions=%lld outside [1,%d]",
+                 (long long)nb, MAX_BINS);
+    annb_ctx *c = ix->ctx;
+    ANNB_CUDA(cudaSetDevice(c->device));
+    Model &M = ix->model;
+    memset(&M, 0, sizeof(M));
+    M.nb = (int)nb;
+    for (int b = 0; b <= nb; ++b) M.edge[b] = (float)bins[b];
+    for (int b = 0; b < nb; ++b) {
+        M.c0[b] = (float)coef[3 * b];
+        M.c1[b] = (float)coef[3 * b + 1];
+        M.c2[b] = (float)coef[3 * b + 2];
+        M.ic[b] = (float)icpt[b];
+    }
+    ix->errs_host.clear();
+    ix->rank_host.clear();
+    ix->nlevels = 0;
+    if (errs && eptr) {
+        const int64_t ne = eptr[nb];
+        ANNB_REQUIRE(ne < (1 << 22), ANNB_ERANGE, "error tables too large (%lld)", (long long)ne);
+        for (int b = 0; b <= nb; ++b) M.eoff[b] = (int)eptr[b];
+        ix->errs_host.resize(ne);
+        for (int64_t k = 0; k < ne; ++k) ix->errs_host[k] = (float)errs[k];
+        // distinct probability values r/len over all labels, ascending -> level ids
+        std::vector<double> vals;
+        for (int b = 0; b < nb; ++b) {
+            const int64_t len = eptr[b + 1] - eptr[b];
+            ANNB_REQUIRE(len > 0, ANNB_EINVAL, "error table of label %d is empty", b);
+            for (int64_t r = 0; r <= len; ++r) vals.push_back((double)r / (double)len);
+        }
+        std::vector<double> uniq = vals;
+        std::sort(uniq.begin(), uniq.end());
+        uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+        ANNB_REQUIRE(uniq.size() < 40000, ANNB_ERANGE,
+                     "too many probability levels (%zu) for the shared-memory histogram", uniq.size());
+        ix->nlevels = (int)uniq.size();
+        ix->rank_host.resize(vals.size());
+        for (size_t k = 0; k < vals.size(); ++k)
+            ix->rank_host[k] = (uint16_t)(std::lower_bound(uniq.begin(), uniq.end(), vals[k]) - uniq.begin());
+        ANNB_TRY(ix->errs_dev.ensure(ix->errs_host.size() * 4));
+        ANNB_TRY(ix->rank_dev.ensure(ix->rank_host.size() * 2));
+        ANNB_CUDA(cudaMemcpyAsync(ix->errs_dev.p, ix->errs_host.data(), ix->errs_host.size() * 4,
+                                  cudaMemcpyHostToDevice, c->stream));
+        ANNB_CUDA(cudaMemcpyAsync(ix->rank_dev.p, ix->rank_host.data(), ix->rank_host.size() * 2,
+                                  cudaMemcpyHostToDevice, c->stream));
+        ANNB_TRY(ix->hist.ensure((size_t)ix->nlevels * 4));
+        ANNB_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    ix->have_model = true;
+    ix->have_thresh = false;
+    return ANNB_OK;
+}
+
+static int run_thresh(annb_index *ix, int k2)
+{
+    annb_ctx *c = ix->ctx;
+    ThreshArgs A;
+    A.V = ix->view();
+    A.M = ix->model;
+    A.k1 = ix->P.n_neighbors + 1;
+    A.k2 = k2;
+    A.thresh = ix->thresh.as<float>();
+    A.l2val = nullptr;
+    A.l2id = nullptr;
+    if (k2 > 0) {
+        ANNB_TRY(ix->l2val.ensure((size_t)ix->n * k2 * 4));
+        ANNB_TRY(ix->l2id.ensure((size_t)ix->n * k2 * 4));
+        A.l2val = ix->l2val.as<float>();
+        A.l2id = ix->l2id.as<int32_t>();
+    }
+    A.rank = ix->P.rank;
+    A.world = ix->P.world;
+    ANNB_CUDA(cudaEventRecord(c->ev0, c->stream));
+    ANNB_TRY(launch_thresh_sweep(c, A));
+    ANNB_CUDA(cudaEventRecord(c->ev1, c->stream));
+    ANNB_CUDA(cudaEventSynchronize(c->ev1));
+    float ms = 0;
+    ANNB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    ix->pairs_swept += ix->n * (ix->n - 1) / ix->P.world;
+    ix->sweeps += 1;
+    ix->have_thresh = true;
+    return ANNB_OK;
+}
+
+ANNB_API int annb_index_row_thresh(annb_index *ix, double *thresh)
+{
+    ANNB_REQUIRE(ix != nullptr, ANNB_EINVAL, "index is NULL");
+    ANNB_REQUIRE(ix->have_anchors && ix->have_model, ANNB_ESTATE, "set anchors and model first");
+    annb_ctx *c = ix->ctx;
+    ANNB_CUDA(cudaSetDevice(c->device));
+    ANNB_TRY(run_thresh(ix, 0));
+    if (thresh) {
+        std::vector<float> h(ix->n);
+        ANNB_CUDA(cudaMemcpyAsync(h.data(), ix->thresh.p, (size_t)ix->n * 4, cudaMemcpyDeviceToHost, c->stream));
+        ANNB_CUDA(cudaStreamSynchronize(c->stream));
+        for (int64_t i = 0; i < ix->n; ++i) thresh[i] = h[i];
+    }
+    return ANNB_OK;
+}
+
+// guarantee_nmin (utils.py:606-621).  The thresh sweep runs with a second per-row list (the
+// nmin+1 smallest not-computed predictions with ids); the reference's serial row loop, in which
+// later rows see the -1 marks of earlier rows, then runs on the host over those short lists.
+ANNB_API int annb_index_guarantee_nmin(annb_index *ix, int64_t nmin, int64_t *n_forced)
+{
+    ANNB_REQUIRE(ix != nullptr, ANNB_EINVAL, "index is NULL");
+    ANNB_REQUIRE(ix->have_anchors && ix->have_model && ix->have_locality, ANNB_ESTATE,
+                 "anchors, locality and model must be set first");
+    ANNB_REQUIRE(nmin >= 0 && nmin + 1 <= MAX_LIST, ANNB_ERANGE,
+                 "nmin=%lld too large for the device row lists (max %d)", (long long)nmin, MAX_LIST - 1);
+    annb_ctx *c = ix->ctx;
+    ANNB_CUDA(cudaSetDevice(c->device));
+    const int64_t n = ix->n;
+    if (n_forced) *n_forced = 0;
+    // computed pairs per row = anchor pairs among the candidates + exactly known pairs
+    ANNB_TRY(ix->kdeg.ensure((size_t)(n + 1) * 4));
+    ANNB_CUDA(cudaMemsetAsync(ix->kdeg.p, 0, (size_t)(n + 1) * 4, c->stream));
+    ANNB_LAUNCH(known_degree_kernel, grid_for_n(c, (int64_t)ix->hcap), 256, 0, c->stream,
+                ix->htab.as<HashSlot>(), ix->hcap, ix->kdeg.as<int32_t>());
+    std::vector<int32_t> ncomp(n);
+    ANNB_CUDA(cudaMemcpyAsync(ncomp.data(), ix->kdeg.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    ANNB_CUDA(cudaStreamSynchronize(c->stream));
+    std::vector<char> is_anchor(n, 0);
+    for (size_t k = 0; k < ix->A_host.size(); ++k) is_anchor[ix->A_host[k]] = 1;
+    bool any = false;
+    for (int64_t i = 0; i < n; ++i) {
+        ncomp[i] += is_anchor[i] ? ix->ncand_host[i] : ix->anc_cand_host[i];
+        any |= ncomp[i] < nmin;
+    }
+    if (!any) {  // every row already has nmin computed pairs: only thresh is needed
+        return run_thresh(ix, 0);
+    }
+    const int k2 = (int)nmin + 1;
+    ANNB_TRY(run_thresh(ix, k2));
+    std::vector<float> lv((size_t)n * k2);
+    std::vector<int32_t> li((size_t)n * k2);
+    ANNB_CUDA(cudaMemcpyAsync(lv.data(), ix->l2val.p, lv.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+    ANNB_CUDA(cudaMemcpyAsync(li.data(), ix->l2id.p, li.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+    ANNB_CUDA(cudaStreamSynchronize(c->stream));
+    std::vector<int64_t> fij;
+    std::unordered_map<int32_t, std::vector<int32_t>> marks;  // row -> earlier rows that forced (row', row)
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t n_todo = nmin - ncomp[i];
+        if (n_todo <= 0) continue;
+        const auto it = marks.find((int32_t)i);
+        const std::vector<int32_t> *mk = it == marks.end() ? nullptr : &it->second;
+        const int64_t m_i = mk ? (int64_t)mk->size() : 0;
+        if (m_i >= n_todo + 1) continue;  // the (n_todo+1)-th smallest is already a -1 mark
+        const float *v = &lv[(size_t)i * k2];
+        const int32_t *id = &li[(size_t)i * k2];
+        std::vector<int> un;  // unmarked entries of the row's list, ascending
+        for (int k = 0; k < k2; ++k) {
+            if (id[k] < 0) continue;
+            bool marked = false;
+            if (mk)
+                for (int32_t r : *mk)
+                    if (r == id[k]) {
+                        marked = true;
+                        break;
+                    }
+            if (!marked) un.push_back(k);
+        }
+        const int64_t need = n_todo + 1 - m_i;  // rank (1-based) of kth among the unmarked values
+        if ((int64_t)un.size() < need) continue;
+        const float kth = v[un[need - 1]];
+        for (int64_t q = 0; q < need - 1; ++q) {
+            if (!(v[un[q]] < kth)) break;  // strict <: ties with kth are dropped (utils.py:602-603)
+            const int32_t j = id[un[q]];
+            fij.push_back(std::min<int64_t>(i, j));
+            fij.push_back(std::max<int64_t>(i, j));
+            if (j > i) marks[j].push_back((int32_t)i);
+        }
+    }
+    const int64_t m = (int64_t)fij.size() / 2;
+    if (m) {
+        ANNB_TRY(upload_pairs(ix, fij.data(), nullptr, m));
+        ANNB_TRY(hash_insert(ix, ix->t1.as<int32_t>(), ix->t2.as<int32_t>(), nullptr, nullptr,
+                             KIND_FORCED, m));
+        ix->has_forced = true;
+    }
+    if (n_forced) *n_forced = m;
+    return ANNB_OK;
+}
+
+// ---- selection --------------------------------------------------------------------------------
+static void fill_efloor(const annb_index *ix, int floor_level, float *efloor, float *ef_min)
+{
+    const Model &M = ix->model;
+    for (int b = 0; b < MAX_BINS; ++b) efloor[b] = INFINITY;
+    float mn = INFINITY;
+    for (int b = 0; b < M.nb; ++b) {
+        const int len = M.eoff[b + 1] - M.eoff[b];
+        int rmin = -1;
+        for (int r = 0; r <= len; ++r)
+            if (ix->rank_host[M.eoff[b] + b + r] >= floor_level) {
+                rmin = r;
+                break;
+            }
+        if (rmin < 0) efloor[b] = INFINITY;
+        else if (rmin == 0) efloor[b] = -INFINITY;
+        else efloor[b] = ix->errs_host[M.eoff[b] + rmin - 1];
+        mn = std::min(mn, efloor[b]);
+    }
+    *ef_min = ix->P.is_metric ? mn : -INFINITY;  // d >= lower bound only holds for metrics
+}
+
+static int run_score(annb_index *ix, int floor_level, int stride, bool emit, int64_t emit_cap,
+                     std::vector<uint32_t> &hist, unsigned long long cnt[3])
+{
+    annb_ctx *c = ix->ctx;
+    ScoreArgs A;
+    A.V = ix->view();
+    A.M = ix->model;
+    A.thresh = ix->thresh.as<float>();
+    A.errs = ix->errs_dev.as<float>();
+    A.ranktab = ix->rank_dev.as<uint16_t>();
+    A.nlevels = ix->nlevels;
+    A.floor_level = floor_level;
+    fill_efloor(ix, floor_level, A.efloor, &A.ef_min);
+    A.has_forced = ix->has_forced ? 1 : 0;
+    A.hist = ix->hist.as<uint32_t>();
+    A.counters = ix->counters.as<unsigned long long>();
+    A.emit_key = nullptr;
+    A.emit_lvl = nullptr;
+    A.emit_cap = 0;
+    if (emit) {
+        ANNB_TRY(ix->emit_key.ensure((size_t)emit_cap * 8));
+        ANNB_TRY(ix->emit_lvl.ensure((size_t)emit_cap * 2));
+        A.emit_key = ix->emit_key.as<uint64_t>();
+        A.emit_lvl = ix->emit_lvl.as<uint16_t>();
+        A.emit_cap = (unsigned long long)emit_cap;
+    }
+    const int64_t nq = (ix->NT - ix->P.rank + ix->P.world - 1) / ix->P.world;
+    A.q_begin = 0;
+    A.q_end = nq;
+    A.q_stride = stride;
+    A.rank = ix->P.rank;
+    A.world = ix->P.world;
+    ANNB_CUDA(cudaMemsetAsync(ix->hist.p, 0, (size_t)ix->nlevels * 4, c->stream));
+    ANNB_CUDA(cudaMemsetAsync(ix->counters.p, 0, 64, c->stream));
+    ANNB_CUDA(cudaEventRecord(c->ev0, c->stream));
+    ANNB_TRY(launch_score_sweep(c, A));
+    ANNB_CUDA(cudaEventRecord(c->ev1, c->stream));
+    hist.resize(ix->nlevels);
+    ANNB_CUDA(cudaMemcpyAsync(hist.data(), ix->hist.p, (size_t)ix->nlevels * 4, cudaMemcpyDeviceToHost, c->stream));
+    ANNB_CUDA(cudaMemcpyAsync(cnt, ix->counters.p, 24, cudaMemcpyDeviceToHost, c->stream));
+    ANNB_CUDA(cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    ANNB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    const int64_t pairs = ix->n * (ix->n - 1) / 2 / ix->P.world / stride;
+    if (stride == 1) {
+        ix->last_sweep_ms = ms;
+        ix->last_sweep_pairs = pairs;
+    }
+    ix->pairs_swept += pairs;
+    ix->sweeps += 1;
+    return ANNB_OK;
+}
+
+// exact t-th smallest (1-based) mixed key among the emitted entries of one level
+static int tie_threshold(annb_index *ix, int64_t E, int level, int64_t level_count, int64_t t, uint64_t *thr)
+{
+    annb_ctx *c = ix->ctx;
+    ANNB_TRY(ix->tiekeys.ensure((size_t)(level_count + 32) * 8));
+    ANNB_CUDA(cudaMemsetAsync(ix->counters.p, 0, 64, c->stream));
+    ANNB_LAUNCH(compact_level_kernel, grid_for_n(c, E), 256, 0, c->stream, ix->emit_key.as<uint64_t>(),
+                ix->emit_lvl.as<uint16_t>(), E, level, ix->tiekeys.as<uint64_t>(),
+                ix->counters.as<unsigned long long>());
+    uint64_t prefix = 0;
+    std::vector<uint32_t> h(65536);
+    for (int shift = 48; shift >= 0; shift -= 16) {
+        ANNB_CUDA(cudaMemsetAsync(ix->tiehist.p, 0, 65536 * 4, c->stream));
+        ANNB_LAUNCH(digit_hist_kernel, grid_for_n(c, level_count), 256, 0, c->stream,
+                    ix->tiekeys.as<uint64_t>(), level_count, prefix, shift, ix->tiehist.as<uint32_t>());
+        ANNB_CUDA(cudaMemcpyAsync(h.data(), ix->tiehist.p, 65536 * 4, cudaMemcpyDeviceToHost, c->stream));
+        ANNB_CUDA(cudaStreamSynchronize(c->stream));
+        int d = 0;
+        for (; d < 65536; ++d) {
+            if (t <= (int64_t)h[d]) break;
+            t -= h[d];
+        }
+        ANNB_REQUIRE(d < 65536, ANNB_ESTATE, "tie selection ran past the histogram");
+        prefix = (prefix << 16) | (uint64_t)d;
+    }
+    *thr = prefix;
+    return ANNB_OK;
+}
+
+// largest level L >= lo_level with sum_{l >= L} h[l] >= target (lo_level if none)
+static int level_cut(const std::vector<uint32_t> &h, int lo_level, int64_t target, int64_t *cum_at)
+{
+    int64_t cum = 0;
+    for (int L = (int)h.size() - 1; L > lo_level; --L) {
+        cum += h[L];
+        if (cum >= target) {
+            if (cum_at) *cum_at = cum;
+            return L;
+        }
+    }
+    cum += h[lo_level];
+    if (cum_at) *cum_at = cum;
+    return lo_level;
+}
+
+ANNB_API int annb_index_select(annb_index *ix, int64_t n_refine, int64_t lookahead,
+                               int64_t *n_selected, int64_t *n_next)
+{
+    ANNB_REQUIRE(ix != nullptr, ANNB_EINVAL, "index is NULL");
+    ANNB_REQUIRE(ix->have_thresh && ix->nlevels > 0 && ix->have_locality, ANNB_ESTATE,
+                 "locality, set_model (with error tables) and row_thresh must run before select");
+    ANNB_REQUIRE(n_refine >= 0 && lookahead >= 1, ANNB_EINVAL, "bad n_refine / lookahead");
+    annb_ctx *c = ix->ctx;
+    ANNB_CUDA(cudaSetDevice(c->device));
+    ix->n_sel = ix->n_next = 0;
+    const int64_t nq = (ix->NT - ix->P.rank + ix->P.world - 1) / ix->P.world;
+    const int64_t n_nc = ix->n_not_computed();  // exact: candidates - anchor pairs - known
+    const int64_t want1 = n_refine, want2 = n_refine * lookahead;
+    // annchor.py:444-457: n_refine >= len(prob) -> everything is candidate AND next;
+    // n_refine*lookahead >= len(prob) -> large_part is everything
+    const int64_t sel_target = std::min<int64_t>(want1, n_nc);
+    const int64_t tot_target = want1 >= n_nc ? n_nc : std::min<int64_t>(want2, n_nc);
+
+    std::vector<uint32_t> h1, h2;
+    unsigned long long c1v[3] = {0, 0, 0}, c2v[3] = {0, 0, 0};
+    int floor_level = 0;
+    int64_t cap = 0;
+    if (tot_target >= n_nc) {
+        floor_level = 0;  // everything is taken: no pilot needed
+        cap = n_nc + 1024;
+    } else {
+        // pass 1: level histogram -- exact for small problems, a pilot over every s-th tile otherwise
+        const int stride = nq > 8192 ? (int)(nq / 2048) : 1;
+        ANNB_TRY(run_score(ix, 0, stride, false, 0, h1, c1v));
+        if (stride == 1) {
+            int64_t cum = 0;
+            floor_level = level_cut(h1, 0, tot_target, &cum);
+            cap = cum + 1024;
+        } else {
+            const double scale = (double)nq / (double)((nq + stride - 1) / stride);
+            const double target = 1.5 * (double)tot_target + 65536.0;
+            double cum = 0;
+            int L = ix->nlevels - 1;
+            for (; L > 0; --L) {
+                cum += (double)h1[L] * scale;
+                if (cum >= target) break;
+            }
+            if (L == 0) cum += (double)h1[0] * scale;
+            floor_level = L;
+            cap = (int64_t)(cum * 1.5) + (1 << 20);
+            if (cap > n_nc + 1024) cap = n_nc + 1024;
+        }
+    }
+    // pass 2: exact histogram of the levels >= floor, with emission; re-plan if the pilot was off
+    int64_t E = 0;
+    for (int attempt = 0;; ++attempt) {
+        ANNB_REQUIRE(attempt < 4, ANNB_ESTATE, "selection did not converge");
+        ANNB_TRY(run_score(ix, floor_level, 1, true, cap, h2, c2v));
+        E = (int64_t)c2v[0];
+        int64_t cum = 0;
+        for (int L = floor_level; L < ix->nlevels; ++L) cum += h2[L];
+        if (E > cap) {
+            // more pairs above the floor than planned: the histogram above it is exact, re-cut exactly
+            int64_t cum2 = 0;
+            floor_level = level_cut(h2, floor_level, tot_target, &cum2);
+            cap = cum2 + 1024;
+            continue;
+        }
+        if (floor_level > 0 && cum < tot_target) {
+            // floor too high: exact full histogram, exact floor
+            ANNB_TRY(run_score(ix, 0, 1, false, 0, h1, c1v));
+            int64_t cum2 = 0;
+            floor_level = level_cut(h1, 0, tot_target, &cum2);
+            cap = cum2 + 1024;
+            continue;
+        }
+        break;
+    }
+    // ---- cut the emitted list: level first, mixed pair key among ties (deterministic) ----
+    int cl1 = ix->nlevels, cl2 = ix->nlevels;
+    int64_t t1 = 0, t2 = 0;
+    {
+        int64_t above = 0;
+        for (int L = ix->nlevels - 1; L >= floor_level; --L) {
+            if (cl1 == ix->nlevels && sel_target > 0 && above + (int64_t)h2[L] >= sel_target) {
+                cl1 = L;
+                t1 = sel_target - above;
+            }
+            if (cl2 == ix->nlevels && tot_target > 0 && above + (int64_t)h2[L] >= tot_target) {
+                cl2 = L;
+                t2 = tot_target - above;
+            }
+            above += h2[L];
+        }
+        ANNB_REQUIRE(above >= tot_target, ANNB_ESTATE,
+                     "scoring sweep found %lld pairs, %lld expected (n_not_computed=%lld)", (long long)above,
+                     (long long)tot_target, (long long)n_nc);
+    }
+    uint64_t thr1 = ~0ull, thr2 = ~0ull;
+    if (cl1 < ix->nlevels && t1 < (int64_t)h2[cl1]) ANNB_TRY(tie_threshold(ix, E, cl1, h2[cl1], t1, &thr1));
+    if (cl2 < ix->nlevels && t2 < (int64_t)h2[cl2]) ANNB_TRY(tie_threshold(ix, E, cl2, h2[cl2], t2, &thr2));
+    const int64_t cap_sel = sel_target + 16, cap_next = tot_target - sel_target + 16;
+    ANNB_TRY(ix->sel_i.ensure((size_t)cap_sel * 4));
+    ANNB_TRY(ix->sel_j.ensure((size_t)cap_sel * 4));
+    ANNB_TRY(ix->nxt_i.ensure((size_t)cap_next * 4));
+    ANNB_TRY(ix->nxt_j.ensure((size_t)cap_next * 4));
+    ANNB_CUDA(cudaMemsetAsync(ix->counters.p, 0, 64, c->stream));
+    if (E > 0)
+        ANNB_LAUNCH(partition_emitted_kernel, grid_for_n(c, E), 256, 0, c->stream,
+                    ix->emit_key.as<uint64_t>(), ix->emit_lvl.as<uint16_t>(), E, cl1, thr1, cl2, thr2,
+                    ix->sel_i.as<int32_t>(), ix->sel_j.as<int32_t>(), ix->nxt_i.as<int32_t>(),
+                    ix->nxt_j.as<int32_t>(), ix->counters.as<unsigned long long>(), cap_sel, cap_next);
+    unsigned long long pc[2] = {0, 0};
+    ANNB_CUDA(cudaMemcpyAsync(pc, ix->counters.p, 16, cudaMemcpyDeviceToHost, c->stream));
+    ANNB_CUDA(cudaStreamSynchronize(c->stream));
+    ANNB_REQUIRE((int64_t)pc[0] == sel_target && (int64_t)pc[1] == tot_target - sel_target, ANNB_ESTATE,
+                 "selection cut produced %llu/%llu pairs for targets %lld/%lld", pc[0], pc[1],
+                 (long long)sel_target, (long long)(tot_target - sel_target));
+    ix->n_sel = (int64_t)pc[0];
+    ix->n_next = (int64_t)pc[1];
+    if (n_selected) *n_selected = ix->n_sel;
+    if (n_next) *n_next = ix->n_next;
+    return ANNB_OK;
+}
+
+ANNB_API int annb_index_get_selected(annb_index *ix, int64_t *ij_sel, int64_t *ij_next)
+{
+    ANNB_REQUIRE(ix != nullptr, ANNB_EINVAL, "index is NULL");
+    annb_ctx *c = ix->ctx;
+    ANNB_CUDA(cudaSetDevice(c->device));
+    auto fetch = [&](const DevBuf &bi, const DevBuf &bj, int64_t m, int64_t *out) -> int {
+        if (!out || m == 0) return ANNB_OK;
+        std::vector<int32_t> hi(m), hj(m);
+        ANNB_CUDA(cudaMemcpyAsync(hi.data(), bi.p, (size_t)m * 4, cudaMemcpyDeviceToHost, c->stream));
+        ANNB_CUDA(cudaMemcpyAsync(hj.data(), bj.p, (size_t)m * 4, cudaMemcpyDeviceToHost, c->stream));
+        ANNB_CUDA(cudaStreamSynchronize(c->stream));
+        for (int64_t p = 0; p < m; ++p) {
+            out[2 * p] = hi[p];
+            out[2 * p + 1] = hj[p];
+        }
+        return ANNB_OK;
+    };
+    ANNB_TRY(fetch(ix->sel_i, ix->sel_j, ix->n_sel, ij_sel));
+    ANNB_TRY(fetch(ix->nxt_i, ix->nxt_j, ix->n_next, ij_next));
+    return ANNB_OK;
+}
+
+ANNB_API int annb_index_refine_selected(annb_index *ix, int64_t *n_evals)
+{
+    ANNB_REQUIRE(ix != nullptr, ANNB_EINVAL, "index is NULL");
+    annb_ctx *c = ix->ctx;
+    ANNB_CUDA(cudaSetDevice(c->device));
+    const int64_t m = ix->n_sel;
+    if (n_evals) *n_evals = m;
+    if (m) {
+        ANNB_TRY(ix->t3.ensure((size_t)m * 4));
+        ANNB_TRY(pair_dists_f32_perm(c, ix->ds, ix->metric, ix->sel_i.as<int32_t>(),
+                                     ix->sel_j.as<int32_t>(), nullptr, m, ix->t3.as<float>()));
+        ANNB_TRY(hash_insert(ix, ix->sel_i.as<int32_t>(), ix->sel_j.as<int32_t>(), ix->t3.as<float>(),
+                             nullptr, KIND_KNOWN, m));
+        ix->n_known += m;
+    }
+    if (ix->has_forced) {
+        // the -1 marks of guarantee_nmin do not survive the iteration (annchor.py:374-379)
+        ANNB_LAUNCH(hash_retire_forced_kernel, grid_for_n(c, (int64_t)ix->hcap), 256, 0, c->stream,
+                    ix->htab.as<HashSlot>(), ix->hcap);
+        ix->has_forced = false;
+    }
+    ix->n_sel = 0;
+    return ANNB_OK;
+}
+
+static int build_known_csr(annb_index *ix)
+{
+    annb_ctx *c = ix->ctx;
+    const int64_t n = ix->n;
+    ANNB_TRY(ix->kdeg.ensure((size_t)(n + 1) * 4));
+    ANNB_TRY(ix->kptr.ensure((size_t)(n + 1) * 8));
+    ANNB_CUDA(cudaMemsetAsync(ix->kdeg.p, 0, (size_t)(n + 1) * 4, c->stream));
+    ANNB_LAUNCH(known_degree_kernel, grid_for_n(c, (int64_t)ix->hcap), 256, 0, c->stream,
+                ix->htab.as<HashSlot>(), ix->hcap, ix->kdeg.as<int32_t>());
+    ANNB_LAUNCH(exclusive_scan_kernel, 1, 1024, 0, c->stream, ix->kdeg.as<int32_t>(),
+                ix->kptr.as<int64_t>(), n);
+    int64_t total = 0;
+    ANNB_CUDA(cudaMemcpyAsync(&total, ix->kptr.as<int64_t>() + n, 8, cudaMemcpyDeviceToHost, c->stream));
+    ANNB_CUDA(cudaStreamSynchronize(c->stream));
+    ix->csr_entries = total;
+    ANNB_TRY(ix->kids.ensure((size_t)(total + 1) * 4));
+    ANNB_TRY(ix->kds.ensure((size_t)(total + 1) * 4));
+    ANNB_CUDA(cudaMemsetAsync(ix->kdeg.p, 0, (size_t)(n + 1) * 4, c->stream));
+    ANNB_LAUNCH(known_fill_kernel, grid_for_n(c, (int64_t)ix->hcap), 256, 0, c->stream,
+                ix->htab.as<HashSlot>(), ix->hcap, ix->kptr.as<int64_t>(), ix->kdeg.as<int32_t>(),
+                ix->kids.as<int32_t>(), ix->kds.as<float>());
+    const int grid = (int)std::min<int64_t>(n, (int64_t)c->num_sms * 8);
+    ANNB_LAUNCH(sort_rows_kernel, grid, 256, 0, c->stream, ix->kptr.as<int64_t>(), n,
+                ix->kids.as<int32_t>(), ix->kds.as<float>());
+    return ANNB_OK;
+}
+
+ANNB_API int annb_index_update_bounds(annb_index *ix, int64_t *n_updated)
+{
+    ANNB_REQUIRE(ix != nullptr, ANNB_EINVAL, "index is NULL");
+    annb_ctx *c = ix->ctx;
+    ANNB_CUDA(cudaSetDevice(c->device));
+    const int64_t m = ix->n_next;
+    if (n_updated) *n_updated = 0;
+    if (m == 0) return ANNB_OK;
+    ANNB_TRY(build_known_csr(ix));
+    ANNB_TRY(ix->t0.ensure((size_t)m * 4));
+    ANNB_TRY(ix->t1.ensure((size_t)m * 4));
+    ANNB_TRY(ix->t2.ensure((size_t)m));
+    ANNB_TRY(ix->t3.ensure((size_t)m * 4));
+    ANNB_TRY(ix->t4.ensure((size_t)m * 4));
+    ANNB_TRY(ix->t5.ensure((size_t)m * 4));
+    ANNB_TRY(ix->t6.ensure((size_t)m * 4));
+    const View V = ix->view();
+    ANNB_LAUNCH(tighten_kernel, c->num_sms * 8, 256, 0, c->stream, V, ix->kptr.as<int64_t>(),
+                ix->kids.as<int32_t>(), ix->kds.as<float>(), ix->nxt_i.as<int32_t>(),
+                ix->nxt_j.as<int32_t>(), m, ix->t0.as<float>(), ix->t1.as<float>(), ix->t2.as<uint8_t>());
+    ANNB_CUDA(cudaMemsetAsync(ix->counters.p, 0, 64, c->stream));
+    ANNB_LAUNCH(compact_improved_kernel, grid_for_n(c, m), 256, 0, c->stream, ix->nxt_i.as<int32_t>(),
+                ix->nxt_j.as<int32_t>(), ix->t0.as<float>(), ix->t1.as<float>(), ix->t2.as<uint8_t>(), m,
+                ix->t3.as<int32_t>(), ix->t4.as<int32_t>(), ix->t5.as<float>(), ix->t6.as<float>(),
+                ix->counters.as<unsigned long long>());
+    unsigned long long k = 0;
+    ANNB_CUDA(cudaMemcpyAsync(&k, ix->counters.p, 8, cudaMemcpyDeviceToHost, c->stream));
+    ANNB_CUDA(cudaStreamSynchronize(c->stream));
+    ANNB_TRY(hash_insert(ix, ix->t3.as<int32_t>(), ix->t4.as<int32_t>(), ix->t5.as<float>(),
+                         ix->t6.as<float>(), KIND_TIGHT, (int64_t)k));
+    ix->n_tight += (int64_t)k;
+    if (n_updated) *n_updated = (int64_t)k;
+    ix->n_next = 0;
+    return ANNB_OK;
+}
+
+ANNB_API int annb_index_neighbor_graph(annb_index *ix, int64_t *idx, double *dist)
+{
+    ANNB_REQUIRE(ix && idx && dist, ANNB_EINVAL, "NULL argument");
+    ANNB_REQUIRE(ix->have_anchors, ANNB_ESTATE, "anchors not computed yet");
+    annb_ctx *c = ix->ctx;
+    ANNB_CUDA(cudaSetDevice(c->device));
+    const int64_t n = ix->n;
+    const int nn = ix->P.n_neighbors;
+    ANNB_TRY(build_known_csr(ix));
+    ANNB_TRY(ix->t0.ensure((size_t)n * nn * 8));
+    ANNB_TRY(ix->t1.ensure((size_t)n * nn * 8));
+    ANNB_CUDA(cudaMemsetAsync(ix->counters.p, 0, 64, c->stream));
+    const int grid = (int)std::min<int64_t>(n, (int64_t)c->num_sms * 8);
+    ANNB_LAUNCH(neighbor_graph_kernel, grid, 256, 0, c->stream, ix->view(), ix->D64.as<double>(),
+                ix->A_dev.as<int32_t>(), (int)ix->A_host.size(), ix->kptr.as<int64_t>(),
+                ix->kids.as<int32_t>(), ix->kds.as<float>(), ix->t0.as<int64_t>(), ix->t1.as<double>(),
+                ix->counters.as<int32_t>());
+    ANNB_CUDA(cudaMemcpyAsync(idx, ix->t0.p, (size_t)n * nn * 8, cudaMemcpyDeviceToHost, c->stream));
+    ANNB_CUDA(cudaMemcpyAsync(dist, ix->t1.p, (size_t)n * nn * 8, cudaMemcpyDeviceToHost, c->stream));
+    ANNB_CUDA(cudaStreamSynchronize(c->stream));
+    return ANNB_OK;
+}
+
+ANNB_API int annb_index_stats(annb_index *ix, int64_t *out, int64_t m)
+{
+    ANNB_REQUIRE(ix && out, ANNB_EINVAL, "NULL argument");
+    const int64_t v[8] = {ix->pairs_swept, ix->n_known,        ix->n_tight,        ix->sweeps,
+                          ix->n_candidates, (int64_t)ix->hcap, ix->n_anchor_pairs, ix->n_not_computed()};
+    for (int64_t k = 0; k < m && k < 8; ++k) out[k] = v[k];
+    return ANNB_OK;
+}
+
+ANNB_API int annb_index_last_sweep(annb_index *ix, float *ms, int64_t *pairs)
+{
+    ANNB_REQUIRE(ix != nullptr, ANNB_EINVAL, "index is NULL");
+    if (ms) *ms = ix->last_sweep_ms;
+    if (pairs) *pairs = ix->last_sweep_pairs;
+    return ANNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// sampler support (annchor/samplers.py:75-140, annchor/utils.py:543-578): a uniform pool of the
+// not-computed candidate pairs with their dad.  When there are at most max_pool such pairs the
+// pool is ALL of them, in any order (the host sorts by (i, j) = the reference's IJs order and can
+// then reproduce the reference's sampler exactly); otherwise a hash-selected uniform sub-sample.
+// ---------------------------------------------------------------------------------------------
+ANNB_API int annb_index_sample_pool(annb_index *ix, uint64_t seed, int64_t max_pool, int64_t *n_pool,
+                                    int64_t *n_not_computed, int *exact)
+{
+    ANNB_REQUIRE(ix && n_pool, ANNB_EINVAL, "NULL argument");
+    ANNB_REQUIRE(ix->have_locality, ANNB_ESTATE, "locality must run before sampling");
+    ANNB_REQUIRE(max_pool >= 1024, ANNB_EINVAL, "max_pool too small");
+    annb_ctx *c = ix->ctx;
+    ANNB_CUDA(cudaSetDevice(c->device));
+    const int64_t n_nc = ix->n_not_computed();
+    if (n_not_computed) *n_not_computed = n_nc;
+    const bool all = n_nc <= max_pool;
+    if (exact) *exact = all ? 1 : 0;
+    ix->n_pool = 0;
+    *n_pool = 0;
+    if (n_nc <= 0) return ANNB_OK;
+    SampleArgs A;
+    A.V = ix->view();
+    A.seed = (uint32_t)(mix64(seed) >> 32);
+    double frac = all ? 1.0 : 0.8 * (double)max_pool / (double)n_nc;
+    for (int attempt = 0;; ++attempt) {
+        ANNB_REQUIRE(attempt < 4, ANNB_ESTATE, "sampler pool did not fit");
+        A.thr = frac >= 1.0 ? 0xffffffffu : (uint32_t)(frac * 4294967295.0);
+        const int64_t cap = all ? n_nc + 1024 : max_pool + max_pool / 4;
+        ANNB_TRY(ix->pool_key.ensure((size_t)cap * 8));
+        ANNB_TRY(ix->pool_dad.ensure((size_t)cap * 4));
+        A.out_key = ix->pool_key.as<uint64_t>();
+        A.out_dad = ix->pool_dad.as<float>();
+        A.out_cap = (unsigned long long)cap;
+        ANNB_CUDA(cudaMemsetAsync(ix->counters.p, 0, 64, c->stream));
+        A.counter = ix->counters.as<unsigned long long>();
+        A.rank = ix->P.rank;
+        A.world = ix->P.world;
+        ANNB_TRY(launch_sample_sweep(c, A));
+        ix->sweeps += 1;
+        unsigned long long got = 0;
+        ANNB_CUDA(cudaMemcpyAsync(&got, ix->counters.p, 8, cudaMemcpyDeviceToHost, c->stream));
+        ANNB_CUDA(cudaStreamSynchronize(c->stream));
+        if ((int64_t)got <= cap) {
+            ix->n_pool = (int64_t)got;
+            break;
+        }
+        ANNB_REQUIRE(!all, ANNB_ESTATE, "pool sweep found %llu pairs but %lld were expected", got,
+                     (long long)n_nc);
+        frac *= 0.7 * (double)cap / (double)got;
+    }
+    if (all && ix->P.world == 1)
+        ANNB_REQUIRE(ix->n_pool == n_nc, ANNB_ESTATE,
+                     "pool sweep found %lld not-computed candidates, bookkeeping says %lld",
+                     (long long)ix->n_pool, (long long)n_nc);
+    *n_pool = ix->n_pool;
+    return ANNB_OK;
+}
+
+ANNB_API int annb_index_get_pool(annb_index *ix, int64_t *ij, double *dad)
+{
+    ANNB_REQUIRE(ix && ij && dad, ANNB_EINVAL, "NULL argument");
+    annb_ctx *c = ix->ctx;
+    ANNB_CUDA(cudaSetDevice(c->device));
+    const int64_t m = ix->n_pool;
+    if (m == 0) return ANNB_OK;
+    std::vector<uint64_t> k(m);
+    std::vector<float> d(m);
+    ANNB_CUDA(cudaMemcpyAsync(k.data(), ix->pool_key.p, (size_t)m * 8, cudaMemcpyDeviceToHost, c->stream));
+    ANNB_CUDA(cudaMemcpyAsync(d.data(), ix->pool_dad.p, (size_t)m * 4, cudaMemcpyDeviceToHost, c->stream));
+    ANNB_CUDA(cudaStreamSynchronize(c->stream));
+    for (int64_t p = 0; p < m; ++p) {
+        ij[2 * p] = (int64_t)(k[p] >> 32);
+        ij[2 * p + 1] = (int64_t)(k[p] & 0xffffffffu);
+        dad[p] = d[p];
+    }
+    return ANNB_OK;
+}

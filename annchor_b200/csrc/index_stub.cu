@@ -1,25 +1,8 @@
-// temporary stubs (replaced by index.cu)
+// stubs for entry points that are declared in include/annb.h but not built yet
 #include "common.cuh"
 using namespace annb;
-#define STUB(name, ...) ANNB_API int name(__VA_ARGS__) { set_error(#name " not implemented yet"); return ANNB_ESTATE; }
-STUB(annb_index_create, annb_ctx *, const annb_dataset *, int, const annb_index_params *, annb_index **)
-STUB(annb_index_destroy, annb_index *)
-STUB(annb_index_maxmin, annb_index *, int64_t, int64_t *)
-STUB(annb_index_set_anchors, annb_index *, const int64_t *, int64_t, const double *)
-STUB(annb_index_get_D, annb_index *, double *)
-STUB(annb_index_locality, annb_index *, int64_t *, int64_t *)
-STUB(annb_index_dad_order_stats, annb_index *, const int64_t *, int64_t, double *, int64_t *)
-STUB(annb_index_sample, annb_index *, const double *, int64_t, const int64_t *, uint64_t, int64_t *, int64_t *, double *)
-STUB(annb_index_add_known, annb_index *, const int64_t *, const double *, int64_t)
-STUB(annb_index_eval_pairs, annb_index *, const int64_t *, int64_t, double *)
-STUB(annb_index_set_model, annb_index *, const double *, const double *, const double *, int64_t, const double *, const int64_t *)
-STUB(annb_index_row_thresh, annb_index *, double *)
-STUB(annb_index_guarantee_nmin, annb_index *, int64_t, int64_t *)
-STUB(annb_index_select, annb_index *, int64_t, int64_t, int64_t *, int64_t *)
-STUB(annb_index_get_selected, annb_index *, int64_t *, int64_t *)
-STUB(annb_index_refine_selected, annb_index *, int64_t *)
-STUB(annb_index_update_bounds, annb_index *, int64_t *)
-STUB(annb_index_neighbor_graph, annb_index *, int64_t *, double *)
-STUB(annb_index_stats, annb_index *, int64_t *, int64_t)
-STUB(annb_index_last_sweep, annb_index *, float *, int64_t *)
-STUB(annb_bruteforce_knn, annb_ctx *, const annb_dataset *, int, int64_t, int64_t *, double *)
+ANNB_API int annb_bruteforce_knn(annb_ctx *, const annb_dataset *, int, int64_t, int64_t *, double *)
+{
+    set_error("annb_bruteforce_knn not implemented yet");
+    return ANNB_ESTATE;
+}

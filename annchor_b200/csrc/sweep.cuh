@@ -1,0 +1,234 @@
+// sweep.cuh -- building blocks shared by the tile-sweep kernels (thresh / score / sample).
+//
+// A tile is 128 x 128 pairs handled by one 256-thread CTA; each thread owns an 8 x 8 micro-tile:
+// rows {4*ty..4*ty+3} U {64+4*ty..}, columns {4*tx..4*tx+3} U {64+4*tx..}, (ty, tx) = (tid/16, tid%16),
+// so every shared-memory read of anchor-distance rows is a conflict-free 128-bit access
+// (8 consecutive threads cover 128 contiguous bytes; the two ty values in a warp broadcast).
+// A warp therefore owns 16 whole rows of the tile ({8w..8w+7} U {64+8w..64+8w+7}) x all 128 columns.
+//
+// Two-phase tile processing keeps the hot loop tiny:
+//   phase 1 (every pair, fully unrolled, registers only): triangle-inequality bounds over the
+//            anchors -- FADD, FMNMX(|.|), FADD, FMNMX per anchor and pair, issue-bound -- then the
+//            clipped stratified-linear prediction (dad from two shared-memory look-ups, bin by
+//            compares against the doubled edges, one 128-bit coefficient fetch, 3 FFMA, clip) and
+//            one compare against the pair's cut-off.  Pairs that beat the cut-off OR carry a flag
+//            bit (exactly known / tightened / forced: their RefineApprox is not the plain
+//            prediction) are compacted with warp ballots into a per-warp queue in shared memory;
+//   phase 2 (survivors only, rolled loop, one survivor per lane): candidate test, known-pair
+//            look-up, label, probability, list insertion / emission.
+// In high dimension the anchor lower bound alone is a weak filter (distances concentrate: on the
+// d=128 benchmark 75 % of all pairs have lb < thresh), hence the prediction is part of phase 1.
+#pragma once
+#include "index.cuh"
+
+namespace annb {
+
+constexpr int QCAP = 256;  // survivors per warp per step: 8 pairs x 32 lanes (one micro-tile row)
+
+struct __align__(4) Survivor {
+    float lb, ub;
+    uint32_t ids;  // li | lj << 8
+};
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// stage the anchor-distance rows and point metadata of tile t
+__device__ __forceinline__ void load_point_tile(const View &V, int t, float *sD, PointMeta *sM)
+{
+    const int tid = threadIdx.x;
+    for (int idx = tid; idx < V.na * 32; idx += blockDim.x) {
+        const int a = idx >> 5, q = idx & 31;
+        cp_async16(sD + a * SROW + q * 4, V.D32 + (int64_t)a * V.npad + (int64_t)t * TILE + q * 4);
+    }
+    if (tid < TILE) cp_async16(sM + tid, V.meta + (int64_t)t * TILE + tid);
+}
+__device__ __forceinline__ void load_bitmap_tile(const View &V, int ti, int tj, uint32_t *sB)
+{
+    const int lo = ti < tj ? ti : tj, hi = ti < tj ? tj : ti;
+    const uint32_t *src = V.bitmap + tile_index(lo, hi, V.T) * BITMAP_WORDS;
+    const int tid = threadIdx.x;
+    if (tid >= 128) cp_async16(sB + (tid - 128) * 4, src + (tid - 128) * 4);
+}
+
+__device__ __forceinline__ int micro_off(int t4, int k)  // local index of the k-th of 8 rows/cols
+{
+    return (k < 4) ? (t4 * 4 + k) : (64 + t4 * 4 + (k - 4));
+}
+
+// triangle-inequality bounds for the 8 x 8 micro-tile (get_bounds_njit_ijs, utils.py:274-301)
+__device__ __forceinline__ void bounds_microtile(const float *__restrict__ sDi,
+                                                 const float *__restrict__ sDj, int na, int ty,
+                                                 int tx, float (&lb)[8][8], float (&ub)[8][8])
+{
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            lb[r][c] = 0.0f;
+            ub[r][c] = INFINITY;
+        }
+#pragma unroll 2
+    for (int a = 0; a < na; ++a) {
+        const float4 i0 = *reinterpret_cast<const float4 *>(sDi + a * SROW + ty * 4);
+        const float4 i1 = *reinterpret_cast<const float4 *>(sDi + a * SROW + 64 + ty * 4);
+        const float4 j0 = *reinterpret_cast<const float4 *>(sDj + a * SROW + tx * 4);
+        const float4 j1 = *reinterpret_cast<const float4 *>(sDj + a * SROW + 64 + tx * 4);
+        const float di[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+        const float dj[8] = {j0.x, j0.y, j0.z, j0.w, j1.x, j1.y, j1.z, j1.w};
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                lb[r][c] = fmaxf(lb[r][c], fabsf(di[r] - dj[c]));
+                ub[r][c] = fminf(ub[r][c], di[r] + dj[c]);
+            }
+    }
+}
+
+// shared-memory copy of the regression model in the form phase 1 consumes
+struct __align__(16) TileModel {
+    float4 cf[MAX_BINS];   // (c0, c1, c2 / 2, intercept) per bin (regressors.py:39-67)
+    float e2[MAX_BINS];    // 2 * interior edge k (k = 1..nb-1), +inf beyond: compared against 2 * dad
+};
+
+__device__ __forceinline__ void build_tile_model(const Model &M, TileModel *tm)
+{
+    const int t = threadIdx.x;
+    if (t < MAX_BINS) {
+        const bool live = t < M.nb;
+        tm->cf[t] = live ? make_float4(M.c0[t], M.c1[t], 0.5f * M.c2[t], M.ic[t]) : make_float4(0, 0, 0, 0);
+        tm->e2[t] = (t >= 1 && t < M.nb) ? 2.0f * M.edge[t] : INFINITY;
+    }
+}
+
+// s = 2 * dad.  Regression bin (lo, hi]: number of interior edges strictly below dad (regressors.py:85-87)
+__device__ __forceinline__ int reg_bin2(const TileModel *tm, float s)
+{
+    int b = 0;
+#pragma unroll
+    for (int k = 1; k < MAX_BINS; ++k) b += (s > tm->e2[k]);
+    return b;
+}
+// error label / sampler bin: closed [lo, hi] with later bins winning (error_predictors.py:63-66)
+__device__ __forceinline__ int err_label2(const TileModel *tm, float s)
+{
+    int b = 0;
+#pragma unroll
+    for (int k = 1; k < MAX_BINS; ++k) b += (s >= tm->e2[k]);
+    return b;
+}
+// clip(lb*c0 + ub*c1 + dad*c2 + icpt, lb, ub)  (annchor.py:356-363); identical code in both phases
+__device__ __forceinline__ float predict_clip2(const TileModel *tm, float lb, float ub, float s)
+{
+    const float4 cf = tm->cf[reg_bin2(tm, s)];
+    const float y = fmaf(lb, cf.x, fmaf(ub, cf.y, fmaf(s, cf.z, cf.w)));
+    return fminf(fmaxf(y, lb), ub);
+}
+
+// the two 32-bit words of a tile bitmap row that hold this thread's 8 columns
+// (columns 4*tx..4*tx+3 sit in word tx>>3, columns 64+4*tx.. in word 2 + (tx>>3), same bit offsets)
+__device__ __forceinline__ void flag_words(const uint32_t *sB, int row, int tx, uint32_t &w0, uint32_t &w1)
+{
+    w0 = sB[row * 4 + (tx >> 3)] >> ((tx & 7) * 4);
+    w1 = sB[row * 4 + 2 + (tx >> 3)] >> ((tx & 7) * 4);
+}
+
+// transpose a 128 x 128 bit tile (rows x 4 words) inside shared memory: dst[c][r] = src[r][c]
+__device__ __forceinline__ void transpose_bitmap(const uint32_t *src, uint32_t *dst)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int combo = warp; combo < 16; combo += nwarps) {
+        const int w = combo >> 2, q = combo & 3;  // source rows 32w..32w+31, source column word q
+        const uint32_t x = src[(w * 32 + lane) * 4 + q];
+#pragma unroll 4
+        for (int k = 0; k < 32; ++k) {
+            const uint32_t m = __ballot_sync(0xffffffffu, (x >> k) & 1u);
+            if (lane == 0) dst[(q * 32 + k) * 4 + w] = m;
+        }
+    }
+}
+
+// ballot-compact one micro-tile row's survivors into the warp queue; returns the new queue length
+__device__ __forceinline__ int stage_row(Survivor *q, int qn, const float (&lb)[8], const float (&ub)[8],
+                                         const bool (&keep)[8], int li, int tx, int lane)
+{
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const unsigned m = __ballot_sync(0xffffffffu, keep[c]);
+        if (keep[c]) {
+            Survivor s;
+            s.lb = lb[c];
+            s.ub = ub[c];
+            s.ids = (uint32_t)li | ((uint32_t)micro_off(tx, c) << 8);
+            q[qn + __popc(m & ((1u << lane) - 1))] = s;
+        }
+        qn += __popc(m);
+    }
+    return qn;
+}
+
+// candidate test (get_check / adjust_check, utils.py:437-491): shared nearest-anchor count
+// >= min of the two rows' thresholds
+__device__ __forceinline__ bool is_candidate(const PointMeta &a, const PointMeta &b)
+{
+    const int t = a.loc_t < b.loc_t ? a.loc_t : b.loc_t;
+    return __popcll(a.amask & b.amask) >= t;
+}
+
+// flag bit of the canonical pair (lo < hi) inside its tile's bitmap
+__device__ __forceinline__ bool flag_bit(const uint32_t *sB, int gi, int gj)
+{
+    const int lo = gi < gj ? gi : gj, hi = gi < gj ? gj : gi;
+    const int r = lo & (TILE - 1), c = hi & (TILE - 1);
+    return (sB[r * 4 + (c >> 5)] >> (c & 31)) & 1u;
+}
+
+struct PairVal {
+    float v;        // RefineApprox value (exact if computed, clipped prediction otherwise, -1 if forced)
+    float dad;      // 2 * double anchor distance
+    bool computed;  // anchor pair or exactly evaluated (not_computed_mask == False)
+};
+
+// RefineApprox of one candidate pair as annchor.py:345-380 leaves it.
+__device__ __forceinline__ PairVal pair_value(const View &V, const TileModel *tm, float lb, float ub,
+                                              int li, int lj, int gi, int gj, const PointMeta &pi,
+                                              const PointMeta &pj, const float *sDi, const float *sDj,
+                                              bool flagged)
+{
+    PairVal out;
+    const float s = sDi[pj.cA * SROW + li] + sDj[pi.cA * SROW + lj];  // 2 * dad (utils.py:378-380)
+    out.dad = s;
+    const bool anchorpair = (pi.slot >= 0) | (pj.slot >= 0);
+    out.computed = anchorpair;
+    if (flagged) {
+        float a = 0.0f, b = 0.0f;
+        const uint32_t lo = gi < gj ? gi : gj, hi = gi < gj ? gj : gi;
+        const uint32_t kind = hash_lookup(V, pair_key(lo, hi), a, b);
+        if (kind == KIND_KNOWN) {
+            out.v = a;
+            out.computed = true;
+            return out;
+        }
+        if (kind == KIND_TIGHT) {  // update_anchor_points, annchor.py:503-510
+            lb = fmaxf(lb, a);
+            ub = fminf(ub, b);
+        } else if (kind == KIND_FORCED) {  // guarantee_nmin, utils.py:619
+            out.v = -1.0f;
+            return out;
+        }
+    }
+    out.v = predict_clip2(tm, lb, ub, s);
+    if (!V.is_metric && anchorpair) {
+        // annchor.py:368-372: anchor distances written explicitly; the later anchor in A wins
+        out.v = (pj.slot > pi.slot) ? sDi[pj.slot * SROW + li] : sDj[pi.slot * SROW + lj];
+    }
+    return out;
+}
+
+}  // namespace annb

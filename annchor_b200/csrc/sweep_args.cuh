@@ -1,0 +1,54 @@
+// sweep_args.cuh -- kernel argument blocks of the tile sweeps (shared by sweep_*.cu and index.cu).
+#pragma once
+#include "index.cuh"
+
+namespace annb {
+
+struct ThreshArgs {
+    View V;
+    Model M;
+    int k1;            // nn + 1
+    int k2;            // nmin + 1 (0 = no second list)
+    float *thresh;     // [npad]
+    float *l2val;      // [n * k2]
+    int32_t *l2id;     // [n * k2]
+    int rank, world;
+};
+
+struct ScoreArgs {
+    View V;
+    Model M;
+    const float *thresh;      // [npad]
+    const float *errs;        // concatenated sorted error tables (global, L1-resident)
+    const uint16_t *ranktab;  // level of (label, r): ranktab[eoff[label] + label + r], r in [0, len]
+    int nlevels;
+    int floor_level;          // histogram / emit only levels >= floor_level
+    float efloor[MAX_BINS];   // p > efloor[label]  <=>  level(label, p) >= floor_level
+    float ef_min;             // min over labels of efloor (phase-1 margin); -inf disables the filter
+    int has_forced;           // FORCED marks exist (iteration 0): flagged pairs always go to phase 2
+    uint32_t *hist;           // [nlevels]
+    unsigned long long *counters;  // [0] emitted, [1] not-computed candidates seen in phase 2, [2] pairs swept
+    uint64_t *emit_key;
+    uint16_t *emit_lvl;
+    unsigned long long emit_cap;
+    int64_t q_begin, q_end;   // range of this rank's tile sequence
+    int q_stride;             // 1 = every tile; s > 1 = pilot over every s-th tile
+    int rank, world;
+};
+
+struct SampleArgs {
+    View V;
+    uint32_t thr;
+    uint32_t seed;
+    uint64_t *out_key;
+    float *out_dad;
+    unsigned long long out_cap;
+    unsigned long long *counter;
+    int rank, world;
+};
+
+int launch_thresh_sweep(annb_ctx *c, const ThreshArgs &A);
+int launch_score_sweep(annb_ctx *c, const ScoreArgs &A);
+int launch_sample_sweep(annb_ctx *c, const SampleArgs &A);
+
+}  // namespace annb

@@ -1,0 +1,358 @@
+// sweep_score.cu -- K2+K3 fused scoring sweep over the upper-triangular tiles, plus the cheap
+// sub-sampling sweep that feeds the sampler.
+//
+// Scoring (annchor/annchor.py:416-457, annchor/utils.py:581-589): for every not-computed
+// candidate pair   p = max(thresh[i], thresh[j]) - RefineApprox,
+//                  prob = searchsorted(errs[label], p, 'left') / len(errs[label]).
+// prob takes at most sum(len+1) distinct values; the host ranks them once ("levels"), the
+// sweep histograms the levels >= floor exactly and emits those pairs, and the top n_refine are
+// then cut out of the emitted list -- the streaming equivalent of the reference's two
+// np.argpartition calls over a materialised prob array.
+//
+// Phase 1 keeps a pair only if  lower bound < max(thresh[i], thresh[j]) - min_label efloor,
+// which is necessary for its level to reach the floor (RefineApprox >= lower bound).
+#include "sweep.cuh"
+#include "sweep_args.cuh"
+
+namespace annb {
+
+constexpr int EMIT_CAP = 256;  // per-warp emission staging (entries)
+
+
+__device__ __forceinline__ void tile_from_index(int64_t t, int T, int &ti, int &tj)
+{
+    // invert tile_index(): largest ti with ti*T - ti*(ti-1)/2 <= t
+    const double b = 2.0 * T + 1.0;
+    int r = (int)((b - sqrt(b * b - 8.0 * (double)t)) * 0.5);
+    if (r < 0) r = 0;
+    if (r > T - 1) r = T - 1;
+    while (r > 0 && tile_index(r, r, T) > t) --r;
+    while (r + 1 < T && tile_index(r + 1, r + 1, T) <= t) ++r;
+    ti = r;
+    tj = r + (int)(t - tile_index(r, r, T));
+}
+
+// flush a warp's staged emissions with ONE global atomic
+__device__ __forceinline__ void flush_emit(const ScoreArgs &A, uint64_t *ek, uint16_t *el, int &en, int lane)
+{
+    if (en == 0) return;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(&A.counters[0], (unsigned long long)en);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    for (int k = lane; k < en; k += 32)
+        if (base + k < A.emit_cap) {
+            A.emit_key[base + k] = ek[k];
+            A.emit_lvl[base + k] = el[k];
+        }
+    __syncwarp();
+    en = 0;
+}
+
+__global__ void __launch_bounds__(256, 1) score_sweep_kernel(const ScoreArgs A)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const View &V = A.V;
+    const int na = V.na;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ty = tid >> 4, tx = tid & 15;
+    float *sD0i = reinterpret_cast<float *>(smem);
+    float *sD0j = sD0i + na * SROW;
+    float *sD1i = sD0j + na * SROW;
+    float *sD1j = sD1i + na * SROW;
+    PointMeta *sM0i = reinterpret_cast<PointMeta *>(sD1j + na * SROW);
+    PointMeta *sM0j = sM0i + TILE;
+    PointMeta *sM1i = sM0j + TILE;
+    PointMeta *sM1j = sM1i + TILE;
+    uint32_t *sB0 = reinterpret_cast<uint32_t *>(sM1j + TILE);
+    uint32_t *sB1 = sB0 + BITMAP_WORDS;
+    unsigned char *sp = reinterpret_cast<unsigned char *>(sB1 + BITMAP_WORDS);
+    Survivor *queue = reinterpret_cast<Survivor *>(sp) + warp * QCAP;
+    sp += 8 * QCAP * sizeof(Survivor);
+    uint64_t *ek = reinterpret_cast<uint64_t *>(sp) + warp * EMIT_CAP;  // per-warp emission staging
+    sp += 8 * EMIT_CAP * sizeof(uint64_t);
+    uint16_t *el = reinterpret_cast<uint16_t *>(sp) + warp * EMIT_CAP;
+    sp += 8 * EMIT_CAP * sizeof(uint16_t);
+    float *thI = reinterpret_cast<float *>(sp);  // [2][128] thresh of the row tile (double-buffered)
+    float *thJ = thI + 2 * TILE;                 // [2][128] thresh of the column tile
+    TileModel *tm = reinterpret_cast<TileModel *>(thJ + 2 * TILE);
+    uint32_t *sHist = reinterpret_cast<uint32_t *>(tm + 1);
+    build_tile_model(A.M, tm);
+
+    for (int k = tid; k < A.nlevels; k += blockDim.x) sHist[k] = 0;
+
+    // this CTA's contiguous slice of the rank's tile sequence
+    const int64_t nq = (A.q_end - A.q_begin + A.q_stride - 1) / A.q_stride;
+    const int64_t per = (nq + gridDim.x - 1) / gridDim.x;
+    const int64_t m0 = (int64_t)blockIdx.x * per, m1 = min(nq, m0 + per);
+    unsigned long long n_nc = 0, n_swept = 0;
+    int en = 0;  // staged emissions of this warp
+
+    auto tile_of = [&](int64_t m, int &ti, int &tj) {
+        const int64_t q = A.q_begin + m * A.q_stride;
+        tile_from_index(q * A.world + A.rank, V.T, ti, tj);
+    };
+    if (m0 < m1) {
+        int ti, tj;
+        tile_of(m0, ti, tj);
+        load_point_tile(V, ti, sD0i, sM0i);
+        load_point_tile(V, tj, sD0j, sM0j);
+        load_bitmap_tile(V, ti, tj, sB0);
+        if (tid < TILE) {
+            thI[tid] = A.thresh[(int64_t)ti * TILE + tid];
+            thJ[tid] = A.thresh[(int64_t)tj * TILE + tid];
+        }
+        cp_async_commit();
+    }
+    for (int64_t m = m0; m < m1; ++m) {
+        const int buf = (int)((m - m0) & 1);
+        int ti, tj;
+        tile_of(m, ti, tj);
+        cp_async_wait_all();
+        __syncthreads();
+        if (m + 1 < m1) {
+            int ni, nj;
+            tile_of(m + 1, ni, nj);
+            load_point_tile(V, ni, buf ? sD0i : sD1i, buf ? sM0i : sM1i);
+            load_point_tile(V, nj, buf ? sD0j : sD1j, buf ? sM0j : sM1j);
+            load_bitmap_tile(V, ni, nj, buf ? sB0 : sB1);
+            if (tid < TILE) {
+                thI[(buf ^ 1) * TILE + tid] = A.thresh[(int64_t)ni * TILE + tid];
+                thJ[(buf ^ 1) * TILE + tid] = A.thresh[(int64_t)nj * TILE + tid];
+            }
+            cp_async_commit();
+        }
+        const float *sDi = buf ? sD1i : sD0i, *sDj = buf ? sD1j : sD0j;
+        const PointMeta *sMi = buf ? sM1i : sM0i, *sMj = buf ? sM1j : sM0j;
+        const uint32_t *bm = buf ? sB1 : sB0;
+        const float *tI = thI + buf * TILE, *tJ = thJ + buf * TILE;
+        // ---- phase 1: bounds + clipped prediction; keep (pred < cut-off) | flagged ----
+        float lb[8][8], ub[8][8];
+        bounds_microtile(sDi, sDj, na, ty, tx, lb, ub);
+        float cj[8];
+        int cAj[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            cj[c] = tJ[micro_off(tx, c)] - A.ef_min;
+            cAj[c] = sMj[micro_off(tx, c)].cA * SROW;
+        }
+        const bool diag = ti == tj;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int li = micro_off(ty, r);
+            const float ci = tI[li] - A.ef_min;
+            const float *dj_row = sDj + sMi[li].cA * SROW;
+            uint32_t w0, w1;
+            flag_words(bm, li, tx, w0, w1);
+            bool keep[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int lj = micro_off(tx, c);
+                const float s2 = sDi[cAj[c] + li] + dj_row[lj];
+                const float y = predict_clip2(tm, lb[r][c], ub[r][c], s2);
+                const uint32_t fl = c < 4 ? (w0 >> c) : (w1 >> (c - 4));
+                keep[c] = ((y < fmaxf(ci, cj[c])) | (fl & 1u)) && (!diag || li < lj);
+            }
+            const int qn = stage_row(queue, 0, lb[r], ub[r], keep, li, tx, lane);
+            __syncwarp();
+            // ---- phase 2 ----
+            for (int e0 = 0; e0 < qn; e0 += 32) {
+                if (en > EMIT_CAP - 32) flush_emit(A, ek, el, en, lane);
+                const int e = e0 + lane;
+                int lvl = -1;
+                uint64_t key = 0;
+                if (e < qn) {
+                    const Survivor s = queue[e];
+                    const int li2 = s.ids & 0xff, lj = s.ids >> 8;
+                    const int gi = ti * TILE + li2, gj = tj * TILE + lj;
+                    if (gj < V.n) {  // gi < gj by construction
+                        const PointMeta pi = sMi[li2], pj = sMj[lj];
+                        if (is_candidate(pi, pj)) {
+                            const PairVal pv = pair_value(V, tm, s.lb, s.ub, li2, lj, gi, gj, pi, pj, sDi,
+                                                          sDj, flag_bit(bm, gi, gj));
+                            if (!pv.computed) {
+                                ++n_nc;
+                                const float p = fmaxf(tI[li2], tJ[lj]) - pv.v;
+                                const int label = err_label2(tm, pv.dad);
+                                if (p > A.efloor[label]) {
+                                    const float *er = A.errs + A.M.eoff[label];
+                                    int lo = 0, hi = A.M.eoff[label + 1] - A.M.eoff[label];
+                                    while (lo < hi) {  // np.searchsorted(errs[label], p, 'left')
+                                        const int mid = (lo + hi) >> 1;
+                                        if (__ldg(er + mid) < p) lo = mid + 1;
+                                        else hi = mid;
+                                    }
+                                    const int l = __ldg(A.ranktab + A.M.eoff[label] + label + lo);
+                                    if (l >= A.floor_level) {
+                                        lvl = l;
+                                        key = pair_key((uint32_t)gi, (uint32_t)gj);
+                                        atomicAdd(&sHist[l], 1u);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+                if (A.emit_key) {
+                    const unsigned mm = __ballot_sync(0xffffffffu, lvl >= 0);
+                    if (lvl >= 0) {
+                        const int pos = en + __popc(mm & ((1u << lane) - 1));
+                        ek[pos] = key;
+                        el[pos] = (uint16_t)lvl;
+                    }
+                    en += __popc(mm);
+                    __syncwarp();
+                }
+            }
+            __syncwarp();
+        }
+        n_swept += 64;
+    }
+    if (A.emit_key) flush_emit(A, ek, el, en, lane);
+    __syncthreads();
+    for (int k = tid; k < A.nlevels; k += blockDim.x)
+        if (sHist[k]) atomicAdd(&A.hist[k], sHist[k]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        n_nc += __shfl_xor_sync(0xffffffffu, n_nc, o);
+        n_swept += __shfl_xor_sync(0xffffffffu, n_swept, o);
+    }
+    if (lane == 0) {
+        atomicAdd(&A.counters[1], n_nc);
+        atomicAdd(&A.counters[2], n_swept);
+    }
+}
+
+int launch_score_sweep(annb_ctx *c, const ScoreArgs &A)
+{
+    const size_t smem = (size_t)4 * A.V.na * SROW * 4 + 4 * TILE * sizeof(PointMeta) +
+                        2 * BITMAP_WORDS * 4 + (size_t)8 * QCAP * sizeof(Survivor) +
+                        (size_t)8 * EMIT_CAP * 10 + 4 * TILE * 4 + sizeof(TileModel) +
+                        (size_t)A.nlevels * 4 + 64;
+    ANNB_REQUIRE(smem <= 227 * 1024, ANNB_ERANGE,
+                 "score sweep needs %zu bytes of shared memory (n_anchors=%d, %d levels)", smem,
+                 A.V.na, A.nlevels);
+    ANNB_CUDA(cudaFuncSetAttribute(score_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+    const int64_t nq = (A.q_end - A.q_begin + A.q_stride - 1) / A.q_stride;
+    int grid = c->num_sms;
+    if (nq < grid) grid = nq < 1 ? 1 : (int)nq;
+    ANNB_LAUNCH(score_sweep_kernel, grid, 256, smem, c->stream, A);
+    return ANNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sampler sweep (annchor/samplers.py:75-140, annchor/utils.py:543-578): emit a uniform
+// sub-sample of the not-computed candidate pairs with their dad.  A pair participates iff
+// hash32(pair, seed) <= thr -- thr = 0xffffffff enumerates every pair (exact mode, small
+// problems).  No anchor loop: ~a dozen issue slots per pair; phase 2 handles the sub-sample.
+// ---------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t hash_pair32(uint32_t i, uint32_t j, uint32_t seed)
+{
+    uint32_t h = (i * 0x9E3779B1u) ^ (j * 0x85EBCA77u) ^ seed;
+    h ^= h >> 15;
+    h *= 0x2C1B3C6Du;
+    h ^= h >> 12;
+    h *= 0x297A2D39u;
+    h ^= h >> 15;
+    return h;
+}
+
+__global__ void __launch_bounds__(256, 2) sample_sweep_kernel(const SampleArgs A)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const View &V = A.V;
+    const int na = V.na;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ty = tid >> 4, tx = tid & 15;
+    float *sDi = reinterpret_cast<float *>(smem);
+    float *sDj = sDi + na * SROW;
+    PointMeta *sMi = reinterpret_cast<PointMeta *>(sDj + na * SROW);
+    PointMeta *sMj = sMi + TILE;
+    uint32_t *bm = reinterpret_cast<uint32_t *>(sMj + TILE);
+    uint32_t *queue = bm + BITMAP_WORDS + warp * QCAP;  // li | lj << 8
+    const int64_t NT = (int64_t)V.T * (V.T + 1) / 2;
+    const int64_t nq = (NT - A.rank + A.world - 1) / A.world;
+    const int64_t per = (nq + gridDim.x - 1) / gridDim.x;
+    const int64_t m0 = (int64_t)blockIdx.x * per, m1 = min(nq, m0 + per);
+    for (int64_t m = m0; m < m1; ++m) {
+        int ti, tj;
+        tile_from_index(m * A.world + A.rank, V.T, ti, tj);
+        __syncthreads();
+        load_point_tile(V, ti, sDi, sMi);
+        load_point_tile(V, tj, sDj, sMj);
+        load_bitmap_tile(V, ti, tj, bm);
+        cp_async_commit();
+        cp_async_wait_all();
+        __syncthreads();
+        const bool diag = ti == tj;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int li = micro_off(ty, r);
+            const uint32_t gi = (uint32_t)(ti * TILE + li);
+            int qn = 0;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int lj = micro_off(tx, c);
+                const uint32_t gj = (uint32_t)(tj * TILE + lj);
+                const bool keep = hash_pair32(gi, gj, A.seed) <= A.thr && (!diag || li < lj) && gj < (uint32_t)V.n;
+                const unsigned mm = __ballot_sync(0xffffffffu, keep);
+                if (keep) queue[qn + __popc(mm & ((1u << lane) - 1))] = (uint32_t)li | ((uint32_t)lj << 8);
+                qn += __popc(mm);
+            }
+            __syncwarp();
+            for (int e0 = 0; e0 < qn; e0 += 32) {
+                const int e = e0 + lane;
+                bool emit = false;
+                uint64_t key = 0;
+                float dad = 0.0f;
+                if (e < qn) {
+                    const uint32_t ids = queue[e];
+                    const int li2 = ids & 0xff, lj = ids >> 8;
+                    const int gi2 = ti * TILE + li2, gj = tj * TILE + lj;
+                    const PointMeta pi = sMi[li2], pj = sMj[lj];
+                    if (pi.slot < 0 && pj.slot < 0 && is_candidate(pi, pj)) {  // anchor pairs are computed
+                        bool known = false;
+                        if (flag_bit(bm, gi2, gj)) {
+                            float a, b;
+                            known = hash_lookup(V, pair_key((uint32_t)gi2, (uint32_t)gj), a, b) == KIND_KNOWN;
+                        }
+                        if (!known) {
+                            emit = true;
+                            key = pair_key((uint32_t)gi2, (uint32_t)gj);
+                            dad = 0.5f * (sDi[pj.cA * SROW + li2] + sDj[pi.cA * SROW + lj]);
+                        }
+                    }
+                }
+                const unsigned mm = __ballot_sync(0xffffffffu, emit);
+                if (mm) {
+                    unsigned long long base = 0;
+                    if (lane == 0) base = atomicAdd(A.counter, (unsigned long long)__popc(mm));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    const unsigned long long pos = base + __popc(mm & ((1u << lane) - 1));
+                    if (emit && pos < A.out_cap) {
+                        A.out_key[pos] = key;
+                        A.out_dad[pos] = dad;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+int launch_sample_sweep(annb_ctx *c, const SampleArgs &A)
+{
+    const size_t smem = (size_t)2 * A.V.na * SROW * 4 + 2 * TILE * sizeof(PointMeta) +
+                        BITMAP_WORDS * 4 + (size_t)8 * QCAP * 4 + 64;
+    ANNB_CUDA(cudaFuncSetAttribute(sample_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+    const int64_t NT = (int64_t)A.V.T * (A.V.T + 1) / 2;
+    const int64_t nq = (NT - A.rank + A.world - 1) / A.world;
+    int grid = c->num_sms * 2;
+    if (nq < grid) grid = nq < 1 ? 1 : (int)nq;
+    ANNB_LAUNCH(sample_sweep_kernel, grid, 256, smem, c->stream, A);
+    return ANNB_OK;
+}
+
+}  // namespace annb

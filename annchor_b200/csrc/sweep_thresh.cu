@@ -1,0 +1,246 @@
+// sweep_thresh.cu -- K5a: per-row selection thresholds without materialising RefineApprox.
+//
+//   thresh[i] = (nn+1)-th smallest RefineApprox over the candidate pairs of row i
+//               (annchor/annchor.py:399-404)
+// and, on iteration 0, the inputs of guarantee_nmin (annchor/utils.py:606-621): per row the
+// nmin+1 smallest NOT-computed predictions with their column ids.
+//
+// One CTA owns a block of 128 rows and streams every column tile past it (both triangles:
+// each pair is evaluated once per endpoint, which keeps all per-row state private -- a warp
+// owns 16 whole rows of the tile, so the sorted row lists in shared memory need no inter-warp
+// synchronisation, no global atomics, and the result is deterministic).  A pair is handed to
+// phase 2 only when its lower bound beats the row's current k-th value, so after the first few
+// column tiles almost nothing survives phase 1.
+#include "sweep.cuh"
+#include "sweep_args.cuh"
+
+namespace annb {
+
+
+struct SortedRow {
+    // warp-cooperative sorted insert into a list of K <= 64 (value, id) pairs kept in shared memory
+    __device__ static __forceinline__ void insert(float *lv, int32_t *li, int K, float v, int32_t id,
+                                                  int lane, float *thr)
+    {
+        const bool h0 = lane < K, h1 = lane + 32 < K;
+        const float x0 = h0 ? lv[lane] : INFINITY, x1 = h1 ? lv[lane + 32] : INFINITY;
+        int32_t a0 = 0, a1 = 0;
+        if (li) {
+            a0 = h0 ? li[lane] : INT32_MAX;
+            a1 = h1 ? li[lane + 32] : INT32_MAX;
+        }
+        const bool le0 = (x0 < v) || (x0 == v && (!li || a0 <= id));
+        const bool le1 = (x1 < v) || (x1 == v && (!li || a1 <= id));
+        const int pos = __popc(__ballot_sync(0xffffffffu, le0 && h0)) +
+                        __popc(__ballot_sync(0xffffffffu, le1 && h1));
+        if (pos >= K) return;
+        const float y0 = __shfl_up_sync(0xffffffffu, x0, 1), y1 = __shfl_up_sync(0xffffffffu, x1, 1);
+        const float carry = __shfl_sync(0xffffffffu, x0, 31);
+        const float n0 = lane < pos ? x0 : (lane == pos ? v : y0);
+        const int i1 = lane + 32;
+        const float n1 = i1 < pos ? x1 : (i1 == pos ? v : (lane == 0 ? carry : y1));
+        if (li) {
+            const int32_t b0 = __shfl_up_sync(0xffffffffu, a0, 1), b1 = __shfl_up_sync(0xffffffffu, a1, 1);
+            const int32_t ca = __shfl_sync(0xffffffffu, a0, 31);
+            const int32_t m0 = lane < pos ? a0 : (lane == pos ? id : b0);
+            const int32_t m1 = i1 < pos ? a1 : (i1 == pos ? id : (lane == 0 ? ca : b1));
+            if (h0) li[lane] = m0;
+            if (h1) li[i1] = m1;
+        }
+        if (h0) lv[lane] = n0;
+        if (h1) lv[i1] = n1;
+        if (lane == ((K - 1) & 31)) *thr = (K - 1 < 32) ? n0 : n1;
+        __syncwarp();
+    }
+};
+
+template <bool L2ON>
+__global__ void __launch_bounds__(256, 1) thresh_sweep_kernel(const ThreshArgs A)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const View &V = A.V;
+    const int na = V.na;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ty = tid >> 4, tx = tid & 15;
+    // ---- shared memory carve-up ----
+    float *sDi = reinterpret_cast<float *>(smem);
+    float *sDj0 = sDi + na * SROW;
+    float *sDj1 = sDj0 + na * SROW;
+    PointMeta *sMi = reinterpret_cast<PointMeta *>(sDj1 + na * SROW);
+    PointMeta *sMj0 = sMi + TILE;
+    PointMeta *sMj1 = sMj0 + TILE;
+    uint32_t *sB0 = reinterpret_cast<uint32_t *>(sMj1 + TILE);
+    uint32_t *sB1 = sB0 + BITMAP_WORDS;
+    uint32_t *sBT = sB1 + BITMAP_WORDS;  // flags re-oriented to (row = this CTA's point, col = column point)
+    TileModel *tm = reinterpret_cast<TileModel *>(sBT + BITMAP_WORDS);
+    Survivor *queue = reinterpret_cast<Survivor *>(tm + 1) + warp * QCAP;
+    float *thr1 = reinterpret_cast<float *>(reinterpret_cast<Survivor *>(tm + 1) + 8 * QCAP);
+    float *thr2 = thr1 + TILE;
+    float *cut = thr2 + TILE;  // max(thr1, thr2): phase-1 cut-off per row
+    float *L1 = cut + TILE;
+    float *L2v = L1 + TILE * A.k1;
+    int32_t *L2i = reinterpret_cast<int32_t *>(L2v + TILE * A.k2);
+    const bool filter = V.is_metric != 0;  // is_metric=False overrides anchor pairs with raw D (annchor.py:368-372)
+
+    build_tile_model(A.M, tm);
+    for (int rb = blockIdx.x * A.world + A.rank; rb < V.T; rb += gridDim.x * A.world) {
+        // ---- init row state, stage the row tile ----
+        for (int k = tid; k < TILE * A.k1; k += blockDim.x) L1[k] = INFINITY;
+        if (L2ON)
+            for (int k = tid; k < TILE * A.k2; k += blockDim.x) {
+                L2v[k] = INFINITY;
+                L2i[k] = -1;
+            }
+        if (tid < TILE) {
+            thr1[tid] = INFINITY;
+            thr2[tid] = L2ON ? INFINITY : -INFINITY;
+            cut[tid] = INFINITY;
+        }
+        load_point_tile(V, rb, sDi, sMi);
+        load_point_tile(V, 0, sDj0, sMj0);
+        load_bitmap_tile(V, rb, 0, sB0);
+        cp_async_commit();
+
+        for (int tc = 0; tc < V.T; ++tc) {
+            const float *sDj = (tc & 1) ? sDj1 : sDj0;
+            const PointMeta *sMj = (tc & 1) ? sMj1 : sMj0;
+            const uint32_t *sBraw = (tc & 1) ? sB1 : sB0;
+            cp_async_wait_all();
+            __syncthreads();
+            if (tc + 1 < V.T) {  // prefetch the next column tile into the other buffer
+                load_point_tile(V, tc + 1, (tc & 1) ? sDj0 : sDj1, (tc & 1) ? sMj0 : sMj1);
+                load_bitmap_tile(V, rb, tc + 1, (tc & 1) ? sB0 : sB1);
+                cp_async_commit();
+            }
+            // flag bits are stored once per pair, in the tile of (lo, hi): re-orient them so that
+            // bit (row, col) of sBF is the flag of (this CTA's row point, column point)
+            const uint32_t *sBF = sBraw;
+            if (tc <= rb) {
+                transpose_bitmap(sBraw, sBT);
+                __syncthreads();
+                if (tc == rb) {
+                    for (int k = tid; k < BITMAP_WORDS; k += blockDim.x) sBT[k] |= sBraw[k];
+                    __syncthreads();
+                }
+                sBF = sBT;
+            }
+            // ---- phase 1: bounds + clipped prediction for all 64 pairs of the micro-tile ----
+            float lb[8][8], ub[8][8];
+            bounds_microtile(sDi, sDj, na, ty, tx, lb, ub);
+            int cAj[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) cAj[c] = sMj[micro_off(tx, c)].cA * SROW;
+
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int li = micro_off(ty, r);
+                const float cr = filter ? cut[li] : INFINITY;
+                const float *dj_row = sDj + sMi[li].cA * SROW;
+                uint32_t w0, w1;
+                flag_words(sBF, li, tx, w0, w1);
+                bool keep[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float s2 = sDi[cAj[c] + li] + dj_row[micro_off(tx, c)];
+                    const float y = predict_clip2(tm, lb[r][c], ub[r][c], s2);
+                    const uint32_t fl = c < 4 ? (w0 >> c) : (w1 >> (c - 4));
+                    keep[c] = (y < cr) | (fl & 1u);
+                }
+                const int qn = stage_row(queue, 0, lb[r], ub[r], keep, li, tx, lane);
+                __syncwarp();
+                // ---- phase 2: survivors of this row step, one per lane ----
+                for (int e0 = 0; e0 < qn; e0 += 32) {
+                    const int e = e0 + lane;
+                    bool w1b = false, w2b = false;
+                    float v = INFINITY;
+                    int row = 0, gj = 0;
+                    if (e < qn) {
+                        const Survivor sv = queue[e];
+                        row = sv.ids & 0xff;
+                        const int lj = sv.ids >> 8;
+                        const int gi = rb * TILE + row;
+                        gj = tc * TILE + lj;
+                        const PointMeta pi = sMi[row], pj = sMj[lj];
+                        if (gi < V.n && gj < V.n && gi != gj && is_candidate(pi, pj)) {
+                            const bool fl = (sBF[row * 4 + (lj >> 5)] >> (lj & 31)) & 1u;
+                            const PairVal pv = pair_value(V, tm, sv.lb, sv.ub, row, lj, gi, gj, pi, pj, sDi,
+                                                          sDj, fl);
+                            v = pv.v;
+                            w1b = v < thr1[row];
+                            w2b = L2ON && !pv.computed && v < thr2[row];
+                        }
+                    }
+                    unsigned m1 = __ballot_sync(0xffffffffu, w1b);
+                    while (m1) {
+                        const int src = __ffs(m1) - 1;
+                        m1 &= m1 - 1;
+                        const float xv = __shfl_sync(0xffffffffu, v, src);
+                        const int sr = __shfl_sync(0xffffffffu, row, src);
+                        SortedRow::insert(L1 + sr * A.k1, nullptr, A.k1, xv, 0, lane, &thr1[sr]);
+                    }
+                    if (L2ON) {
+                        unsigned m2 = __ballot_sync(0xffffffffu, w2b);
+                        while (m2) {
+                            const int src = __ffs(m2) - 1;
+                            m2 &= m2 - 1;
+                            const float xv = __shfl_sync(0xffffffffu, v, src);
+                            const int sr = __shfl_sync(0xffffffffu, row, src);
+                            const int sj = __shfl_sync(0xffffffffu, gj, src);
+                            SortedRow::insert(L2v + sr * A.k2, L2i + sr * A.k2, A.k2, xv, sj, lane, &thr2[sr]);
+                        }
+                    }
+                }
+                __syncwarp();
+                // refresh the phase-1 cut-off of the two rows this warp just processed (warp-private rows)
+                if ((lane & 15) == 0) cut[li] = fmaxf(thr1[li], thr2[li]);
+                __syncwarp();
+            }
+        }
+
+        // ---- write the row block's results ----
+        __syncthreads();
+        if (tid < TILE) A.thresh[rb * TILE + tid] = L1[tid * A.k1 + (A.k1 - 1)];
+        if (L2ON) {
+            for (int k = tid; k < TILE * A.k2; k += blockDim.x) {
+                const int gi = rb * TILE + k / A.k2;
+                if (gi < V.n) {
+                    A.l2val[(int64_t)gi * A.k2 + k % A.k2] = L2v[k];
+                    A.l2id[(int64_t)gi * A.k2 + k % A.k2] = L2i[k];
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+size_t thresh_smem_bytes(int na, int k1, int k2)
+{
+    return (size_t)3 * na * SROW * 4 + 3 * TILE * sizeof(PointMeta) + 3 * BITMAP_WORDS * 4 +
+           sizeof(TileModel) + (size_t)8 * QCAP * sizeof(Survivor) + 3 * TILE * 4 +
+           (size_t)TILE * k1 * 4 + (size_t)TILE * k2 * 8 + 64;
+}
+
+int launch_thresh_sweep(annb_ctx *c, const ThreshArgs &A)
+{
+    const size_t smem = thresh_smem_bytes(A.V.na, A.k1, A.k2);
+    ANNB_REQUIRE(smem <= 227 * 1024, ANNB_ERANGE,
+                 "thresh sweep needs %zu bytes of shared memory (n_anchors=%d, lists %d/%d)", smem,
+                 A.V.na, A.k1, A.k2);
+    ANNB_REQUIRE(A.k1 <= MAX_LIST && A.k2 <= MAX_LIST, ANNB_ERANGE,
+                 "n_neighbors too large for the device row lists (k1=%d, k2=%d, max %d)", A.k1, A.k2,
+                 MAX_LIST);
+    const int rows_here = (A.V.T - A.rank + A.world - 1) / A.world;
+    const int grid = rows_here < 1 ? 1 : rows_here;
+    if (A.k2 > 0) {
+        ANNB_CUDA(cudaFuncSetAttribute(thresh_sweep_kernel<true>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ANNB_LAUNCH(thresh_sweep_kernel<true>, grid, 256, smem, c->stream, A);
+    } else {
+        ANNB_CUDA(cudaFuncSetAttribute(thresh_sweep_kernel<false>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ANNB_LAUNCH(thresh_sweep_kernel<false>, grid, 256, smem, c->stream, A);
+    }
+    return ANNB_OK;
+}
+
+}  // namespace annb

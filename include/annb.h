@@ -158,16 +158,16 @@ int annb_index_get_D(annb_index *ix, double *D);
 /* candidate set (get_locality): returns number of candidate pairs P and the number of rows
  * whose locality threshold had to be relaxed (annchor/utils.py:472-480) */
 int annb_index_locality(annb_index *ix, int64_t *n_candidates, int64_t *n_relaxed);
-/* sampler support (annchor/samplers.py:119-140): order statistics of dad over the
- * not-computed candidate pairs: ranks[nr] (0-based) -> values[nr]; *n_not_computed out */
-int annb_index_dad_order_stats(annb_index *ix, const int64_t *ranks, int64_t nr, double *values,
-                               int64_t *n_not_computed);
-/* per-bin uniform sample without replacement over not-computed candidates with
- * bins[b] <= dad < bins[b+1] (annchor/utils.py:543-557): want[b] pairs per bin;
- * out_ij (sum(want), 2) int64, out_bin_count[nb] = pairs actually returned per bin,
- * out_feat (sum(want), 3) = [lb, ub, dad] of each returned pair */
-int annb_index_sample(annb_index *ix, const double *bins, int64_t nb, const int64_t *want,
-                      uint64_t seed, int64_t *out_ij, int64_t *out_bin_count, double *out_feat);
+/* sampler support (annchor/samplers.py:75-140, annchor/utils.py:543-578): a uniform pool of the
+ * not-computed candidate pairs with their double-anchor distance.  If at most max_pool such pairs
+ * exist the pool is ALL of them (*exact = 1: the host can sort it into the reference's IJs order
+ * and reproduce the reference's sampler bit for bit); otherwise a hash-selected uniform sub-sample. */
+int annb_index_sample_pool(annb_index *ix, uint64_t seed, int64_t max_pool, int64_t *n_pool,
+                           int64_t *n_not_computed, int *exact);
+/* copy the pool out: ij (n_pool, 2) int64, dad float64[n_pool] */
+int annb_index_get_pool(annb_index *ix, int64_t *ij, double *dad);
+/* features [lb, ub, dad] of explicit pairs in the sweeps' float32 arithmetic: feat (n, 3) */
+int annb_index_pair_features(annb_index *ix, const int64_t *ij, int64_t n, double *feat);
 /* mark pairs as exactly computed with distance d (sample_y / refine results,
  * annchor/annchor.py:342,380,472-473) */
 int annb_index_add_known(annb_index *ix, const int64_t *ij, const double *d, int64_t n);
@@ -196,7 +196,8 @@ int annb_index_update_bounds(annb_index *ix, int64_t *n_updated);
 /* get_ann / get_nn (annchor/annchor.py:514-530): idx int64 (n, nn), dist float64 (n, nn),
  * column 0 = self / 0 */
 int annb_index_neighbor_graph(annb_index *ix, int64_t *idx, double *dist);
-/* counters: [0] pairs swept, [1] known pairs, [2] tightened pairs, [3] sweep launches */
+/* counters: [0] pairs swept, [1] known pairs, [2] tightened pairs, [3] sweep launches,
+ * [4] candidate pairs, [5] hash capacity, [6] anchor pairs, [7] not-computed candidates */
 int annb_index_stats(annb_index *ix, int64_t *out, int64_t n);
 /* device-time (ms) of the last sweep kernel and the pairs it covered */
 int annb_index_last_sweep(annb_index *ix, float *ms, int64_t *pairs);
