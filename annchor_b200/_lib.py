@@ -74,6 +74,10 @@ _SIGS = {
     "annb_index_neighbor_graph": [_P, _P, _P],
     "annb_index_stats": [_P, _P, _I64],
     "annb_index_last_sweep": [_P, C.POINTER(C.c_float), C.POINTER(_I64)],
+    "annb_index_set_reducer": [_P, _P, _P],
+    "annb_index_export_refined": [_P, _P, _P, _P, _I64, C.POINTER(_I64)],
+    "annb_index_export_tightened": [_P, _P, _P, _P, _P, _I64, C.POINTER(_I64)],
+    "annb_index_import_dev": [_P, _I32, _P, _P, _P, _P, _I64],
     "annb_bruteforce_knn": [_P, _P, _I32, _I64, _P, _P],
     "annb_numba_rng_new": [C.c_uint32, _PP],
     "annb_numba_rng_free": [_P],
@@ -89,7 +93,7 @@ def declared_symbols():
     """Every function name declared in include/annb.h (parsed from the header)."""
     import re
     hdr = open(os.path.join(_HERE, "..", "include", "annb.h")).read()
-    return sorted(set(re.findall(r"\b(annb_[a-z0-9_]+)\s*\(", hdr)))
+    return sorted(set(re.findall(r"\b(annb_[a-z0-9_]+)\s*\(", hdr)) - {"annb_reduce_fn"})
 
 
 def load():

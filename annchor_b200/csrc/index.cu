@@ -25,7 +25,7 @@ int pair_dists_f32_perm(annb_ctx *c, const annb_dataset *ds, int metric, const i
 // D (na, n) float64 anchor-major -> float32 (na, npad) + per-point metadata
 __global__ void build_meta_kernel(const double *__restrict__ D64, int64_t n, int64_t npad, int na,
                                   int locality, int loc_thresh, float *__restrict__ D32,
-                                  PointMeta *__restrict__ meta)
+                                  float *__restrict__ Dpm, int dpitch, PointMeta *__restrict__ meta)
 {
     for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < npad;
          j += (int64_t)gridDim.x * blockDim.x) {
@@ -40,6 +40,7 @@ __global__ void build_meta_kernel(const double *__restrict__ D64, int64_t n, int
             for (int a = 0; a < na; ++a) {
                 const double v = D64[(int64_t)a * n + j];
                 D32[(int64_t)a * npad + j] = (float)v;
+                Dpm[j * dpitch + a] = (float)v;
                 if (v < best) {  // first minimum (np.argmin)
                     best = v;
                     m.cA = a;
@@ -60,7 +61,10 @@ __global__ void build_meta_kernel(const double *__restrict__ D64, int64_t n, int
                 m.amask |= 1ull << ba;
             }
         } else {
-            for (int a = 0; a < na; ++a) D32[(int64_t)a * npad + j] = 0.0f;
+            for (int a = 0; a < na; ++a) {
+                D32[(int64_t)a * npad + j] = 0.0f;
+                Dpm[j * dpitch + a] = 0.0f;
+            }
             m.loc_t = 127;  // padding rows are never candidates
         }
         meta[j] = m;
@@ -455,65 +459,195 @@ sort_rows_kernel(const int64_t *__restrict__ ptr, int64_t n, int32_t *__restrict
     }
 }
 
-// update_bounds (utils.py:304-352) for the look-ahead pairs: one warp per pair; the shorter
-// list is streamed coalesced, each lane binary-searches the longer one.
-__global__ void __launch_bounds__(256)
-tighten_kernel(View V, const int64_t *__restrict__ ptr, const int32_t *__restrict__ ids,
-               const float *__restrict__ ds, const int32_t *__restrict__ I,
-               const int32_t *__restrict__ J, int64_t m, float *__restrict__ out_lb,
-               float *__restrict__ out_ub, uint8_t *__restrict__ improved)
+// ---- update_bounds (utils.py:304-352) for the look-ahead pairs -------------------------------
+// Every point k with both d(i,k) and d(j,k) known acts as an extra anchor for the pair (i,j):
+//   lb = max_k |d_ik - d_jk|,  ub = min_k (d_ik + d_jk)   over k in N(i) & N(j).
+// The reference merge-joins two id-sorted lists per pair.  Here the pairs are grouped by their
+// lower endpoint i; one CTA owns an i, puts N(i) into a shared-memory hash table once, and each
+// of its warps streams the (coalesced) list of one partner j at a time, probing the table.
+// group key of a pair = its endpoint with the longer known-neighbour list (ties: lower id): that
+// list is hashed once per group, the shorter partner lists are streamed
+__device__ __forceinline__ void group_key(const int64_t *__restrict__ kptr, int a, int b, int &key, int &other)
 {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t p = warp; p < m; p += nwarps) {
-        int i = I[p], j = J[p];
-        int64_t bi = ptr[i], bj = ptr[j];
-        int mi = (int)(ptr[i + 1] - bi), mj = (int)(ptr[j + 1] - bj);
-        if (mi > mj) {  // stream the shorter list
-            const int64_t tb = bi; bi = bj; bj = tb;
-            const int tm = mi; mi = mj; mj = tm;
+    const int64_t da = kptr[a + 1] - kptr[a], db = kptr[b + 1] - kptr[b];
+    const bool a_key = da > db || (da == db && a < b);
+    key = a_key ? a : b;
+    other = a_key ? b : a;
+}
+
+__global__ void count_by_lo_kernel(const int32_t *__restrict__ I, const int32_t *__restrict__ J, int64_t m,
+                                   const int64_t *__restrict__ kptr, int32_t *__restrict__ cnt)
+{
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < m;
+         p += (int64_t)gridDim.x * blockDim.x) {
+        int key, other;
+        group_key(kptr, I[p], J[p], key, other);
+        atomicAdd(&cnt[key], 1);
+    }
+}
+
+__global__ void scatter_by_lo_kernel(const int32_t *__restrict__ I, const int32_t *__restrict__ J, int64_t m,
+                                     const int64_t *__restrict__ kptr, const int64_t *__restrict__ ptr,
+                                     int32_t *__restrict__ cursor, int32_t *__restrict__ gJ /* partner */,
+                                     int32_t *__restrict__ gsrc)
+{
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < m;
+         p += (int64_t)gridDim.x * blockDim.x) {
+        int key, other;
+        group_key(kptr, I[p], J[p], key, other);
+        const int64_t q = ptr[key] + atomicAdd(&cursor[key], 1);
+        gJ[q] = other;
+        gsrc[q] = (int32_t)p;
+    }
+}
+
+// rows ordered by closest anchor (counting sort over <= 64 buckets)
+__global__ void cA_hist_kernel(const PointMeta *__restrict__ meta, int64_t n, int32_t *__restrict__ hist)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        atomicAdd(&hist[meta[i].cA], 1);
+}
+__global__ void cA_scatter_kernel(const PointMeta *__restrict__ meta, int64_t n, int32_t *__restrict__ cursor,
+                                  int32_t *__restrict__ order)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        order[atomicAdd(&cursor[meta[i].cA], 1)] = (int32_t)i;
+}
+
+__global__ void tighten_work_kernel(const int64_t *__restrict__ kptr, const int64_t *__restrict__ gptr,
+                                    const int32_t *__restrict__ gJ, int64_t n,
+                                    unsigned long long *__restrict__ out /* [0] sum deg_j, [1] sum min, [2] max deg */)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long di = kptr[i + 1] - kptr[i];
+        unsigned long long s = 0, sm = 0;
+        for (int64_t g = gptr[i]; g < gptr[i + 1]; ++g) {
+            const int j = gJ[g];
+            const unsigned long long dj = kptr[j + 1] - kptr[j];
+            s += dj;
+            sm += dj < di ? dj : di;
         }
-        float lb = 0.0f, ub = INFINITY;
-        for (int k = lane; k < mi; k += 32) {
-            const int32_t id = ids[bi + k];
-            int lo = 0, hi = mj;
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if (ids[bj + mid] < id) lo = mid + 1;
-                else hi = mid;
+        atomicAdd(&out[0], s);
+        atomicAdd(&out[1], sm);
+        atomicMax(&out[2], di);
+    }
+}
+
+constexpr int TG_SLOTS = 8192;   // shared-memory hash slots (64 KB dynamic shared memory)
+constexpr int TG_CHUNK = 4096;   // entries of N(i) hashed at a time (load factor <= 0.5)
+
+__global__ void __launch_bounds__(256)
+tighten_grouped_kernel(View V, const int64_t *__restrict__ kptr, const int32_t *__restrict__ kids,
+                       const float *__restrict__ kds, const int64_t *__restrict__ gptr,
+                       const int32_t *__restrict__ gJ, const int32_t *__restrict__ gsrc,
+                       const int32_t *__restrict__ row_order, float *__restrict__ out_lb,
+                       float *__restrict__ out_ub, uint8_t *__restrict__ improved)
+{
+    extern __shared__ __align__(16) unsigned char tg_smem[];
+    int32_t *h_id = reinterpret_cast<int32_t *>(tg_smem);
+    float *h_d = reinterpret_cast<float *>(h_id + TG_SLOTS);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    // rows are visited in closest-anchor order: CTAs running at the same time then work on points of
+    // the same neighbourhood, whose partner lists overlap -> the streamed lists hit in L2
+    for (int64_t ri = blockIdx.x; ri < V.n; ri += gridDim.x) {
+        const int64_t i = row_order[ri];
+        const int64_t g0 = gptr[i], g1 = gptr[i + 1];
+        if (g0 == g1) continue;
+        const int64_t bi = kptr[i];
+        const int mi = (int)(kptr[i + 1] - bi);
+        // N(i) goes through the shared-memory hash table in chunks (one chunk for all but hub points)
+        for (int c0 = 0; c0 == 0 || c0 < mi; c0 += TG_CHUNK) {
+            const int mc = min(TG_CHUNK, mi - c0);
+            const bool first = c0 == 0, last = c0 + TG_CHUNK >= mi;
+            int slots = 64;
+            while (slots < 2 * mc) slots <<= 1;
+            const uint32_t hmask = (uint32_t)slots - 1;
+            __syncthreads();
+            for (int k = threadIdx.x; k < slots; k += blockDim.x) h_id[k] = -1;
+            __syncthreads();
+            for (int k = threadIdx.x; k < mc; k += blockDim.x) {
+                const int32_t id = kids[bi + c0 + k];
+                uint32_t h = ((uint32_t)id * 2654435761u) & hmask;
+                while (atomicCAS(&h_id[h], -1, id) != -1) h = (h + 1) & hmask;
+                h_d[h] = kds[bi + c0 + k];
             }
-            if (lo < mj && ids[bj + lo] == id) {
-                const float x = ds[bi + k], y = ds[bj + lo];
-                lb = fmaxf(lb, fabsf(x - y));
-                ub = fminf(ub, x + y);
-            }
-        }
+            __syncthreads();
+            for (int64_t g = g0 + warp; g < g1; g += nwarps) {
+                const int j = gJ[g];
+                const int64_t bj = kptr[j];
+                const int mj = (int)(kptr[j + 1] - bj);
+                float lb = 0.0f, ub = INFINITY;
+                // 4 x 32 entries of j's list in flight per warp before the first probe
+                for (int k0 = 0; k0 < mj; k0 += 128) {
+                    int32_t idv[4];
+                    float yv[4];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            lb = fmaxf(lb, __shfl_xor_sync(0xffffffffu, lb, o));
-            ub = fminf(ub, __shfl_xor_sync(0xffffffffu, ub, o));
-        }
-        if (lane == 0) {
-            // combine with what the pair already has (anchor bounds and any earlier tightening)
-            i = I[p];
-            j = J[p];
-            float l0 = 0.0f, u0 = INFINITY;
-            for (int a = 0; a < V.na; ++a) {
-                const float x = V.D32[(int64_t)a * V.npad + i], y = V.D32[(int64_t)a * V.npad + j];
-                l0 = fmaxf(l0, fabsf(x - y));
-                u0 = fminf(u0, x + y);
+                    for (int u = 0; u < 4; ++u) {
+                        const int k = k0 + u * 32 + lane;
+                        idv[u] = k < mj ? __ldg(kids + bj + k) : -2;
+                        yv[u] = k < mj ? __ldg(kds + bj + k) : 0.0f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (idv[u] < 0) continue;
+                        uint32_t h = ((uint32_t)idv[u] * 2654435761u) & hmask;
+                        for (;;) {
+                            const int32_t t = h_id[h];
+                            if (t == idv[u]) {
+                                const float x = h_d[h];
+                                lb = fmaxf(lb, fabsf(x - yv[u]));
+                                ub = fminf(ub, x + yv[u]);
+                                break;
+                            }
+                            if (t == -1) break;
+                            h = (h + 1) & hmask;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    lb = fmaxf(lb, __shfl_xor_sync(0xffffffffu, lb, o));
+                    ub = fminf(ub, __shfl_xor_sync(0xffffffffu, ub, o));
+                }
+                const int32_t p = gsrc[g];
+                if (!first) {  // combine with the earlier chunks of N(i)
+                    lb = fmaxf(lb, out_lb[p]);
+                    ub = fminf(ub, out_ub[p]);
+                }
+                if (!last) {
+                    if (lane == 0) {
+                        out_lb[p] = lb;
+                        out_ub[p] = ub;
+                    }
+                    continue;
+                }
+                // anchor bounds + any earlier tightening of this pair: lanes over anchors
+                float l0 = 0.0f, u0 = INFINITY;
+                for (int a = lane; a < V.na; a += 32) {
+                    const float x = __ldg(V.Dpm + i * V.dpitch + a), y = __ldg(V.Dpm + (int64_t)j * V.dpitch + a);
+                    l0 = fmaxf(l0, fabsf(x - y));
+                    u0 = fminf(u0, x + y);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    l0 = fmaxf(l0, __shfl_xor_sync(0xffffffffu, l0, o));
+                    u0 = fminf(u0, __shfl_xor_sync(0xffffffffu, u0, o));
+                }
+                if (lane == 0) {
+                    float ta = 0.0f, tb = 0.0f;
+                    const uint32_t plo = (uint32_t)min((int64_t)j, i), phi = (uint32_t)max((int64_t)j, i);
+                    if (hash_lookup(V, pair_key(plo, phi), ta, tb) == KIND_TIGHT) {
+                        l0 = fmaxf(l0, ta);
+                        u0 = fminf(u0, tb);
+                    }
+                    out_lb[p] = fmaxf(lb, l0);
+                    out_ub[p] = fminf(ub, u0);
+                    improved[p] = (lb > l0 || ub < u0) ? 1 : 0;
+                }
             }
-            const uint32_t lo = i < j ? i : j, hi = i < j ? j : i;
-            float ta = 0.0f, tb = 0.0f;
-            if (hash_lookup(V, pair_key(lo, hi), ta, tb) == KIND_TIGHT) {
-                l0 = fmaxf(l0, ta);
-                u0 = fminf(u0, tb);
-            }
-            const bool imp = lb > l0 || ub < u0;
-            out_lb[p] = fmaxf(lb, l0);
-            out_ub[p] = fminf(ub, u0);
-            improved[p] = imp ? 1 : 0;
         }
     }
 }
@@ -631,7 +765,7 @@ namespace annb {
 
 // mixed keys of the emitted entries at one level (ties at a selection cut)
 __global__ void compact_level_kernel(const uint64_t *__restrict__ keys, const uint16_t *__restrict__ lvl,
-                                     int64_t E, int level, uint64_t *__restrict__ out,
+                                     int64_t E, int level, uint64_t *__restrict__ out, int64_t out_cap,
                                      unsigned long long *__restrict__ cnt)
 {
     // warp-uniform trip count: every ballot / shuffle below is executed by all 32 lanes
@@ -646,7 +780,8 @@ __global__ void compact_level_kernel(const uint64_t *__restrict__ keys, const ui
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(cnt, (unsigned long long)__popc(m));
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (hit) out[base + __popc(m & ((1u << lane) - 1))] = mix64(keys[p]);
+        const unsigned long long pos = base + __popc(m & ((1u << lane) - 1));
+        if (hit && (int64_t)pos < out_cap) out[pos] = mix64(keys[p]);
     }
 }
 
@@ -689,7 +824,8 @@ struct annb_index {
     bool have_anchors = false, have_locality = false, have_model = false, have_thresh = false;
     bool has_forced = false;
     std::vector<int32_t> A_host;
-    DevBuf A_dev, D64, D32, meta, scratch;
+    DevBuf A_dev, D64, D32, Dpm, meta, scratch;
+    int dpitch = 32;
     // known-pair store
     DevBuf htab, bitmap;
     uint64_t hcap = 0;
@@ -714,12 +850,32 @@ struct annb_index {
     // temporaries
     DevBuf t0, t1, t2, t3, t4, t5, t6;
     // CSR of known pairs
-    DevBuf kptr, kids, kds, kdeg;
+    DevBuf kptr, kids, kds, kdeg, gptr, gJ, gsrc, row_order;
     int64_t csr_entries = 0;
     // stats
     int64_t pairs_swept = 0, sweeps = 0, n_tight = 0, n_known = 0;
     float last_sweep_ms = 0;
     int64_t last_sweep_pairs = 0;
+    // multi-GPU: host-buffer sum all-reduce supplied by the caller (torch.distributed in Python)
+    annb_reduce_fn reducer = nullptr;
+    void *reducer_user = nullptr;
+    // results of the last refine / tighten kept on device for export to the other ranks
+    int64_t n_refined = 0, n_tightened = 0;
+
+    int reduce(void *buf, int64_t count, int dtype) const
+    {
+        if (P.world <= 1) return ANNB_OK;
+        if (!reducer) {
+            set_error("index is sharded (world=%d) but no reducer was set (annb_index_set_reducer)", P.world);
+            return ANNB_ESTATE;
+        }
+        const int rc = reducer(reducer_user, buf, count, dtype);
+        if (rc != 0) {
+            set_error("reducer callback failed with code %d", rc);
+            return ANNB_ESTATE;
+        }
+        return ANNB_OK;
+    }
 
     View view() const
     {
@@ -731,6 +887,8 @@ struct annb_index {
         V.nn = P.n_neighbors;
         V.is_metric = P.is_metric;
         V.D32 = D32.as<float>();
+        V.Dpm = Dpm.as<float>();
+        V.dpitch = dpitch;
         V.meta = meta.as<PointMeta>();
         V.htab = htab.as<HashSlot>();
         V.hmask = hcap - 1;
@@ -794,7 +952,7 @@ static int finish_anchors(annb_index *ix)
     annb_ctx *c = ix->ctx;
     ANNB_LAUNCH(build_meta_kernel, grid_for_n(c, ix->npad), 256, 0, c->stream, ix->D64.as<double>(),
                 ix->n, ix->npad, ix->na, ix->P.locality, ix->P.loc_thresh, ix->D32.as<float>(),
-                ix->meta.as<PointMeta>());
+                ix->Dpm.as<float>(), ix->dpitch, ix->meta.as<PointMeta>());
     if (!ix->A_host.empty())
         ANNB_LAUNCH(set_slots_kernel, 1, 32, 0, c->stream, ix->A_dev.as<int32_t>(),
                     (int)ix->A_host.size(), ix->meta.as<PointMeta>());
@@ -832,6 +990,8 @@ ANNB_API int annb_index_create(annb_ctx *c, const annb_dataset *ds, int metric,
         if ((rc = ix->A_dev.ensure((size_t)ix->na * 4))) break;
         if ((rc = ix->D64.ensure((size_t)ix->na * ix->n * 8))) break;
         if ((rc = ix->D32.ensure((size_t)ix->na * ix->npad * 4))) break;
+        ix->dpitch = (ix->na + 31) / 32 * 32;
+        if ((rc = ix->Dpm.ensure((size_t)ix->npad * ix->dpitch * 4))) break;
         if ((rc = ix->meta.ensure((size_t)ix->npad * sizeof(PointMeta)))) break;
         if ((rc = ix->bitmap.ensure((size_t)ix->NT * BITMAP_WORDS * 4))) break;
         if ((rc = ix->thresh.ensure((size_t)ix->npad * 4))) break;
@@ -853,12 +1013,12 @@ ANNB_API int annb_index_destroy(annb_index *ix)
     if (!ix) return ANNB_OK;
     cudaSetDevice(ix->ctx->device);
     cudaStreamSynchronize(ix->ctx->stream);
-    DevBuf *all[] = {&ix->A_dev, &ix->D64, &ix->D32, &ix->meta, &ix->scratch, &ix->htab, &ix->bitmap,
+    DevBuf *all[] = {&ix->A_dev, &ix->D64, &ix->D32, &ix->Dpm, &ix->meta, &ix->scratch, &ix->htab, &ix->bitmap,
                      &ix->errs_dev, &ix->rank_dev, &ix->thresh, &ix->l2val, &ix->l2id, &ix->hist,
                      &ix->counters, &ix->emit_key, &ix->emit_lvl, &ix->sel_i, &ix->sel_j, &ix->nxt_i,
                      &ix->nxt_j, &ix->tiehist, &ix->tiekeys, &ix->pool_key, &ix->pool_dad, &ix->t0,
                      &ix->t1, &ix->t2, &ix->t3, &ix->t4, &ix->t5, &ix->t6, &ix->kptr, &ix->kids,
-                     &ix->kds, &ix->kdeg};
+                     &ix->kds, &ix->kdeg, &ix->gptr, &ix->gJ, &ix->gsrc, &ix->row_order};
     for (DevBuf *b : all) b->release();
     delete ix;
     return ANNB_OK;
@@ -1150,6 +1310,13 @@ static int run_thresh(annb_index *ix, int k2)
     }
     A.rank = ix->P.rank;
     A.world = ix->P.world;
+    if (ix->P.world > 1) {  // rows of other ranks stay 0 so that a sum all-reduce assembles the result
+        ANNB_CUDA(cudaMemsetAsync(ix->thresh.p, 0, (size_t)ix->npad * 4, c->stream));
+        if (k2 > 0) {
+            ANNB_CUDA(cudaMemsetAsync(ix->l2val.p, 0, (size_t)ix->n * k2 * 4, c->stream));
+            ANNB_CUDA(cudaMemsetAsync(ix->l2id.p, 0, (size_t)ix->n * k2 * 4, c->stream));
+        }
+    }
     ANNB_CUDA(cudaEventRecord(c->ev0, c->stream));
     ANNB_TRY(launch_thresh_sweep(c, A));
     ANNB_CUDA(cudaEventRecord(c->ev1, c->stream));
@@ -1158,6 +1325,23 @@ static int run_thresh(annb_index *ix, int k2)
     ANNB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     ix->pairs_swept += ix->n * (ix->n - 1) / ix->P.world;
     ix->sweeps += 1;
+    if (ix->P.world > 1) {
+        // every row block was computed by exactly one rank: sum-reduce the slices through the host
+        auto exchange = [&](DevBuf &b, size_t count, int dtype) -> int {
+            std::vector<uint32_t> h(count);
+            ANNB_CUDA(cudaMemcpyAsync(h.data(), b.p, count * 4, cudaMemcpyDeviceToHost, c->stream));
+            ANNB_CUDA(cudaStreamSynchronize(c->stream));
+            ANNB_TRY(ix->reduce(h.data(), (int64_t)count, dtype));
+            ANNB_CUDA(cudaMemcpyAsync(b.p, h.data(), count * 4, cudaMemcpyHostToDevice, c->stream));
+            ANNB_CUDA(cudaStreamSynchronize(c->stream));
+            return ANNB_OK;
+        };
+        ANNB_TRY(exchange(ix->thresh, (size_t)ix->npad, ANNB_RED_F32));
+        if (k2 > 0) {
+            ANNB_TRY(exchange(ix->l2val, (size_t)ix->n * k2, ANNB_RED_F32));
+            ANNB_TRY(exchange(ix->l2id, (size_t)ix->n * k2, ANNB_RED_I32));
+        }
+    }
     ix->have_thresh = true;
     return ANNB_OK;
 }
@@ -1285,7 +1469,7 @@ static void fill_efloor(const annb_index *ix, int floor_level, float *efloor, fl
 }
 
 static int run_score(annb_index *ix, int floor_level, int stride, bool emit, int64_t emit_cap,
-                     std::vector<uint32_t> &hist, unsigned long long cnt[3])
+                     std::vector<uint64_t> &hist, unsigned long long cnt[3])
 {
     annb_ctx *c = ix->ctx;
     ScoreArgs A;
@@ -1321,10 +1505,12 @@ static int run_score(annb_index *ix, int floor_level, int stride, bool emit, int
     ANNB_CUDA(cudaEventRecord(c->ev0, c->stream));
     ANNB_TRY(launch_score_sweep(c, A));
     ANNB_CUDA(cudaEventRecord(c->ev1, c->stream));
-    hist.resize(ix->nlevels);
-    ANNB_CUDA(cudaMemcpyAsync(hist.data(), ix->hist.p, (size_t)ix->nlevels * 4, cudaMemcpyDeviceToHost, c->stream));
+    std::vector<uint32_t> h32(ix->nlevels);
+    ANNB_CUDA(cudaMemcpyAsync(h32.data(), ix->hist.p, (size_t)ix->nlevels * 4, cudaMemcpyDeviceToHost, c->stream));
     ANNB_CUDA(cudaMemcpyAsync(cnt, ix->counters.p, 24, cudaMemcpyDeviceToHost, c->stream));
     ANNB_CUDA(cudaStreamSynchronize(c->stream));
+    hist.assign(h32.begin(), h32.end());
+    ANNB_TRY(ix->reduce(hist.data(), (int64_t)hist.size(), ANNB_RED_U64));  // global level counts
     float ms = 0;
     ANNB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     const int64_t pairs = ix->n * (ix->n - 1) / 2 / ix->P.world / stride;
@@ -1344,16 +1530,29 @@ static int tie_threshold(annb_index *ix, int64_t E, int level, int64_t level_cou
     ANNB_TRY(ix->tiekeys.ensure((size_t)(level_count + 32) * 8));
     ANNB_CUDA(cudaMemsetAsync(ix->counters.p, 0, 64, c->stream));
     ANNB_LAUNCH(compact_level_kernel, grid_for_n(c, E), 256, 0, c->stream, ix->emit_key.as<uint64_t>(),
-                ix->emit_lvl.as<uint16_t>(), E, level, ix->tiekeys.as<uint64_t>(),
+                ix->emit_lvl.as<uint16_t>(), E, level, ix->tiekeys.as<uint64_t>(), level_count + 32,
                 ix->counters.as<unsigned long long>());
+    unsigned long long found = 0;
+    ANNB_CUDA(cudaMemcpyAsync(&found, ix->counters.p, 8, cudaMemcpyDeviceToHost, c->stream));
+    ANNB_CUDA(cudaStreamSynchronize(c->stream));
+    const int64_t found_local = (int64_t)found;
+    uint64_t found_all = found;
+    ANNB_TRY(ix->reduce(&found_all, 1, ANNB_RED_U64));
+    ANNB_REQUIRE((int64_t)found_all == level_count, ANNB_ESTATE,
+                 "tie compaction found %llu emitted pairs at level %d, the level histogram says %lld (E=%lld)",
+                 (unsigned long long)found_all, level, (long long)level_count, (long long)E);
     uint64_t prefix = 0;
-    std::vector<uint32_t> h(65536);
+    std::vector<uint32_t> h32(65536);
+    std::vector<uint64_t> h(65536);
     for (int shift = 48; shift >= 0; shift -= 16) {
         ANNB_CUDA(cudaMemsetAsync(ix->tiehist.p, 0, 65536 * 4, c->stream));
-        ANNB_LAUNCH(digit_hist_kernel, grid_for_n(c, level_count), 256, 0, c->stream,
-                    ix->tiekeys.as<uint64_t>(), level_count, prefix, shift, ix->tiehist.as<uint32_t>());
-        ANNB_CUDA(cudaMemcpyAsync(h.data(), ix->tiehist.p, 65536 * 4, cudaMemcpyDeviceToHost, c->stream));
+        if (found_local > 0)
+            ANNB_LAUNCH(digit_hist_kernel, grid_for_n(c, found_local), 256, 0, c->stream,
+                        ix->tiekeys.as<uint64_t>(), found_local, prefix, shift, ix->tiehist.as<uint32_t>());
+        ANNB_CUDA(cudaMemcpyAsync(h32.data(), ix->tiehist.p, 65536 * 4, cudaMemcpyDeviceToHost, c->stream));
         ANNB_CUDA(cudaStreamSynchronize(c->stream));
+        h.assign(h32.begin(), h32.end());
+        ANNB_TRY(ix->reduce(h.data(), 65536, ANNB_RED_U64));
         int d = 0;
         for (; d < 65536; ++d) {
             if (t <= (int64_t)h[d]) break;
@@ -1367,7 +1566,7 @@ static int tie_threshold(annb_index *ix, int64_t E, int level, int64_t level_cou
 }
 
 // largest level L >= lo_level with sum_{l >= L} h[l] >= target (lo_level if none)
-static int level_cut(const std::vector<uint32_t> &h, int lo_level, int64_t target, int64_t *cum_at)
+static int level_cut(const std::vector<uint64_t> &h, int lo_level, int64_t target, int64_t *cum_at)
 {
     int64_t cum = 0;
     for (int L = (int)h.size() - 1; L > lo_level; --L) {
@@ -1397,34 +1596,40 @@ ANNB_API int annb_index_select(annb_index *ix, int64_t n_refine, int64_t lookahe
     const int64_t want1 = n_refine, want2 = n_refine * lookahead;
     // annchor.py:444-457: n_refine >= len(prob) -> everything is candidate AND next;
     // n_refine*lookahead >= len(prob) -> large_part is everything
-    const int64_t sel_target = std::min<int64_t>(want1, n_nc);
-    const int64_t tot_target = want1 >= n_nc ? n_nc : std::min<int64_t>(want2, n_nc);
+    int64_t sel_target = std::min<int64_t>(want1, n_nc);
+    int64_t tot_target = want1 >= n_nc ? n_nc : std::min<int64_t>(want2, n_nc);
 
-    std::vector<uint32_t> h1, h2;
+    std::vector<uint64_t> h1, h2;
     unsigned long long c1v[3] = {0, 0, 0}, c2v[3] = {0, 0, 0};
-    int floor_level = 0;
+    // Level 0 is probability 0.  On small problems it takes part like any other level (the
+    // reference's argpartition then picks arbitrary probability-0 pairs).  On large problems
+    // emitting the probability-0 bulk is pointless and Theta(N^2): the cut never goes below level 1,
+    // and if fewer positive-probability pairs exist than asked for, the look-ahead set (then the
+    // selection) is truncated to what exists.
+    const bool small = tot_target >= n_nc || n_nc <= (int64_t)64000000;
+    const int min_floor = small ? 0 : 1;
+    int floor_level = min_floor;
     int64_t cap = 0;
     if (tot_target >= n_nc) {
-        floor_level = 0;  // everything is taken: no pilot needed
-        cap = n_nc + 1024;
+        cap = n_nc + 1024;  // everything is taken: no pilot needed
     } else {
         // pass 1: level histogram -- exact for small problems, a pilot over every s-th tile otherwise
         const int stride = nq > 8192 ? (int)(nq / 2048) : 1;
-        ANNB_TRY(run_score(ix, 0, stride, false, 0, h1, c1v));
+        ANNB_TRY(run_score(ix, min_floor, stride, false, 0, h1, c1v));
         if (stride == 1) {
             int64_t cum = 0;
-            floor_level = level_cut(h1, 0, tot_target, &cum);
+            floor_level = level_cut(h1, min_floor, tot_target, &cum);
             cap = cum + 1024;
         } else {
             const double scale = (double)nq / (double)((nq + stride - 1) / stride);
             const double target = 1.5 * (double)tot_target + 65536.0;
             double cum = 0;
             int L = ix->nlevels - 1;
-            for (; L > 0; --L) {
+            for (; L > min_floor; --L) {
                 cum += (double)h1[L] * scale;
                 if (cum >= target) break;
             }
-            if (L == 0) cum += (double)h1[0] * scale;
+            if (L == min_floor) cum += (double)h1[min_floor] * scale;
             floor_level = L;
             cap = (int64_t)(cum * 1.5) + (1 << 20);
             if (cap > n_nc + 1024) cap = n_nc + 1024;
@@ -1434,24 +1639,32 @@ ANNB_API int annb_index_select(annb_index *ix, int64_t n_refine, int64_t lookahe
     int64_t E = 0;
     for (int attempt = 0;; ++attempt) {
         ANNB_REQUIRE(attempt < 4, ANNB_ESTATE, "selection did not converge");
-        ANNB_TRY(run_score(ix, floor_level, 1, true, cap, h2, c2v));
+        // `cap` counts pairs over all ranks; a rank's own list gets its share plus slack
+        const int64_t cap_local = ix->P.world > 1 ? cap / ix->P.world + cap / (4 * ix->P.world) + (1 << 16) : cap;
+        ANNB_TRY(run_score(ix, floor_level, 1, true, cap_local, h2, c2v));
         E = (int64_t)c2v[0];
         int64_t cum = 0;
         for (int L = floor_level; L < ix->nlevels; ++L) cum += h2[L];
-        if (E > cap) {
+        uint64_t overflow = E > cap_local ? 1 : 0;
+        ANNB_TRY(ix->reduce(&overflow, 1, ANNB_RED_U64));  // every rank must take the same branch
+        if (overflow) {
             // more pairs above the floor than planned: the histogram above it is exact, re-cut exactly
             int64_t cum2 = 0;
             floor_level = level_cut(h2, floor_level, tot_target, &cum2);
             cap = cum2 + 1024;
             continue;
         }
-        if (floor_level > 0 && cum < tot_target) {
+        if (floor_level > min_floor && cum < tot_target) {
             // floor too high: exact full histogram, exact floor
-            ANNB_TRY(run_score(ix, 0, 1, false, 0, h1, c1v));
+            ANNB_TRY(run_score(ix, min_floor, 1, false, 0, h1, c1v));
             int64_t cum2 = 0;
-            floor_level = level_cut(h1, 0, tot_target, &cum2);
+            floor_level = level_cut(h1, min_floor, tot_target, &cum2);
             cap = cum2 + 1024;
             continue;
+        }
+        if (cum < tot_target) {  // large problem, not enough positive-probability pairs
+            tot_target = cum;
+            sel_target = std::min<int64_t>(sel_target, cum);
         }
         break;
     }
@@ -1478,7 +1691,8 @@ ANNB_API int annb_index_select(annb_index *ix, int64_t n_refine, int64_t lookahe
     uint64_t thr1 = ~0ull, thr2 = ~0ull;
     if (cl1 < ix->nlevels && t1 < (int64_t)h2[cl1]) ANNB_TRY(tie_threshold(ix, E, cl1, h2[cl1], t1, &thr1));
     if (cl2 < ix->nlevels && t2 < (int64_t)h2[cl2]) ANNB_TRY(tie_threshold(ix, E, cl2, h2[cl2], t2, &thr2));
-    const int64_t cap_sel = sel_target + 16, cap_next = tot_target - sel_target + 16;
+    const int64_t cap_sel = std::min<int64_t>(sel_target, E) + 16;
+    const int64_t cap_next = std::min<int64_t>(tot_target - sel_target, E) + 16;
     ANNB_TRY(ix->sel_i.ensure((size_t)cap_sel * 4));
     ANNB_TRY(ix->sel_j.ensure((size_t)cap_sel * 4));
     ANNB_TRY(ix->nxt_i.ensure((size_t)cap_next * 4));
@@ -1492,9 +1706,12 @@ ANNB_API int annb_index_select(annb_index *ix, int64_t n_refine, int64_t lookahe
     unsigned long long pc[2] = {0, 0};
     ANNB_CUDA(cudaMemcpyAsync(pc, ix->counters.p, 16, cudaMemcpyDeviceToHost, c->stream));
     ANNB_CUDA(cudaStreamSynchronize(c->stream));
-    ANNB_REQUIRE((int64_t)pc[0] == sel_target && (int64_t)pc[1] == tot_target - sel_target, ANNB_ESTATE,
-                 "selection cut produced %llu/%llu pairs for targets %lld/%lld", pc[0], pc[1],
-                 (long long)sel_target, (long long)(tot_target - sel_target));
+    uint64_t pg[2] = {pc[0], pc[1]};
+    ANNB_TRY(ix->reduce(pg, 2, ANNB_RED_U64));
+    ANNB_REQUIRE((int64_t)pg[0] == sel_target && (int64_t)pg[1] == tot_target - sel_target, ANNB_ESTATE,
+                 "selection cut produced %llu/%llu pairs for targets %lld/%lld",
+                 (unsigned long long)pg[0], (unsigned long long)pg[1], (long long)sel_target,
+                 (long long)(tot_target - sel_target));
     ix->n_sel = (int64_t)pc[0];
     ix->n_next = (int64_t)pc[1];
     if (n_selected) *n_selected = ix->n_sel;
@@ -1539,6 +1756,7 @@ ANNB_API int annb_index_refine_selected(annb_index *ix, int64_t *n_evals)
                              nullptr, KIND_KNOWN, m));
         ix->n_known += m;
     }
+    ix->n_refined = m;  // (sel_i, sel_j, t3) stay valid until the next select for annb_index_export_refined
     if (ix->has_forced) {
         // the -1 marks of guarantee_nmin do not survive the iteration (annchor.py:374-379)
         ANNB_LAUNCH(hash_retire_forced_kernel, grid_for_n(c, (int64_t)ix->hcap), 256, 0, c->stream,
@@ -1583,6 +1801,7 @@ ANNB_API int annb_index_update_bounds(annb_index *ix, int64_t *n_updated)
     ANNB_CUDA(cudaSetDevice(c->device));
     const int64_t m = ix->n_next;
     if (n_updated) *n_updated = 0;
+    ix->n_tightened = 0;
     if (m == 0) return ANNB_OK;
     ANNB_TRY(build_known_csr(ix));
     ANNB_TRY(ix->t0.ensure((size_t)m * 4));
@@ -1593,9 +1812,54 @@ ANNB_API int annb_index_update_bounds(annb_index *ix, int64_t *n_updated)
     ANNB_TRY(ix->t5.ensure((size_t)m * 4));
     ANNB_TRY(ix->t6.ensure((size_t)m * 4));
     const View V = ix->view();
-    ANNB_LAUNCH(tighten_kernel, c->num_sms * 8, 256, 0, c->stream, V, ix->kptr.as<int64_t>(),
-                ix->kids.as<int32_t>(), ix->kds.as<float>(), ix->nxt_i.as<int32_t>(),
-                ix->nxt_j.as<int32_t>(), m, ix->t0.as<float>(), ix->t1.as<float>(), ix->t2.as<uint8_t>());
+    // group the look-ahead pairs by their lower endpoint
+    const int64_t n = ix->n;
+    ANNB_TRY(ix->kdeg.ensure((size_t)(n + 1) * 4));
+    ANNB_TRY(ix->gptr.ensure((size_t)(n + 1) * 8));
+    ANNB_TRY(ix->gJ.ensure((size_t)m * 4));
+    ANNB_TRY(ix->gsrc.ensure((size_t)m * 4));
+    ANNB_CUDA(cudaMemsetAsync(ix->kdeg.p, 0, (size_t)(n + 1) * 4, c->stream));
+    ANNB_LAUNCH(count_by_lo_kernel, grid_for_n(c, m), 256, 0, c->stream, ix->nxt_i.as<int32_t>(),
+                ix->nxt_j.as<int32_t>(), m, ix->kptr.as<int64_t>(), ix->kdeg.as<int32_t>());
+    ANNB_LAUNCH(exclusive_scan_kernel, 1, 1024, 0, c->stream, ix->kdeg.as<int32_t>(),
+                ix->gptr.as<int64_t>(), n);
+    ANNB_CUDA(cudaMemsetAsync(ix->kdeg.p, 0, (size_t)(n + 1) * 4, c->stream));
+    ANNB_LAUNCH(scatter_by_lo_kernel, grid_for_n(c, m), 256, 0, c->stream, ix->nxt_i.as<int32_t>(),
+                ix->nxt_j.as<int32_t>(), m, ix->kptr.as<int64_t>(), ix->gptr.as<int64_t>(),
+                ix->kdeg.as<int32_t>(), ix->gJ.as<int32_t>(), ix->gsrc.as<int32_t>());
+    if (g_debug_sync) {
+        unsigned long long w[3] = {0, 0, 0};
+        ANNB_CUDA(cudaMemsetAsync(ix->counters.p, 0, 64, c->stream));
+        ANNB_LAUNCH(tighten_work_kernel, grid_for_n(c, n), 256, 0, c->stream, ix->kptr.as<int64_t>(),
+                    ix->gptr.as<int64_t>(), ix->gJ.as<int32_t>(), n, ix->counters.as<unsigned long long>());
+        ANNB_CUDA(cudaMemcpyAsync(w, ix->counters.p, 24, cudaMemcpyDeviceToHost, c->stream));
+        ANNB_CUDA(cudaStreamSynchronize(c->stream));
+        fprintf(stderr, "[annb] tighten: %lld pairs, sum deg_j = %llu (%.1f/pair), sum min(deg) = %llu, max deg = %llu, csr = %lld\n",
+                (long long)m, w[0], (double)w[0] / (double)m, w[1], w[2], (long long)ix->csr_entries);
+    }
+    if (ix->row_order.p == nullptr) {
+        ANNB_TRY(ix->row_order.ensure((size_t)n * 4));
+        int32_t hcnt[kMaxAnchors], hoff[kMaxAnchors];
+        ANNB_CUDA(cudaMemsetAsync(ix->counters.p, 0, 256, c->stream));
+        ANNB_LAUNCH(cA_hist_kernel, grid_for_n(c, n), 256, 0, c->stream, ix->meta.as<PointMeta>(), n,
+                    ix->counters.as<int32_t>());
+        ANNB_CUDA(cudaMemcpyAsync(hcnt, ix->counters.p, sizeof(hcnt), cudaMemcpyDeviceToHost, c->stream));
+        ANNB_CUDA(cudaStreamSynchronize(c->stream));
+        int32_t acc = 0;
+        for (int a = 0; a < kMaxAnchors; ++a) {
+            hoff[a] = acc;
+            acc += hcnt[a];
+        }
+        ANNB_CUDA(cudaMemcpyAsync(ix->counters.p, hoff, sizeof(hoff), cudaMemcpyHostToDevice, c->stream));
+        ANNB_LAUNCH(cA_scatter_kernel, grid_for_n(c, n), 256, 0, c->stream, ix->meta.as<PointMeta>(), n,
+                    ix->counters.as<int32_t>(), ix->row_order.as<int32_t>());
+    }
+    ANNB_CUDA(cudaFuncSetAttribute(tighten_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   TG_SLOTS * 8));
+    ANNB_LAUNCH(tighten_grouped_kernel, c->num_sms * 3, 256, TG_SLOTS * 8, c->stream, V, ix->kptr.as<int64_t>(),
+                ix->kids.as<int32_t>(), ix->kds.as<float>(), ix->gptr.as<int64_t>(), ix->gJ.as<int32_t>(),
+                ix->gsrc.as<int32_t>(), ix->row_order.as<int32_t>(), ix->t0.as<float>(),
+                ix->t1.as<float>(), ix->t2.as<uint8_t>());
     ANNB_CUDA(cudaMemsetAsync(ix->counters.p, 0, 64, c->stream));
     ANNB_LAUNCH(compact_improved_kernel, grid_for_n(c, m), 256, 0, c->stream, ix->nxt_i.as<int32_t>(),
                 ix->nxt_j.as<int32_t>(), ix->t0.as<float>(), ix->t1.as<float>(), ix->t2.as<uint8_t>(), m,
@@ -1607,6 +1871,7 @@ ANNB_API int annb_index_update_bounds(annb_index *ix, int64_t *n_updated)
     ANNB_TRY(hash_insert(ix, ix->t3.as<int32_t>(), ix->t4.as<int32_t>(), ix->t5.as<float>(),
                          ix->t6.as<float>(), KIND_TIGHT, (int64_t)k));
     ix->n_tight += (int64_t)k;
+    ix->n_tightened = (int64_t)k;  // (t3, t4, t5, t6) stay valid for annb_index_export_tightened
     if (n_updated) *n_updated = (int64_t)k;
     ix->n_next = 0;
     return ANNB_OK;
@@ -1688,8 +1953,8 @@ ANNB_API int annb_index_sample_pool(annb_index *ix, uint64_t seed, int64_t max_p
         A.out_cap = (unsigned long long)cap;
         ANNB_CUDA(cudaMemsetAsync(ix->counters.p, 0, 64, c->stream));
         A.counter = ix->counters.as<unsigned long long>();
-        A.rank = ix->P.rank;
-        A.world = ix->P.world;
+        A.rank = 0;  // the pool is cheap and replicated: every rank sweeps every tile
+        A.world = 1;
         ANNB_TRY(launch_sample_sweep(c, A));
         ix->sweeps += 1;
         unsigned long long got = 0;
@@ -1703,7 +1968,7 @@ ANNB_API int annb_index_sample_pool(annb_index *ix, uint64_t seed, int64_t max_p
                      (long long)n_nc);
         frac *= 0.7 * (double)cap / (double)got;
     }
-    if (all && ix->P.world == 1)
+    if (all)
         ANNB_REQUIRE(ix->n_pool == n_nc, ANNB_ESTATE,
                      "pool sweep found %lld not-computed candidates, bookkeeping says %lld",
                      (long long)ix->n_pool, (long long)n_nc);
@@ -1728,5 +1993,67 @@ ANNB_API int annb_index_get_pool(annb_index *ix, int64_t *ij, double *dad)
         ij[2 * p + 1] = (int64_t)(k[p] & 0xffffffffu);
         dad[p] = d[p];
     }
+    return ANNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// multi-GPU plumbing: reducer hook + device-to-device export / import of per-rank results
+// ---------------------------------------------------------------------------------------------
+ANNB_API int annb_index_set_reducer(annb_index *ix, annb_reduce_fn fn, void *user)
+{
+    ANNB_REQUIRE(ix != nullptr, ANNB_EINVAL, "index is NULL");
+    ix->reducer = fn;
+    ix->reducer_user = user;
+    return ANNB_OK;
+}
+
+ANNB_API int annb_index_export_refined(annb_index *ix, int32_t *i_dev, int32_t *j_dev, float *d_dev,
+                                       int64_t cap, int64_t *n)
+{
+    ANNB_REQUIRE(ix && n, ANNB_EINVAL, "NULL argument");
+    annb_ctx *c = ix->ctx;
+    ANNB_CUDA(cudaSetDevice(c->device));
+    *n = ix->n_refined;
+    if (ix->n_refined == 0 || !i_dev) return ANNB_OK;
+    ANNB_REQUIRE(cap >= ix->n_refined, ANNB_ERANGE, "export buffer too small");
+    const size_t b = (size_t)ix->n_refined * 4;
+    ANNB_CUDA(cudaMemcpyAsync(i_dev, ix->sel_i.p, b, cudaMemcpyDeviceToDevice, c->stream));
+    ANNB_CUDA(cudaMemcpyAsync(j_dev, ix->sel_j.p, b, cudaMemcpyDeviceToDevice, c->stream));
+    ANNB_CUDA(cudaMemcpyAsync(d_dev, ix->t3.p, b, cudaMemcpyDeviceToDevice, c->stream));
+    ANNB_CUDA(cudaStreamSynchronize(c->stream));
+    return ANNB_OK;
+}
+
+ANNB_API int annb_index_export_tightened(annb_index *ix, int32_t *i_dev, int32_t *j_dev, float *lb_dev,
+                                         float *ub_dev, int64_t cap, int64_t *n)
+{
+    ANNB_REQUIRE(ix && n, ANNB_EINVAL, "NULL argument");
+    annb_ctx *c = ix->ctx;
+    ANNB_CUDA(cudaSetDevice(c->device));
+    *n = ix->n_tightened;
+    if (ix->n_tightened == 0 || !i_dev) return ANNB_OK;
+    ANNB_REQUIRE(cap >= ix->n_tightened, ANNB_ERANGE, "export buffer too small");
+    const size_t b = (size_t)ix->n_tightened * 4;
+    ANNB_CUDA(cudaMemcpyAsync(i_dev, ix->t3.p, b, cudaMemcpyDeviceToDevice, c->stream));
+    ANNB_CUDA(cudaMemcpyAsync(j_dev, ix->t4.p, b, cudaMemcpyDeviceToDevice, c->stream));
+    ANNB_CUDA(cudaMemcpyAsync(lb_dev, ix->t5.p, b, cudaMemcpyDeviceToDevice, c->stream));
+    ANNB_CUDA(cudaMemcpyAsync(ub_dev, ix->t6.p, b, cudaMemcpyDeviceToDevice, c->stream));
+    ANNB_CUDA(cudaStreamSynchronize(c->stream));
+    return ANNB_OK;
+}
+
+// kind: 1 = exactly known (a = distance), 2 = tightened (a, b) = (lb, ub); all pointers device
+ANNB_API int annb_index_import_dev(annb_index *ix, int kind, const int32_t *i_dev, const int32_t *j_dev,
+                                   const float *a_dev, const float *b_dev, int64_t n)
+{
+    ANNB_REQUIRE(ix != nullptr, ANNB_EINVAL, "index is NULL");
+    ANNB_REQUIRE(kind == (int)KIND_KNOWN || kind == (int)KIND_TIGHT, ANNB_EINVAL, "kind must be 1 or 2");
+    if (n == 0) return ANNB_OK;
+    ANNB_REQUIRE(i_dev && j_dev && a_dev, ANNB_EINVAL, "NULL buffer");
+    ANNB_CUDA(cudaSetDevice(ix->ctx->device));
+    ANNB_TRY(hash_insert(ix, i_dev, j_dev, a_dev, kind == (int)KIND_TIGHT ? b_dev : nullptr, (uint32_t)kind, n));
+    if (kind == (int)KIND_KNOWN) ix->n_known += n;
+    else ix->n_tight += n;
+    ANNB_CUDA(cudaStreamSynchronize(ix->ctx->stream));
     return ANNB_OK;
 }

@@ -58,6 +58,8 @@ struct View {
     int64_t n, npad;
     int na, T, nn, is_metric;
     const float *D32;          // (na, npad) anchor-major
+    const float *Dpm;          // (npad, dpitch) point-major copy (one coalesced row per point)
+    int dpitch;
     const PointMeta *meta;     // npad
     const HashSlot *htab;
     uint64_t hmask;            // capacity - 1

@@ -95,6 +95,7 @@ __device__ __forceinline__ void bounds_microtile(const float *__restrict__ sDi,
 struct __align__(16) TileModel {
     float4 cf[MAX_BINS];   // (c0, c1, c2 / 2, intercept) per bin (regressors.py:39-67)
     float e2[MAX_BINS];    // 2 * interior edge k (k = 1..nb-1), +inf beyond: compared against 2 * dad
+    float mg[MAX_BINS];    // scoring only: conservative per-bin margin min(efloor[b], efloor[b+1])
 };
 
 __device__ __forceinline__ void build_tile_model(const Model &M, TileModel *tm)
@@ -104,29 +105,35 @@ __device__ __forceinline__ void build_tile_model(const Model &M, TileModel *tm)
         const bool live = t < M.nb;
         tm->cf[t] = live ? make_float4(M.c0[t], M.c1[t], 0.5f * M.c2[t], M.ic[t]) : make_float4(0, 0, 0, 0);
         tm->e2[t] = (t >= 1 && t < M.nb) ? 2.0f * M.edge[t] : INFINITY;
+        tm->mg[t] = 0.0f;
     }
 }
 
-// s = 2 * dad.  Regression bin (lo, hi]: number of interior edges strictly below dad (regressors.py:85-87)
+// s = 2 * dad.  Regression bin (lo, hi]: number of interior edges strictly below dad
+// (regressors.py:85-87), found with a 3-level compare tree over the 7 (padded) edges.
 __device__ __forceinline__ int reg_bin2(const TileModel *tm, float s)
 {
-    int b = 0;
-#pragma unroll
-    for (int k = 1; k < MAX_BINS; ++k) b += (s > tm->e2[k]);
-    return b;
+    const bool p4 = s > tm->e2[4];
+    const bool p2 = s > (p4 ? tm->e2[6] : tm->e2[2]);
+    const float lo = p2 ? tm->e2[3] : tm->e2[1], hi = p2 ? tm->e2[7] : tm->e2[5];
+    const bool p1 = s > (p4 ? hi : lo);
+    return (p4 ? 4 : 0) + (p2 ? 2 : 0) + (p1 ? 1 : 0);
 }
-// error label / sampler bin: closed [lo, hi] with later bins winning (error_predictors.py:63-66)
+// error label / sampler bin: closed [lo, hi] with later bins winning (error_predictors.py:63-66):
+// number of interior edges <= dad
 __device__ __forceinline__ int err_label2(const TileModel *tm, float s)
 {
-    int b = 0;
-#pragma unroll
-    for (int k = 1; k < MAX_BINS; ++k) b += (s >= tm->e2[k]);
-    return b;
+    const bool p4 = s >= tm->e2[4];
+    const bool p2 = s >= (p4 ? tm->e2[6] : tm->e2[2]);
+    const float lo = p2 ? tm->e2[3] : tm->e2[1], hi = p2 ? tm->e2[7] : tm->e2[5];
+    const bool p1 = s >= (p4 ? hi : lo);
+    return (p4 ? 4 : 0) + (p2 ? 2 : 0) + (p1 ? 1 : 0);
 }
 // clip(lb*c0 + ub*c1 + dad*c2 + icpt, lb, ub)  (annchor.py:356-363); identical code in both phases
-__device__ __forceinline__ float predict_clip2(const TileModel *tm, float lb, float ub, float s)
+__device__ __forceinline__ float predict_clip2(const TileModel *tm, float lb, float ub, float s, int &bin)
 {
-    const float4 cf = tm->cf[reg_bin2(tm, s)];
+    bin = reg_bin2(tm, s);
+    const float4 cf = tm->cf[bin];
     const float y = fmaf(lb, cf.x, fmaf(ub, cf.y, fmaf(s, cf.z, cf.w)));
     return fminf(fmaxf(y, lb), ub);
 }
@@ -158,6 +165,10 @@ __device__ __forceinline__ void transpose_bitmap(const uint32_t *src, uint32_t *
 __device__ __forceinline__ int stage_row(Survivor *q, int qn, const float (&lb)[8], const float (&ub)[8],
                                          const bool (&keep)[8], int li, int tx, int lane)
 {
+    bool any = false;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) any |= keep[c];
+    if (!__any_sync(0xffffffffu, any)) return qn;  // common case: nothing in this row step survives
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
         const unsigned m = __ballot_sync(0xffffffffu, keep[c]);
@@ -223,7 +234,8 @@ __device__ __forceinline__ PairVal pair_value(const View &V, const TileModel *tm
             return out;
         }
     }
-    out.v = predict_clip2(tm, lb, ub, s);
+    int bin;
+    out.v = predict_clip2(tm, lb, ub, s, bin);
     if (!V.is_metric && anchorpair) {
         // annchor.py:368-372: anchor distances written explicitly; the later anchor in A wins
         out.v = (pj.slot > pi.slot) ? sDi[pj.slot * SROW + li] : sDj[pi.slot * SROW + lj];

@@ -77,6 +77,13 @@ __global__ void __launch_bounds__(256, 1) score_sweep_kernel(const ScoreArgs A)
     TileModel *tm = reinterpret_cast<TileModel *>(thJ + 2 * TILE);
     uint32_t *sHist = reinterpret_cast<uint32_t *>(tm + 1);
     build_tile_model(A.M, tm);
+    if (tid < MAX_BINS) {
+        // the error label of a pair is its regression bin b, or b + 1 when dad sits exactly on an edge
+        const int t1 = tid + 1 < A.M.nb ? tid + 1 : (A.M.nb > 0 ? A.M.nb - 1 : 0);
+        float m = tid < A.M.nb ? fminf(A.efloor[tid], A.efloor[t1]) : INFINITY;
+        if (A.ef_min == -INFINITY) m = -INFINITY;  // filter off (floor 0 or non-metric)
+        tm->mg[tid] = m;
+    }
 
     for (int k = tid; k < A.nlevels; k += blockDim.x) sHist[k] = 0;
 
@@ -132,14 +139,14 @@ __global__ void __launch_bounds__(256, 1) score_sweep_kernel(const ScoreArgs A)
         int cAj[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-            cj[c] = tJ[micro_off(tx, c)] - A.ef_min;
+            cj[c] = tJ[micro_off(tx, c)];
             cAj[c] = sMj[micro_off(tx, c)].cA * SROW;
         }
         const bool diag = ti == tj;
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
             const int li = micro_off(ty, r);
-            const float ci = tI[li] - A.ef_min;
+            const float ci = tI[li];
             const float *dj_row = sDj + sMi[li].cA * SROW;
             uint32_t w0, w1;
             flag_words(bm, li, tx, w0, w1);
@@ -148,9 +155,11 @@ __global__ void __launch_bounds__(256, 1) score_sweep_kernel(const ScoreArgs A)
             for (int c = 0; c < 8; ++c) {
                 const int lj = micro_off(tx, c);
                 const float s2 = sDi[cAj[c] + li] + dj_row[lj];
-                const float y = predict_clip2(tm, lb[r][c], ub[r][c], s2);
+                int bin;
+                const float y = predict_clip2(tm, lb[r][c], ub[r][c], s2, bin);
                 const uint32_t fl = c < 4 ? (w0 >> c) : (w1 >> (c - 4));
-                keep[c] = ((y < fmaxf(ci, cj[c])) | (fl & 1u)) && (!diag || li < lj);
+                // level >= floor needs  max(th_i, th_j) - RefineApprox > efloor[label]
+                keep[c] = ((y + tm->mg[bin] < fmaxf(ci, cj[c])) | (fl & 1u)) && (!diag || li < lj);
             }
             const int qn = stage_row(queue, 0, lb[r], ub[r], keep, li, tx, lane);
             __syncwarp();

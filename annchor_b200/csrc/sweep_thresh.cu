@@ -142,7 +142,8 @@ __global__ void __launch_bounds__(256, 1) thresh_sweep_kernel(const ThreshArgs A
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     const float s2 = sDi[cAj[c] + li] + dj_row[micro_off(tx, c)];
-                    const float y = predict_clip2(tm, lb[r][c], ub[r][c], s2);
+                    int bin;
+                    const float y = predict_clip2(tm, lb[r][c], ub[r][c], s2, bin);
                     const uint32_t fl = c < 4 ? (w0 >> c) : (w1 >> (c - 4));
                     keep[c] = (y < cr) | (fl & 1u);
                 }

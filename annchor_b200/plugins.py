@@ -97,19 +97,20 @@ class SimpleStratifiedSampler:
     (annchor/samplers.py:113-140, annchor/utils.py:543-578).
 
     The device returns a uniform pool of the not-computed candidates (annb_index_sample_pool).
-      * exact mode -- at most ``max_pool`` such pairs exist (N up to a few thousand): the pool is
+      * exact mode -- at most ``exact_limit`` such pairs exist (N up to a few thousand): the pool is
         all of them; sorted by (i, j) it is the reference's ``indices`` array, dad is recomputed in
         float64 from D, and the reference's algorithm runs verbatim including numba's MT19937
         Fisher-Yates draw -- the sample equals the reference's bit for bit.
       * pool mode -- larger problems: the 1 % / 99 % order statistics and the per-bin uniform
-        draws are taken on the hash-selected pool (a uniform sub-sample of ~max_pool pairs), since
+        draws are taken on the hash-selected pool (a uniform sub-sample of ~pool_size pairs), since
         the reference's draw needs the materialised Theta(N^2) pair list."""
 
     def __init__(self, partition_feature_name="double anchor distance", n_partitions=7,
-                 max_pool=4_000_000):
+                 exact_limit=4_000_000, pool_size=1_000_000):
         self.partition_feature_name = partition_feature_name
         self.n_partitions = n_partitions
-        self.max_pool = max_pool
+        self.exact_limit = exact_limit   # at most this many not-computed candidates -> exact mode
+        self.pool_size = pool_size       # size of the uniform pool otherwise
         self.loop_num = 0
 
     def get_partition(self, sample_feature, n_samples, n_total=None):
@@ -134,7 +135,9 @@ class SimpleStratifiedSampler:
     def sample_index(self, ann):
         ix = ann._index
         seed = int(ann.random_seed) + self.loop_num
-        n_pool, n_nc, exact = ix.sample_pool(seed, self.max_pool)
+        n_nc = ix.stats()["n_not_computed"]
+        n_pool, n_nc, exact = ix.sample_pool(seed, self.exact_limit if n_nc <= self.exact_limit
+                                             else self.pool_size)
         if n_nc <= 0 or n_pool == 0:
             raise NothingToSample()
         ijs, dad = ix.get_pool()
@@ -154,7 +157,15 @@ class SimpleStratifiedSampler:
             raise NothingToSample()
         bin_size, rem = n_samples // self.n_partitions, n_samples % self.n_partitions
         indices = np.arange(sf.shape[0])
-        rng = NumbaRNG(seed) if exact else np.random.RandomState(seed & 0xFFFFFFFF)
+        rng = NumbaRNG(seed) if exact else None
+        if not exact:
+            # order-independent priorities (the pool arrives in atomic order): splitmix64 of the pair
+            key = (ijs[:, 0].astype(np.uint64) << np.uint64(32)) | ijs[:, 1].astype(np.uint64)
+            with np.errstate(over="ignore"):
+                z = key + np.uint64((seed * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF)
+                z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+                z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+                prio = z ^ (z >> np.uint64(31))
         self.loop_num += 1
         parts = []
         for b in range(self.n_partitions):
@@ -164,8 +175,8 @@ class SimpleStratifiedSampler:
                 parts.append(ixmask)
             elif exact:
                 parts.append(rng.choice_no_replace(ixmask, want))
-            else:
-                parts.append(rng.choice(ixmask, size=want, replace=False))
+            else:  # uniform without replacement: the `want` smallest priorities of the bin
+                parts.append(ixmask[np.argpartition(prio[ixmask], want - 1)[:want]] if want > 0 else ixmask[:0])
             if parts[-1].shape[0] < 2:
                 raise Exception("Some sampler bins contain too few samples")
         sel = np.hstack(parts)

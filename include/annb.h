@@ -202,6 +202,27 @@ int annb_index_stats(annb_index *ix, int64_t *out, int64_t n);
 /* device-time (ms) of the last sweep kernel and the pairs it covered */
 int annb_index_last_sweep(annb_index *ix, float *ms, int64_t *pairs);
 
+/* ---- multi-GPU (no counterpart in the single-host reference) ----------------------
+ * An index created with world > 1 sweeps only its shard of the tiles.  Small host-side reductions
+ * (thresholds, level / digit histograms, branch flags) go through a caller-supplied sum all-reduce;
+ * bulk per-rank results (evaluated pairs, tightened bounds) are exported device-to-device for the
+ * caller's NCCL all-gather and imported on the other ranks. */
+#define ANNB_RED_U64 0
+#define ANNB_RED_F32 1
+#define ANNB_RED_I32 2
+/* in-place sum all-reduce over `count` elements of `dtype` in host memory; returns 0 on success */
+typedef int (*annb_reduce_fn)(void *user, void *buf, int64_t count, int dtype);
+int annb_index_set_reducer(annb_index *ix, annb_reduce_fn fn, void *user);
+/* pairs this rank evaluated in the last annb_index_refine_selected: device int32 i, j and float d */
+int annb_index_export_refined(annb_index *ix, int32_t *i_dev, int32_t *j_dev, float *d_dev,
+                              int64_t cap, int64_t *n);
+/* bounds this rank tightened in the last annb_index_update_bounds */
+int annb_index_export_tightened(annb_index *ix, int32_t *i_dev, int32_t *j_dev, float *lb_dev,
+                                float *ub_dev, int64_t cap, int64_t *n);
+/* insert entries received from other ranks: kind 1 = known (a = d), 2 = tightened (a, b) = (lb, ub) */
+int annb_index_import_dev(annb_index *ix, int kind, const int32_t *i_dev, const int32_t *j_dev,
+                          const float *a_dev, const float *b_dev, int64_t n);
+
 /* brute-force k-NN on device (recall oracle at sizes where the CPU cannot;
  * annchor/annchor.py:943-1023): idx int64 (n,k), dist float64 (n,k), column 0 = self */
 int annb_bruteforce_knn(annb_ctx *ctx, const annb_dataset *ds, int metric, int64_t k,
