@@ -158,6 +158,25 @@ class Index:
         check(self._L.annb_index_last_sweep(self.handle, C.byref(ms), C.byref(pairs)))
         return ms.value, pairs.value
 
+    # -- multi-GPU hooks (annchor_b200.dist) ---------------------------------------------------
+    def set_reducer(self, cb):
+        self._reducer = cb  # keep the ctypes callback alive as long as the index
+        check(self._L.annb_index_set_reducer(self.handle, C.cast(cb, C.c_void_p), None))
+
+    def export_refined(self, i_dev, j_dev, d_dev, cap):
+        n = C.c_int64()
+        check(self._L.annb_index_export_refined(self.handle, i_dev, j_dev, d_dev, int(cap), C.byref(n)))
+        return n.value
+
+    def export_tightened(self, i_dev, j_dev, lb_dev, ub_dev, cap):
+        n = C.c_int64()
+        check(self._L.annb_index_export_tightened(self.handle, i_dev, j_dev, lb_dev, ub_dev, int(cap),
+                                                  C.byref(n)))
+        return n.value
+
+    def import_dev(self, kind, i_dev, j_dev, a_dev, b_dev, n):
+        check(self._L.annb_index_import_dev(self.handle, int(kind), i_dev, j_dev, a_dev, b_dev, int(n)))
+
 
 class Annchor:
     """Quickly computes the approximate k-NN graph for slow metrics -- on a B200.
@@ -173,7 +192,7 @@ class Annchor:
                  p_work=0.1, anchor_picker=None, sampler=None, regression=None, error_predictor=None,
                  random_seed=42, locality=5, loc_thresh=1, loc_min=None, verbose=False, is_metric=True,
                  get_exact_ijs=None, backend="loky", niters=2, lookahead=5, device=0, ctx=None,
-                 _dataset=None):
+                 comm=None, _dataset=None):
         if not isinstance(func, str):
             raise NotImplementedError(
                 "annchor_b200 evaluates metrics on the GPU; pass one of 'euclidean', 'cosine', "
@@ -234,8 +253,17 @@ class Annchor:
         self._plug = GpuExactIJs(func, self.ctx, cost)
         self._plug._cache = (X, self._dataset)
         self.get_exact_ijs = self._plug  # same call contract as annchor/annchor.py:77-82
+        # comm: an annchor_b200.dist.Comm -- this process is one rank of a sharded fit (every rank
+        # calls fit() with the same X and arguments; the tile sweeps are split, results identical)
+        self.comm = comm
+        rank, world = (comm.rank, comm.world) if comm is not None else (0, 1)
         self._index = Index(self.ctx, self._dataset, n_anchors, n_neighbors, locality, loc_thresh,
-                            self.loc_min, is_metric)
+                            self.loc_min, is_metric, rank=rank, world=world)
+        self._xchg = None
+        if comm is not None and world > 1:
+            from .dist import IndexExchange
+            self._index.set_reducer(comm.reducer)
+            self._xchg = IndexExchange(self._index, comm)
         self._D = None
         self.stage_times = {}
 
@@ -290,10 +318,17 @@ class Annchor:
         n_refine = 0 if n_refine < 0 else n_refine
         self.n_refine = n_refine
         self._index.select(n_refine, self.lookahead)
-        self.evals += self._index.refine_selected()
+        n_eval = self._index.refine_selected()
+        if self._xchg is not None:  # every rank evaluated its own share: make all stores identical
+            self._xchg.refined()
+            n_eval = self.comm.all_reduce_sum(n_eval)
+        self.evals += n_eval
 
     def update_anchor_points(self):
         self.n_tightened = self._index.update_bounds()
+        if self._xchg is not None:
+            self._xchg.tightened()
+            self.n_tightened = self.comm.all_reduce_sum(self.n_tightened)
 
     def get_ann(self):
         self.neighbor_graph = self._index.neighbor_graph()

@@ -518,7 +518,8 @@ __global__ void cA_scatter_kernel(const PointMeta *__restrict__ meta, int64_t n,
 
 __global__ void tighten_work_kernel(const int64_t *__restrict__ kptr, const int64_t *__restrict__ gptr,
                                     const int32_t *__restrict__ gJ, int64_t n,
-                                    unsigned long long *__restrict__ out /* [0] sum deg_j, [1] sum min, [2] max deg */)
+                                    unsigned long long *__restrict__ out /* [0] sum deg_j, [1] sum min, [2] max deg */,
+                                    unsigned long long *__restrict__ row_work /* [n] sum deg_j of the row's group */)
 {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -530,6 +531,7 @@ __global__ void tighten_work_kernel(const int64_t *__restrict__ kptr, const int6
             s += dj;
             sm += dj < di ? dj : di;
         }
+        if (row_work) row_work[i] = s;
         atomicAdd(&out[0], s);
         atomicAdd(&out[1], sm);
         atomicMax(&out[2], di);
@@ -1326,20 +1328,13 @@ static int run_thresh(annb_index *ix, int k2)
     ix->pairs_swept += ix->n * (ix->n - 1) / ix->P.world;
     ix->sweeps += 1;
     if (ix->P.world > 1) {
-        // every row block was computed by exactly one rank: sum-reduce the slices through the host
-        auto exchange = [&](DevBuf &b, size_t count, int dtype) -> int {
-            std::vector<uint32_t> h(count);
-            ANNB_CUDA(cudaMemcpyAsync(h.data(), b.p, count * 4, cudaMemcpyDeviceToHost, c->stream));
-            ANNB_CUDA(cudaStreamSynchronize(c->stream));
-            ANNB_TRY(ix->reduce(h.data(), (int64_t)count, dtype));
-            ANNB_CUDA(cudaMemcpyAsync(b.p, h.data(), count * 4, cudaMemcpyHostToDevice, c->stream));
-            ANNB_CUDA(cudaStreamSynchronize(c->stream));
-            return ANNB_OK;
-        };
-        ANNB_TRY(exchange(ix->thresh, (size_t)ix->npad, ANNB_RED_F32));
+        // every row block was computed by exactly one rank (the others hold zeros): a sum
+        // all-reduce of the device buffers assembles the full vectors on every rank
+        ANNB_CUDA(cudaStreamSynchronize(c->stream));
+        ANNB_TRY(ix->reduce(ix->thresh.p, ix->npad, ANNB_RED_F32 | ANNB_RED_DEVICE));
         if (k2 > 0) {
-            ANNB_TRY(exchange(ix->l2val, (size_t)ix->n * k2, ANNB_RED_F32));
-            ANNB_TRY(exchange(ix->l2id, (size_t)ix->n * k2, ANNB_RED_I32));
+            ANNB_TRY(ix->reduce(ix->l2val.p, ix->n * k2, ANNB_RED_F32 | ANNB_RED_DEVICE));
+            ANNB_TRY(ix->reduce(ix->l2id.p, ix->n * k2, ANNB_RED_I32 | ANNB_RED_DEVICE));
         }
     }
     ix->have_thresh = true;
@@ -1830,12 +1825,43 @@ ANNB_API int annb_index_update_bounds(annb_index *ix, int64_t *n_updated)
     if (g_debug_sync) {
         unsigned long long w[3] = {0, 0, 0};
         ANNB_CUDA(cudaMemsetAsync(ix->counters.p, 0, 64, c->stream));
+        ANNB_TRY(ix->t5.ensure((size_t)n * 8));
         ANNB_LAUNCH(tighten_work_kernel, grid_for_n(c, n), 256, 0, c->stream, ix->kptr.as<int64_t>(),
-                    ix->gptr.as<int64_t>(), ix->gJ.as<int32_t>(), n, ix->counters.as<unsigned long long>());
+                    ix->gptr.as<int64_t>(), ix->gJ.as<int32_t>(), n, ix->counters.as<unsigned long long>(),
+                    ix->t5.as<unsigned long long>());
+        std::vector<unsigned long long> rw(n);
+        std::vector<int64_t> kp(n + 1), gp(n + 1);
         ANNB_CUDA(cudaMemcpyAsync(w, ix->counters.p, 24, cudaMemcpyDeviceToHost, c->stream));
+        ANNB_CUDA(cudaMemcpyAsync(rw.data(), ix->t5.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+        ANNB_CUDA(cudaMemcpyAsync(kp.data(), ix->kptr.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+        ANNB_CUDA(cudaMemcpyAsync(gp.data(), ix->gptr.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
         ANNB_CUDA(cudaStreamSynchronize(c->stream));
         fprintf(stderr, "[annb] tighten: %lld pairs, sum deg_j = %llu (%.1f/pair), sum min(deg) = %llu, max deg = %llu, csr = %lld\n",
                 (long long)m, w[0], (double)w[0] / (double)m, w[1], w[2], (long long)ix->csr_entries);
+        std::vector<int64_t> deg(n), gs(n);
+        for (int64_t i = 0; i < n; ++i) {
+            deg[i] = kp[i + 1] - kp[i];
+            gs[i] = gp[i + 1] - gp[i];
+        }
+        auto q = [&](std::vector<int64_t> v, const char *nm) {
+            std::sort(v.begin(), v.end());
+            fprintf(stderr, "[annb]   %s: p50 %lld p90 %lld p99 %lld p99.9 %lld max %lld\n", nm, (long long)v[n / 2],
+                    (long long)v[n * 9 / 10], (long long)v[n * 99 / 100], (long long)v[n * 999 / 1000], (long long)v[n - 1]);
+        };
+        q(deg, "known degree");
+        q(gs, "group size  ");
+        std::vector<int64_t> rwi(rw.begin(), rw.end());
+        q(rwi, "row work    ");
+        // imbalance of the static round-robin row -> CTA assignment
+        const int G = c->num_sms * 3;
+        std::vector<unsigned long long> cta(G, 0);
+        for (int64_t r = 0; r < n; ++r) cta[r % G] += rw[r];  // (ignores row_order; same statistics)
+        unsigned long long mx = 0, sm = 0;
+        for (int g = 0; g < G; ++g) {
+            mx = std::max(mx, cta[g]);
+            sm += cta[g];
+        }
+        fprintf(stderr, "[annb]   CTA work: max/mean = %.2f\n", (double)mx / ((double)sm / G));
     }
     if (ix->row_order.p == nullptr) {
         ANNB_TRY(ix->row_order.ensure((size_t)n * 4));

@@ -168,6 +168,10 @@ def run_ours(args, w):
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    comm = None
+    if world > 1:
+        from annchor_b200.dist import Comm
+        comm = Comm(device=torch.device("cuda", local))
     ctx = ab.default_context(local)
     X = make_blobs(w["N"], w["d"], w["centers"], w["seed"])
     Xpin = torch.from_numpy(X).pin_memory().numpy() if torch.cuda.is_available() else X
@@ -195,7 +199,7 @@ def run_ours(args, w):
             clocks.start()
             launches = ab.launch_count()
             t_region = time.time()
-        ann = Annchor(X, "euclidean", ctx=ctx, _dataset=ds, **kw)
+        ann = Annchor(X, "euclidean", ctx=ctx, comm=comm, _dataset=ds, **kw)
         ctx.timer_start()
         ann.fit()
         ms = ctx.timer_stop()
@@ -221,7 +225,7 @@ def run_ours(args, w):
         flush.fill_(it)
         barrier()
         t0 = time.perf_counter()
-        a2 = Annchor(Xpin, "euclidean", ctx=ctx, **kw).fit()
+        a2 = Annchor(Xpin, "euclidean", ctx=ctx, comm=comm, **kw).fit()
         g = a2.neighbor_graph
         ctx.sync()
         e2e_times.append(time.perf_counter() - t0)

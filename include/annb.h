@@ -210,7 +210,9 @@ int annb_index_last_sweep(annb_index *ix, float *ms, int64_t *pairs);
 #define ANNB_RED_U64 0
 #define ANNB_RED_F32 1
 #define ANNB_RED_I32 2
-/* in-place sum all-reduce over `count` elements of `dtype` in host memory; returns 0 on success */
+#define ANNB_RED_DEVICE 0x100 /* or-ed into dtype: buf is a device pointer on the index's GPU */
+/* in-place sum all-reduce over `count` elements of `dtype` (host memory unless ANNB_RED_DEVICE is
+ * set; the library has synchronised its stream before the call); returns 0 on success */
 typedef int (*annb_reduce_fn)(void *user, void *buf, int64_t count, int dtype);
 int annb_index_set_reducer(annb_index *ix, annb_reduce_fn fn, void *user);
 /* pairs this rank evaluated in the last annb_index_refine_selected: device int32 i, j and float d */
