@@ -33,6 +33,7 @@ _PP = C.POINTER(C.c_void_p)
 _SIGS = {
     "annb_ctx_create": [_I32, _PP],
     "annb_ctx_destroy": [_P],
+    "annb_pool_trim": [],
     "annb_sync": [_P],
     "annb_ctx_stream": [_P, C.POINTER(_U64)],
     "annb_timer_start": [_P],
@@ -55,6 +56,7 @@ _SIGS = {
     "annb_get_nn": [_P, _I64, _I64, _P, _P, _I64, _P, _P, _P, _P, _P],
     "annb_index_create": [_P, _P, _I32, C.POINTER(IndexParams), _PP],
     "annb_index_destroy": [_P],
+    "annb_index_reserve_pairs": [_P, _I64],
     "annb_index_maxmin": [_P, _I64, _P],
     "annb_index_set_anchors": [_P, _P, _I64, _P],
     "annb_index_get_D": [_P, _P],
@@ -93,7 +95,7 @@ def declared_symbols():
     """Every function name declared in include/annb.h (parsed from the header)."""
     import re
     hdr = open(os.path.join(_HERE, "..", "include", "annb.h")).read()
-    return sorted(set(re.findall(r"\b(annb_[a-z0-9_]+)\s*\(", hdr)) - {"annb_reduce_fn"})
+    return sorted(set(re.findall(r"\b(annb_[A-Za-z0-9_]+)\s*\(", hdr)) - {"annb_reduce_fn"})
 
 
 def load():

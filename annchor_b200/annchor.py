@@ -50,6 +50,9 @@ class Index:
         except Exception:
             pass
 
+    def reserve_pairs(self, n_pairs):
+        check(self._L.annb_index_reserve_pairs(self.handle, int(n_pairs)))
+
     def maxmin(self, first):
         A = np.empty(self.na, dtype=np.int64)
         check(self._L.annb_index_maxmin(self.handle, int(first), ptr(A)))
@@ -259,6 +262,12 @@ class Annchor:
         rank, world = (comm.rank, comm.world) if comm is not None else (0, 1)
         self._index = Index(self.ctx, self._dataset, n_anchors, n_neighbors, locality, loc_thresh,
                             self.loc_min, is_metric, rank=rank, world=world)
+        # size the known-pair store once: all exact evaluations + the look-ahead pairs that
+        # update_anchor_points may tighten (annchor.py:440,444-457)
+        budget = int(self.p_work * self.N)
+        n_ref = max(budget // max(niters, 1), 0)
+        self._index.reserve_pairs(min(budget + n_ref * (lookahead - 1) * max(niters - 1, 0) + n_samples * niters,
+                                      self.N) + 1024)
         self._xchg = None
         if comm is not None and world > 1:
             from .dist import IndexExchange

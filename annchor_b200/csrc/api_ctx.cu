@@ -1,6 +1,8 @@
 // api_ctx.cu -- contexts, datasets, error plumbing of libannb.so.
 #include <stdarg.h>
 
+#include <time.h>
+#include <mutex>
 #include "common.cuh"
 
 namespace annb {
@@ -8,6 +10,69 @@ namespace annb {
 static thread_local char g_err[1024] = "";
 int64_t g_launches = 0;
 bool g_debug_sync = getenv("ANNB_DEBUG_SYNC") != nullptr;
+bool g_trace = getenv("ANNB_TRACE") != nullptr;
+namespace {
+struct PoolBlock {
+    void *p;
+    size_t cap;
+    int dev;
+};
+std::vector<PoolBlock> g_pool;
+std::mutex g_pool_mu;
+}  // namespace
+
+void *pool_take(size_t bytes, size_t *cap)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    int best = -1;
+    for (int k = 0; k < (int)g_pool.size(); ++k) {
+        const PoolBlock &b = g_pool[k];
+        if (b.dev != dev || b.cap < bytes || b.cap > 2 * bytes + (8u << 20)) continue;
+        if (best < 0 || b.cap < g_pool[best].cap) best = k;
+    }
+    if (best < 0) return nullptr;
+    void *p = g_pool[best].p;
+    *cap = g_pool[best].cap;
+    g_pool.erase(g_pool.begin() + best);
+    return p;
+}
+
+void pool_give(void *p, size_t cap)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (g_pool.size() >= 512) {  // keep the pool bounded: drop the smallest block
+        int k0 = 0;
+        for (int k = 1; k < (int)g_pool.size(); ++k)
+            if (g_pool[k].cap < g_pool[k0].cap) k0 = k;
+        cudaFree(g_pool[k0].p);
+        g_pool.erase(g_pool.begin() + k0);
+    }
+    g_pool.push_back({p, cap, dev});
+}
+
+void pool_trim()
+{
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (const PoolBlock &b : g_pool) {
+        cudaSetDevice(b.dev);
+        cudaFree(b.p);
+    }
+    cudaSetDevice(cur);
+    g_pool.clear();
+}
+
+double now_ms()
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
 
 void set_error(const char *fmt, ...)
 {
@@ -101,6 +166,12 @@ ANNB_API int annb_ctx_create(int device, annb_ctx **out)
     return ANNB_OK;
 }
 
+ANNB_API int annb_pool_trim(void)
+{
+    pool_trim();
+    return ANNB_OK;
+}
+
 ANNB_API int annb_ctx_destroy(annb_ctx *c)
 {
     if (!c) return ANNB_OK;
@@ -108,6 +179,7 @@ ANNB_API int annb_ctx_destroy(annb_ctx *c)
     cudaStreamSynchronize(c->stream);
     for (auto &b : c->s_in) b.release();
     for (auto &b : c->s_out) b.release();
+    pool_trim();
     if (c->pinned) cudaFreeHost(c->pinned);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);

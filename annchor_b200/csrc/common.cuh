@@ -21,6 +21,17 @@ constexpr int kMaxAnchors = 64;
 void set_error(const char *fmt, ...);
 extern int64_t g_launches;
 extern bool g_debug_sync;
+extern bool g_trace;  // ANNB_TRACE=1: wall-clock of every index entry point and large allocation on stderr
+double now_ms();
+struct TraceScope {
+    const char *name;
+    double t0;
+    explicit TraceScope(const char *n) : name(n), t0(g_trace ? now_ms() : 0.0) {}
+    ~TraceScope()
+    {
+        if (g_trace) fprintf(stderr, "[annb-trace] %-34s %9.3f ms\n", name, now_ms() - t0);
+    }
+};
 
 #define ANNB_CUDA(expr)                                                                  \
     do {                                                                                 \
@@ -62,6 +73,13 @@ extern bool g_debug_sync;
         }                                                                         \
     } while (0)
 
+// Freed device blocks are kept in a per-process pool and handed out again (best fit) instead of
+// going back to the driver: cudaMalloc / cudaFree of the multi-GB index buffers cost milliseconds
+// each and cudaFree synchronises the device.  annb_pool_trim() / context destruction release them.
+void *pool_take(size_t bytes, size_t *cap);
+void pool_give(void *p, size_t cap);
+void pool_trim();
+
 // Device buffer with grow-only reuse (avoids cudaMalloc on the hot path).
 struct DevBuf {
     void *p = nullptr;
@@ -69,12 +87,18 @@ struct DevBuf {
     int ensure(size_t bytes)
     {
         if (bytes <= cap) return ANNB_OK;
-        if (p) cudaFree(p);
+        if (p) pool_give(p, cap);
         p = nullptr;
         cap = 0;
         size_t want = bytes + (bytes >> 3) + 256;
+        if ((p = pool_take(bytes, &cap)) != nullptr) return ANNB_OK;
+        const double t0 = g_trace ? now_ms() : 0.0;
         cudaError_t e = cudaMalloc(&p, want);
-        if (e != cudaSuccess) {
+        if (g_trace && want > (64u << 20))
+            fprintf(stderr, "[annb-trace]   cudaMalloc %.1f MB %9.3f ms\n", want / 1048576.0, now_ms() - t0);
+        if (e != cudaSuccess) {  // give cached blocks back to the driver and retry with the exact size
+            cudaGetLastError();
+            pool_trim();
             e = cudaMalloc(&p, bytes);
             want = bytes;
         }
@@ -89,7 +113,7 @@ struct DevBuf {
     }
     void release()
     {
-        if (p) cudaFree(p);
+        if (p) pool_give(p, cap);
         p = nullptr;
         cap = 0;
     }

@@ -278,46 +278,86 @@ __global__ void tie_hist_kernel(const uint64_t *__restrict__ keys, const uint16_
     }
 }
 
-// selected: lvl > c1 or (lvl == c1 and mix <= thr1); next: not selected and (lvl > c2 or
-// (lvl == c2 and mix <= thr2))
-__global__ void partition_emitted_kernel(const uint64_t *__restrict__ keys,
-                                         const uint16_t *__restrict__ lvl, int64_t E, int c1,
-                                         uint64_t thr1, int c2, uint64_t thr2,
-                                         int32_t *__restrict__ sel_i, int32_t *__restrict__ sel_j,
-                                         int32_t *__restrict__ nxt_i, int32_t *__restrict__ nxt_j,
-                                         unsigned long long *__restrict__ cnt /* [0] sel, [1] next */,
-                                         int64_t cap_sel, int64_t cap_next)
+// block-wide exclusive scan of a packed pair of 16-bit counts (lo | hi << 16); returns this
+// thread's exclusive prefix and the block total (256 threads, each count <= 8 per half)
+__device__ __forceinline__ uint32_t block_scan_packed(uint32_t v, uint32_t *s_warp /* [9] */, uint32_t &total)
 {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t b0 = warp * 32; b0 < E; b0 += nwarps * 32) {  // warp-uniform trip count
-        const int64_t p = b0 + lane;
-        const bool live = p < E;
-        const int l = live ? lvl[p] : -1;
-        const uint64_t key = live ? keys[p] : 0ull;
-        const uint64_t mk = mix64(key);
-        const bool sel = live && (l > c1 || (l == c1 && mk <= thr1));
-        const bool nxt = live && !sel && (l > c2 || (l == c2 && mk <= thr2));
-        const unsigned ms = __ballot_sync(0xffffffffu, sel), mn = __ballot_sync(0xffffffffu, nxt);
-        unsigned long long bs = 0, bn = 0;
-        if (lane == 0) {
-            if (ms) bs = atomicAdd(&cnt[0], (unsigned long long)__popc(ms));
-            if (mn) bn = atomicAdd(&cnt[1], (unsigned long long)__popc(mn));
-        }
-        bs = __shfl_sync(0xffffffffu, bs, 0);
-        bn = __shfl_sync(0xffffffffu, bn, 0);
-        if (sel) {
-            const unsigned long long s = bs + __popc(ms & ((1u << lane) - 1));
-            if ((int64_t)s < cap_sel) {
-                sel_i[s] = (int32_t)(key >> 32);
-                sel_j[s] = (int32_t)(key & 0xffffffffu);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    __syncthreads();  // protects s_warp across successive calls
+    if (lane == 31) s_warp[w] = x;
+    __syncthreads();
+    uint32_t base = 0, tot = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const uint32_t t = s_warp[q];
+        if (q < w) base += t;
+        tot += t;
+    }
+    total = tot;
+    return base + x - v;
+}
+
+constexpr int PE_ITEMS = 8;  // entries per thread per block step
+
+// selected: lvl > c1 or (lvl == c1 and mix <= thr1); next: not selected and (lvl > c2 or
+// (lvl == c2 and mix <= thr2)).  One pair of global atomics per 2048 entries.
+__global__ void __launch_bounds__(256)
+partition_emitted_kernel(const uint64_t *__restrict__ keys, const uint16_t *__restrict__ lvl, int64_t E,
+                         uint64_t salt, int c1, uint64_t thr1, int c2, uint64_t thr2, int32_t *__restrict__ sel_i,
+                         int32_t *__restrict__ sel_j, int32_t *__restrict__ nxt_i,
+                         int32_t *__restrict__ nxt_j, unsigned long long *__restrict__ cnt /* [0] sel, [1] next */,
+                         int64_t cap_sel, int64_t cap_next)
+{
+    __shared__ uint32_t s_warp[9];
+    __shared__ unsigned long long s_base[2];
+    const int64_t step = 256 * PE_ITEMS;
+    for (int64_t b0 = blockIdx.x * step; b0 < E; b0 += (int64_t)gridDim.x * step) {
+        uint64_t key[PE_ITEMS];
+        uint8_t cls[PE_ITEMS];  // 1 = selected, 2 = next
+        uint32_t mine = 0;
+#pragma unroll
+        for (int k = 0; k < PE_ITEMS; ++k) {
+            const int64_t p = b0 + k * 256 + threadIdx.x;
+            cls[k] = 0;
+            key[k] = 0;
+            if (p < E) {
+                const int l = lvl[p];
+                key[k] = keys[p];
+                const uint64_t mk = mix64(key[k] ^ salt);
+                const bool sel = l > c1 || (l == c1 && mk <= thr1);
+                const bool nxt = !sel && (l > c2 || (l == c2 && mk <= thr2));
+                cls[k] = sel ? 1 : (nxt ? 2 : 0);
+                mine += sel ? 1u : (nxt ? 0x10000u : 0u);
             }
-        } else if (nxt) {
-            const unsigned long long s = bn + __popc(mn & ((1u << lane) - 1));
-            if ((int64_t)s < cap_next) {
-                nxt_i[s] = (int32_t)(key >> 32);
-                nxt_j[s] = (int32_t)(key & 0xffffffffu);
+        }
+        uint32_t total;
+        const uint32_t ex = block_scan_packed(mine, s_warp, total);
+        if (threadIdx.x == 0) {
+            s_base[0] = (total & 0xffff) ? atomicAdd(&cnt[0], (unsigned long long)(total & 0xffff)) : 0ull;
+            s_base[1] = (total >> 16) ? atomicAdd(&cnt[1], (unsigned long long)(total >> 16)) : 0ull;
+        }
+        __syncthreads();
+        unsigned long long ps = s_base[0] + (ex & 0xffff), pn = s_base[1] + (ex >> 16);
+#pragma unroll
+        for (int k = 0; k < PE_ITEMS; ++k) {
+            if (cls[k] == 1) {
+                if ((int64_t)ps < cap_sel) {
+                    sel_i[ps] = (int32_t)(key[k] >> 32);
+                    sel_j[ps] = (int32_t)(key[k] & 0xffffffffu);
+                }
+                ++ps;
+            } else if (cls[k] == 2) {
+                if ((int64_t)pn < cap_next) {
+                    nxt_i[pn] = (int32_t)(key[k] >> 32);
+                    nxt_j[pn] = (int32_t)(key[k] & 0xffffffffu);
+                }
+                ++pn;
             }
         }
     }
@@ -538,75 +578,141 @@ __global__ void tighten_work_kernel(const int64_t *__restrict__ kptr, const int6
     }
 }
 
-constexpr int TG_SLOTS = 8192;   // shared-memory hash slots (64 KB dynamic shared memory)
+constexpr int TG_SLOTS = 8192;   // shared-memory table slots: 2048 buckets of 4 ids (+ 4 values)
 constexpr int TG_CHUNK = 4096;   // entries of N(i) hashed at a time (load factor <= 0.5)
 
+// rows whose group streams more than `thr` list entries are queued first (longest-processing-time
+// first keeps the dynamic row scheduler's tail short)
+__global__ void tighten_heavy_kernel(const unsigned long long *__restrict__ work, int64_t n,
+                                     unsigned long long thr, int32_t *__restrict__ heavy,
+                                     unsigned long long *__restrict__ n_heavy)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        if (work[i] >= thr) heavy[atomicAdd(n_heavy, 1ull)] = (int32_t)i;
+}
+
+// K2b.  Dynamic row scheduling (one atomic per row), bucketed shared-memory hash (4 ids per bucket,
+// one 128-bit probe, no divergent chains at load <= 0.25), partner lists streamed with the next
+// 128 entries in flight while the current ones are probed.
 __global__ void __launch_bounds__(256)
 tighten_grouped_kernel(View V, const int64_t *__restrict__ kptr, const int32_t *__restrict__ kids,
                        const float *__restrict__ kds, const int64_t *__restrict__ gptr,
                        const int32_t *__restrict__ gJ, const int32_t *__restrict__ gsrc,
-                       const int32_t *__restrict__ row_order, float *__restrict__ out_lb,
-                       float *__restrict__ out_ub, uint8_t *__restrict__ improved)
+                       const int32_t *__restrict__ row_order, const int32_t *__restrict__ heavy,
+                       const unsigned long long *__restrict__ sched /* [0] n_heavy, [1] next ticket */,
+                       const unsigned long long *__restrict__ work, unsigned long long heavy_thr,
+                       int has_tight, float *__restrict__ out_lb, float *__restrict__ out_ub,
+                       uint8_t *__restrict__ improved)
 {
     extern __shared__ __align__(16) unsigned char tg_smem[];
     int32_t *h_id = reinterpret_cast<int32_t *>(tg_smem);
     float *h_d = reinterpret_cast<float *>(h_id + TG_SLOTS);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    // rows are visited in closest-anchor order: CTAs running at the same time then work on points of
-    // the same neighbourhood, whose partner lists overlap -> the streamed lists hit in L2
-    for (int64_t ri = blockIdx.x; ri < V.n; ri += gridDim.x) {
-        const int64_t i = row_order[ri];
+    __shared__ long long s_ticket;
+    __shared__ int s_next;
+    const int lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const long long n_heavy = (long long)sched[0];
+    unsigned long long *ticket = const_cast<unsigned long long *>(sched) + 1;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_ticket = (long long)atomicAdd(ticket, 1ull);
+        __syncthreads();
+        const long long tk = s_ticket;
+        if (tk >= n_heavy + V.n) break;
+        int64_t i;
+        if (tk < n_heavy) {
+            i = heavy[tk];
+        } else {
+            // rows in closest-anchor order: CTAs running at the same time then work on points of the
+            // same neighbourhood, whose partner lists overlap -> the streamed lists hit in L2
+            i = row_order[tk - n_heavy];
+            if (work[i] >= heavy_thr) continue;  // already done from the heavy queue
+        }
         const int64_t g0 = gptr[i], g1 = gptr[i + 1];
         if (g0 == g1) continue;
         const int64_t bi = kptr[i];
         const int mi = (int)(kptr[i + 1] - bi);
-        // N(i) goes through the shared-memory hash table in chunks (one chunk for all but hub points)
+        // this row's anchor distances, one anchor per lane (coalesced 128 B row of Dpm)
+        float xa[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) xa[q] = (lane + 32 * q < V.na) ? __ldg(V.Dpm + i * V.dpitch + lane + 32 * q) : 0.0f;
+        // N(i) goes through the shared-memory table in chunks (one chunk for all but hub points)
         for (int c0 = 0; c0 == 0 || c0 < mi; c0 += TG_CHUNK) {
             const int mc = min(TG_CHUNK, mi - c0);
             const bool first = c0 == 0, last = c0 + TG_CHUNK >= mi;
-            int slots = 64;
-            while (slots < 2 * mc) slots <<= 1;
-            const uint32_t hmask = (uint32_t)slots - 1;
+            int nb = 16;  // buckets: load <= 0.25 where the table allows it
+            while (nb < mc && nb < TG_SLOTS / 4) nb <<= 1;
+            const uint32_t bmask = (uint32_t)nb - 1;
             __syncthreads();
-            for (int k = threadIdx.x; k < slots; k += blockDim.x) h_id[k] = -1;
+            for (int k = threadIdx.x; k < nb * 4; k += blockDim.x) h_id[k] = -1;
+            if (threadIdx.x == 0) s_next = 0;
             __syncthreads();
             for (int k = threadIdx.x; k < mc; k += blockDim.x) {
                 const int32_t id = kids[bi + c0 + k];
-                uint32_t h = ((uint32_t)id * 2654435761u) & hmask;
-                while (atomicCAS(&h_id[h], -1, id) != -1) h = (h + 1) & hmask;
-                h_d[h] = kds[bi + c0 + k];
+                uint32_t bk = ((uint32_t)id * 2654435761u >> 7) & bmask;
+                for (;;) {  // slots of a bucket fill in order 0..3
+                    int sl = 0;
+                    for (; sl < 4; ++sl)
+                        if (atomicCAS(&h_id[bk * 4 + sl], -1, id) == -1) break;
+                    if (sl < 4) {
+                        h_d[bk * 4 + sl] = kds[bi + c0 + k];
+                        break;
+                    }
+                    bk = (bk + 1) & bmask;
+                }
             }
             __syncthreads();
-            for (int64_t g = g0 + warp; g < g1; g += nwarps) {
+            for (;;) {
+                int gq = 0;
+                if (lane == 0) gq = atomicAdd(&s_next, 1);
+                gq = __shfl_sync(0xffffffffu, gq, 0);
+                const int64_t g = g0 + gq;
+                if (g >= g1) break;
                 const int j = gJ[g];
                 const int64_t bj = kptr[j];
                 const int mj = (int)(kptr[j + 1] - bj);
                 float lb = 0.0f, ub = INFINITY;
-                // 4 x 32 entries of j's list in flight per warp before the first probe
-                for (int k0 = 0; k0 < mj; k0 += 128) {
-                    int32_t idv[4];
-                    float yv[4];
+                int32_t idv[4], idn[4];
+                float yv[4], yn[4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int k = k0 + u * 32 + lane;
-                        idv[u] = k < mj ? __ldg(kids + bj + k) : -2;
-                        yv[u] = k < mj ? __ldg(kds + bj + k) : 0.0f;
+                for (int u = 0; u < 4; ++u) {
+                    const int k = u * 32 + lane;
+                    idv[u] = k < mj ? __ldg(kids + bj + k) : -2;
+                    yv[u] = k < mj ? __ldg(kds + bj + k) : 0.0f;
+                }
+                for (int k0 = 0; k0 < mj; k0 += 128) {
+                    if (k0 + 128 < mj) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int k = k0 + 128 + u * 32 + lane;
+                            idn[u] = k < mj ? __ldg(kids + bj + k) : -2;
+                            yn[u] = k < mj ? __ldg(kds + bj + k) : 0.0f;
+                        }
                     }
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        if (idv[u] < 0) continue;
-                        uint32_t h = ((uint32_t)idv[u] * 2654435761u) & hmask;
-                        for (;;) {
-                            const int32_t t = h_id[h];
-                            if (t == idv[u]) {
-                                const float x = h_d[h];
+                        const int32_t id = idv[u];
+                        uint32_t bk = ((uint32_t)id * 2654435761u >> 7) & bmask;
+                        bool more = id >= 0;
+                        while (more) {
+                            const int4 t = *reinterpret_cast<const int4 *>(h_id + bk * 4);
+                            const int sl = t.x == id ? 0 : (t.y == id ? 1 : (t.z == id ? 2 : (t.w == id ? 3 : -1)));
+                            if (sl >= 0) {
+                                const float x = h_d[bk * 4 + sl];
                                 lb = fmaxf(lb, fabsf(x - yv[u]));
                                 ub = fminf(ub, x + yv[u]);
-                                break;
+                                more = false;
+                            } else if (t.w == -1) {
+                                more = false;  // bucket never overflowed: the id is absent
+                            } else {
+                                bk = (bk + 1) & bmask;
                             }
-                            if (t == -1) break;
-                            h = (h + 1) & hmask;
                         }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        idv[u] = idn[u];
+                        yv[u] = yn[u];
                     }
                 }
 #pragma unroll
@@ -628,22 +734,26 @@ tighten_grouped_kernel(View V, const int64_t *__restrict__ kptr, const int32_t *
                 }
                 // anchor bounds + any earlier tightening of this pair: lanes over anchors
                 float l0 = 0.0f, u0 = INFINITY;
-                for (int a = lane; a < V.na; a += 32) {
-                    const float x = __ldg(V.Dpm + i * V.dpitch + a), y = __ldg(V.Dpm + (int64_t)j * V.dpitch + a);
-                    l0 = fmaxf(l0, fabsf(x - y));
-                    u0 = fminf(u0, x + y);
-                }
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+                    if (lane + 32 * q < V.na) {
+                        const float y = __ldg(V.Dpm + (int64_t)j * V.dpitch + lane + 32 * q);
+                        l0 = fmaxf(l0, fabsf(xa[q] - y));
+                        u0 = fminf(u0, xa[q] + y);
+                    }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
                     l0 = fmaxf(l0, __shfl_xor_sync(0xffffffffu, l0, o));
                     u0 = fminf(u0, __shfl_xor_sync(0xffffffffu, u0, o));
                 }
                 if (lane == 0) {
-                    float ta = 0.0f, tb = 0.0f;
-                    const uint32_t plo = (uint32_t)min((int64_t)j, i), phi = (uint32_t)max((int64_t)j, i);
-                    if (hash_lookup(V, pair_key(plo, phi), ta, tb) == KIND_TIGHT) {
-                        l0 = fmaxf(l0, ta);
-                        u0 = fminf(u0, tb);
+                    if (has_tight) {
+                        float ta = 0.0f, tb = 0.0f;
+                        const uint32_t plo = (uint32_t)min((int64_t)j, i), phi = (uint32_t)max((int64_t)j, i);
+                        if (hash_lookup(V, pair_key(plo, phi), ta, tb) == KIND_TIGHT) {
+                            l0 = fmaxf(l0, ta);
+                            u0 = fminf(u0, tb);
+                        }
                     }
                     out_lb[p] = fmaxf(lb, l0);
                     out_ub[p] = fminf(ub, u0);
@@ -765,25 +875,36 @@ using namespace annb;
 
 namespace annb {
 
-// mixed keys of the emitted entries at one level (ties at a selection cut)
-__global__ void compact_level_kernel(const uint64_t *__restrict__ keys, const uint16_t *__restrict__ lvl,
-                                     int64_t E, int level, uint64_t *__restrict__ out, int64_t out_cap,
-                                     unsigned long long *__restrict__ cnt)
+// mixed keys of the emitted entries at one level (ties at a selection cut); one global atomic per
+// 2048 entries
+__global__ void __launch_bounds__(256)
+compact_level_kernel(const uint64_t *__restrict__ keys, const uint16_t *__restrict__ lvl, int64_t E,
+                     uint64_t salt, int level, uint64_t *__restrict__ out, int64_t out_cap,
+                     unsigned long long *__restrict__ cnt)
 {
-    // warp-uniform trip count: every ballot / shuffle below is executed by all 32 lanes
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t b0 = warp * 32; b0 < E; b0 += nwarps * 32) {
-        const int64_t p = b0 + lane;
-        const bool hit = p < E && lvl[p] == level;
-        const unsigned m = __ballot_sync(0xffffffffu, hit);
-        if (!m) continue;
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(cnt, (unsigned long long)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        const unsigned long long pos = base + __popc(m & ((1u << lane) - 1));
-        if (hit && (int64_t)pos < out_cap) out[pos] = mix64(keys[p]);
+    __shared__ uint32_t s_warp[9];
+    __shared__ unsigned long long s_base;
+    const int64_t step = 256 * PE_ITEMS;
+    for (int64_t b0 = blockIdx.x * step; b0 < E; b0 += (int64_t)gridDim.x * step) {
+        bool hit[PE_ITEMS];
+        uint32_t mine = 0;
+#pragma unroll
+        for (int k = 0; k < PE_ITEMS; ++k) {
+            const int64_t p = b0 + k * 256 + threadIdx.x;
+            hit[k] = p < E && lvl[p] == level;
+            mine += hit[k] ? 1u : 0u;
+        }
+        uint32_t total;
+        const uint32_t ex = block_scan_packed(mine, s_warp, total);
+        if (threadIdx.x == 0) s_base = total ? atomicAdd(cnt, (unsigned long long)total) : 0ull;
+        __syncthreads();
+        unsigned long long pos = s_base + ex;
+#pragma unroll
+        for (int k = 0; k < PE_ITEMS; ++k)
+            if (hit[k]) {
+                if ((int64_t)pos < out_cap) out[pos] = mix64(keys[b0 + k * 256 + threadIdx.x] ^ salt);
+                ++pos;
+            }
     }
 }
 
@@ -846,13 +967,18 @@ struct annb_index {
     // selection
     DevBuf hist, counters, emit_key, emit_lvl, sel_i, sel_j, nxt_i, nxt_j, tiehist, tiekeys;
     int64_t n_sel = 0, n_next = 0;
+    // ties at a selection cut are broken by splitmix64(pair key ^ tie_salt); the salt changes with
+    // every selection so that the tie-break of one iteration is independent of the previous ones
+    // (the survivors of an earlier cut are exactly the pairs with LARGE mixed keys under its salt)
+    uint64_t tie_salt = 0;
+    int64_t n_selects = 0;
     // sampler pool
     DevBuf pool_key, pool_dad;
     int64_t n_pool = 0;
     // temporaries
     DevBuf t0, t1, t2, t3, t4, t5, t6;
     // CSR of known pairs
-    DevBuf kptr, kids, kds, kdeg, gptr, gJ, gsrc, row_order;
+    DevBuf kptr, kids, kds, kdeg, gptr, gJ, gsrc, row_order, twork, theavy;
     int64_t csr_entries = 0;
     // stats
     int64_t pairs_swept = 0, sweeps = 0, n_tight = 0, n_known = 0;
@@ -966,6 +1092,7 @@ static int finish_anchors(annb_index *ix)
 ANNB_API int annb_index_create(annb_ctx *c, const annb_dataset *ds, int metric,
                                const annb_index_params *P, annb_index **out)
 {
+    TraceScope _ts("annb_index_create");
     ANNB_REQUIRE(c && ds && P && out, ANNB_EINVAL, "NULL argument");
     ANNB_TRY(check_metric(ds, metric));
     ANNB_REQUIRE(P->n_anchors > 0 && P->n_anchors <= kMaxAnchors, ANNB_ERANGE,
@@ -1010,8 +1137,20 @@ ANNB_API int annb_index_create(annb_ctx *c, const annb_dataset *ds, int metric,
     return ANNB_OK;
 }
 
+// size the known-pair store once for the whole fit (p_work * N(N-1)/2 evaluations plus the
+// look-ahead pairs that may be tightened): growing it later means a rehash of GBs
+ANNB_API int annb_index_reserve_pairs(annb_index *ix, int64_t n_pairs)
+{
+    TraceScope _ts("annb_index_reserve_pairs");
+    ANNB_REQUIRE(ix != nullptr && n_pairs >= 0, ANNB_EINVAL, "bad argument");
+    ANNB_CUDA(cudaSetDevice(ix->ctx->device));
+    const int64_t extra = n_pairs - ix->hcount_ub;
+    return extra > 0 ? hash_reserve(ix, extra) : ANNB_OK;
+}
+
 ANNB_API int annb_index_destroy(annb_index *ix)
 {
+    TraceScope _ts("annb_index_destroy");
     if (!ix) return ANNB_OK;
     cudaSetDevice(ix->ctx->device);
     cudaStreamSynchronize(ix->ctx->stream);
@@ -1020,7 +1159,7 @@ ANNB_API int annb_index_destroy(annb_index *ix)
                      &ix->counters, &ix->emit_key, &ix->emit_lvl, &ix->sel_i, &ix->sel_j, &ix->nxt_i,
                      &ix->nxt_j, &ix->tiehist, &ix->tiekeys, &ix->pool_key, &ix->pool_dad, &ix->t0,
                      &ix->t1, &ix->t2, &ix->t3, &ix->t4, &ix->t5, &ix->t6, &ix->kptr, &ix->kids,
-                     &ix->kds, &ix->kdeg, &ix->gptr, &ix->gJ, &ix->gsrc, &ix->row_order};
+                     &ix->kds, &ix->kdeg, &ix->gptr, &ix->gJ, &ix->gsrc, &ix->row_order, &ix->twork, &ix->theavy};
     for (DevBuf *b : all) b->release();
     delete ix;
     return ANNB_OK;
@@ -1028,6 +1167,7 @@ ANNB_API int annb_index_destroy(annb_index *ix)
 
 ANNB_API int annb_index_maxmin(annb_index *ix, int64_t first, int64_t *A)
 {
+    TraceScope _ts("annb_index_maxmin");
     ANNB_REQUIRE(ix != nullptr, ANNB_EINVAL, "index is NULL");
     ANNB_REQUIRE(first >= 0 && first < ix->n, ANNB_EINVAL, "first anchor out of range");
     annb_ctx *c = ix->ctx;
@@ -1047,6 +1187,7 @@ ANNB_API int annb_index_maxmin(annb_index *ix, int64_t first, int64_t *A)
 
 ANNB_API int annb_index_set_anchors(annb_index *ix, const int64_t *A, int64_t nA, const double *D)
 {
+    TraceScope _ts("annb_index_set_anchors");
     ANNB_REQUIRE(ix && D, ANNB_EINVAL, "NULL argument");
     ANNB_REQUIRE(nA == 0 || nA == ix->na, ANNB_EINVAL, "A must be empty or have n_anchors entries");
     annb_ctx *c = ix->ctx;
@@ -1083,6 +1224,7 @@ ANNB_API int annb_index_get_D(annb_index *ix, double *D)
 
 ANNB_API int annb_index_locality(annb_index *ix, int64_t *n_candidates, int64_t *n_relaxed)
 {
+    TraceScope _ts("annb_index_locality");
     ANNB_REQUIRE(ix != nullptr, ANNB_EINVAL, "index is NULL");
     ANNB_REQUIRE(ix->have_anchors, ANNB_ESTATE, "anchors not computed yet");
     annb_ctx *c = ix->ctx;
@@ -1185,6 +1327,7 @@ static int upload_pairs(annb_index *ix, const int64_t *ij, const double *d, int6
 
 ANNB_API int annb_index_add_known(annb_index *ix, const int64_t *ij, const double *d, int64_t m)
 {
+    TraceScope _ts("annb_index_add_known");
     ANNB_REQUIRE(ix && (m == 0 || (ij && d)), ANNB_EINVAL, "NULL argument");
     if (m == 0) return ANNB_OK;
     ANNB_CUDA(cudaSetDevice(ix->ctx->device));
@@ -1197,6 +1340,7 @@ ANNB_API int annb_index_add_known(annb_index *ix, const int64_t *ij, const doubl
 
 ANNB_API int annb_index_eval_pairs(annb_index *ix, const int64_t *ij, int64_t m, double *d)
 {
+    TraceScope _ts("annb_index_eval_pairs");
     ANNB_REQUIRE(ix && (m == 0 || ij), ANNB_EINVAL, "NULL argument");
     if (m == 0) return ANNB_OK;
     annb_ctx *c = ix->ctx;
@@ -1219,6 +1363,7 @@ ANNB_API int annb_index_eval_pairs(annb_index *ix, const int64_t *ij, int64_t m,
 
 ANNB_API int annb_index_pair_features(annb_index *ix, const int64_t *ij, int64_t m, double *feat)
 {
+    TraceScope _ts("annb_index_pair_features");
     ANNB_REQUIRE(ix && (m == 0 || (ij && feat)), ANNB_EINVAL, "NULL argument");
     ANNB_REQUIRE(ix->have_anchors, ANNB_ESTATE, "anchors not computed yet");
     if (m == 0) return ANNB_OK;
@@ -1239,6 +1384,7 @@ ANNB_API int annb_index_set_model(annb_index *ix, const double *bins, const doub
                                   const double *icpt, int64_t nb, const double *errs,
                                   const int64_t *eptr)
 {
+    TraceScope _ts("annb_index_set_model");
     ANNB_REQUIRE(ix && bins && coef && icpt, ANNB_EINVAL, "NULL argument");
     ANNB_REQUIRE(nb >= 1 && nb <= MAX_BINS, ANNB_ERANGE, "n_partitions=%lld outside [1,%d]",
                  (long long)nb, MAX_BINS);
@@ -1248,6 +1394,7 @@ ANNB_API int annb_index_set_model(annb_index *ix, const double *bins, const doub
     memset(&M, 0, sizeof(M));
     M.nb = (int)nb;
     for (int b = 0; b <= nb; ++b) M.edge[b] = (float)bins[b];
+    for (int b = 0; b < MAX_BINS; ++b) M.e2[b] = (b >= 1 && b < nb) ? 2.0f * M.edge[b] : INFINITY;
     for (int b = 0; b < nb; ++b) {
         M.c0[b] = (float)coef[3 * b];
         M.c1[b] = (float)coef[3 * b + 1];
@@ -1343,6 +1490,7 @@ static int run_thresh(annb_index *ix, int k2)
 
 ANNB_API int annb_index_row_thresh(annb_index *ix, double *thresh)
 {
+    TraceScope _ts("annb_index_row_thresh");
     ANNB_REQUIRE(ix != nullptr, ANNB_EINVAL, "index is NULL");
     ANNB_REQUIRE(ix->have_anchors && ix->have_model, ANNB_ESTATE, "set anchors and model first");
     annb_ctx *c = ix->ctx;
@@ -1362,6 +1510,7 @@ ANNB_API int annb_index_row_thresh(annb_index *ix, double *thresh)
 // later rows see the -1 marks of earlier rows, then runs on the host over those short lists.
 ANNB_API int annb_index_guarantee_nmin(annb_index *ix, int64_t nmin, int64_t *n_forced)
 {
+    TraceScope _ts("annb_index_guarantee_nmin");
     ANNB_REQUIRE(ix != nullptr, ANNB_EINVAL, "index is NULL");
     ANNB_REQUIRE(ix->have_anchors && ix->have_model && ix->have_locality, ANNB_ESTATE,
                  "anchors, locality and model must be set first");
@@ -1463,8 +1612,8 @@ static void fill_efloor(const annb_index *ix, int floor_level, float *efloor, fl
     *ef_min = ix->P.is_metric ? mn : -INFINITY;  // d >= lower bound only holds for metrics
 }
 
-static int run_score(annb_index *ix, int floor_level, int stride, bool emit, int64_t emit_cap,
-                     std::vector<uint64_t> &hist, unsigned long long cnt[3])
+static int run_score(annb_index *ix, int floor_level, uint64_t floor_mix_thr, int stride, bool emit,
+                     int64_t emit_cap, std::vector<uint64_t> &hist, unsigned long long cnt[3])
 {
     annb_ctx *c = ix->ctx;
     ScoreArgs A;
@@ -1474,7 +1623,10 @@ static int run_score(annb_index *ix, int floor_level, int stride, bool emit, int
     A.errs = ix->errs_dev.as<float>();
     A.ranktab = ix->rank_dev.as<uint16_t>();
     A.nlevels = ix->nlevels;
+    A.n_errs = (int)ix->errs_host.size();
     A.floor_level = floor_level;
+    A.floor_mix_thr = floor_mix_thr;
+    A.tie_salt = ix->tie_salt;
     fill_efloor(ix, floor_level, A.efloor, &A.ef_min);
     A.has_forced = ix->has_forced ? 1 : 0;
     A.hist = ix->hist.as<uint32_t>();
@@ -1520,12 +1672,14 @@ static int run_score(annb_index *ix, int floor_level, int stride, bool emit, int
 
 // exact t-th smallest (1-based) mixed key among the emitted entries of one level
 static int tie_threshold(annb_index *ix, int64_t E, int level, int64_t level_count, int64_t t, uint64_t *thr)
+// level_count = number of EMITTED pairs at this level (all of them, or -- at the floor level -- those
+// whose mixed key passed the emission threshold, which are exactly the smallest ones)
 {
     annb_ctx *c = ix->ctx;
     ANNB_TRY(ix->tiekeys.ensure((size_t)(level_count + 32) * 8));
     ANNB_CUDA(cudaMemsetAsync(ix->counters.p, 0, 64, c->stream));
-    ANNB_LAUNCH(compact_level_kernel, grid_for_n(c, E), 256, 0, c->stream, ix->emit_key.as<uint64_t>(),
-                ix->emit_lvl.as<uint16_t>(), E, level, ix->tiekeys.as<uint64_t>(), level_count + 32,
+    ANNB_LAUNCH(compact_level_kernel, grid_for_n(c, E, 256 * PE_ITEMS), 256, 0, c->stream, ix->emit_key.as<uint64_t>(),
+                ix->emit_lvl.as<uint16_t>(), E, ix->tie_salt, level, ix->tiekeys.as<uint64_t>(), level_count + 32,
                 ix->counters.as<unsigned long long>());
     unsigned long long found = 0;
     ANNB_CUDA(cudaMemcpyAsync(&found, ix->counters.p, 8, cudaMemcpyDeviceToHost, c->stream));
@@ -1579,6 +1733,7 @@ static int level_cut(const std::vector<uint64_t> &h, int lo_level, int64_t targe
 ANNB_API int annb_index_select(annb_index *ix, int64_t n_refine, int64_t lookahead,
                                int64_t *n_selected, int64_t *n_next)
 {
+    TraceScope _ts("annb_index_select");
     ANNB_REQUIRE(ix != nullptr, ANNB_EINVAL, "index is NULL");
     ANNB_REQUIRE(ix->have_thresh && ix->nlevels > 0 && ix->have_locality, ANNB_ESTATE,
                  "locality, set_model (with error tables) and row_thresh must run before select");
@@ -1586,6 +1741,9 @@ ANNB_API int annb_index_select(annb_index *ix, int64_t n_refine, int64_t lookahe
     annb_ctx *c = ix->ctx;
     ANNB_CUDA(cudaSetDevice(c->device));
     ix->n_sel = ix->n_next = 0;
+    ix->n_selects += 1;
+    static const uint64_t salt0 = getenv("ANNB_TIE_SALT") ? strtoull(getenv("ANNB_TIE_SALT"), nullptr, 0) : 0ull;
+    ix->tie_salt = mix64(0x9E3779B97F4A7C15ull * (uint64_t)ix->n_selects + salt0);  // ANNB_TIE_SALT: test knob
     const int64_t nq = (ix->NT - ix->P.rank + ix->P.world - 1) / ix->P.world;
     const int64_t n_nc = ix->n_not_computed();  // exact: candidates - anchor pairs - known
     const int64_t want1 = n_refine, want2 = n_refine * lookahead;
@@ -1604,66 +1762,102 @@ ANNB_API int annb_index_select(annb_index *ix, int64_t n_refine, int64_t lookahe
     const bool small = tot_target >= n_nc || n_nc <= (int64_t)64000000;
     const int min_floor = small ? 0 : 1;
     int floor_level = min_floor;
+    // Probability levels are heavily tied (<= ~716 values per label), so the level that contains the
+    // cut can hold many times more pairs than are needed from it.  Ties at a cut are resolved by the
+    // smallest splitmix64(pair key); the sweep therefore emits, AT the floor level, only the pairs whose
+    // mixed key is below `floor_thr` -- a superset of the ones the cut can take.
+    uint64_t floor_thr = ~0ull;
     int64_t cap = 0;
+    // floor level + emission threshold + list capacity from (estimated) level counts h * scale
+    // (valid for levels >= lo_level only: an emitting pass does not count the levels below its floor)
+    auto plan = [&](const std::vector<uint64_t> &h, int lo_level, double scale, double slack) {
+        const double target = slack * (double)tot_target + (scale > 1.0 ? 65536.0 : 0.0);
+        double above = 0;
+        int L = ix->nlevels - 1;
+        for (; L > lo_level; --L) {
+            if (above + (double)h[L] * scale >= target) break;
+            above += (double)h[L] * scale;
+        }
+        const double at = (double)h[L] * scale;
+        double need = target - above;
+        if (need < 0) need = 0;
+        double want = need + 6.0 * sqrt(need) + 64.0;  // binomial slack of the hash threshold
+        if (scale > 1.0) want = want * 1.1 + 4096.0;   // + pilot sampling error
+        floor_level = L;
+        if (want >= 0.999 * at) {
+            floor_thr = ~0ull;
+            want = at;
+        } else {
+            floor_thr = (uint64_t)((want / at) * 18446744073709551615.0);
+        }
+        cap = (int64_t)((above + want) * (scale > 1.0 ? 1.15 : 1.0)) + (int64_t)(8.0 * sqrt(above + want)) + 65536;
+        if (cap > n_nc + 1024) cap = n_nc + 1024;
+    };
     if (tot_target >= n_nc) {
         cap = n_nc + 1024;  // everything is taken: no pilot needed
     } else {
         // pass 1: level histogram -- exact for small problems, a pilot over every s-th tile otherwise
         const int stride = nq > 8192 ? (int)(nq / 2048) : 1;
-        ANNB_TRY(run_score(ix, min_floor, stride, false, 0, h1, c1v));
-        if (stride == 1) {
-            int64_t cum = 0;
-            floor_level = level_cut(h1, min_floor, tot_target, &cum);
-            cap = cum + 1024;
-        } else {
-            const double scale = (double)nq / (double)((nq + stride - 1) / stride);
-            const double target = 1.5 * (double)tot_target + 65536.0;
-            double cum = 0;
-            int L = ix->nlevels - 1;
-            for (; L > min_floor; --L) {
-                cum += (double)h1[L] * scale;
-                if (cum >= target) break;
-            }
-            if (L == min_floor) cum += (double)h1[min_floor] * scale;
-            floor_level = L;
-            cap = (int64_t)(cum * 1.5) + (1 << 20);
-            if (cap > n_nc + 1024) cap = n_nc + 1024;
-        }
+        ANNB_TRY(run_score(ix, min_floor, ~0ull, stride, false, 0, h1, c1v));
+        if (stride == 1) plan(h1, min_floor, 1.0, 1.0);
+        else plan(h1, min_floor, (double)nq / (double)((nq + stride - 1) / stride), 1.25);
     }
     // pass 2: exact histogram of the levels >= floor, with emission; re-plan if the pilot was off
-    int64_t E = 0;
+    int64_t E = 0, E_all = 0, at_floor_emitted = 0;
     for (int attempt = 0;; ++attempt) {
-        ANNB_REQUIRE(attempt < 4, ANNB_ESTATE, "selection did not converge");
+        ANNB_REQUIRE(attempt < 5, ANNB_ESTATE, "selection did not converge");
         // `cap` counts pairs over all ranks; a rank's own list gets its share plus slack
         const int64_t cap_local = ix->P.world > 1 ? cap / ix->P.world + cap / (4 * ix->P.world) + (1 << 16) : cap;
-        ANNB_TRY(run_score(ix, floor_level, 1, true, cap_local, h2, c2v));
+        ANNB_TRY(run_score(ix, floor_level, floor_thr, 1, true, cap_local, h2, c2v));
         E = (int64_t)c2v[0];
+        uint64_t red[2] = {E > cap_local ? 1ull : 0ull, (uint64_t)E};
+        ANNB_TRY(ix->reduce(red, 2, ANNB_RED_U64));  // every rank must take the same branch
+        E_all = (int64_t)red[1];
         int64_t cum = 0;
         for (int L = floor_level; L < ix->nlevels; ++L) cum += h2[L];
-        uint64_t overflow = E > cap_local ? 1 : 0;
-        ANNB_TRY(ix->reduce(&overflow, 1, ANNB_RED_U64));  // every rank must take the same branch
-        if (overflow) {
-            // more pairs above the floor than planned: the histogram above it is exact, re-cut exactly
-            int64_t cum2 = 0;
-            floor_level = level_cut(h2, floor_level, tot_target, &cum2);
-            cap = cum2 + 1024;
+        const int64_t above = cum - (int64_t)h2[floor_level];
+        if (red[0]) {
+            if (g_trace) fprintf(stderr, "[annb-trace]   select attempt %d: overflow E %lld cap %lld floor %d\n", attempt,
+                                 (long long)E_all, (long long)cap, floor_level);
+            // more pairs emitted than planned: the histogram above the floor is exact, re-plan exactly
+            plan(h2, floor_level, 1.0, 1.0);
             continue;
         }
+        at_floor_emitted = E_all - above;
+        if (g_trace)
+            fprintf(stderr, "[annb-trace]   select attempt %d: floor %d thr %.6f cap %lld E %lld cum %lld above %lld "
+                            "at_floor %llu emitted_at_floor %lld targets %lld/%lld n_nc %lld overflow %d\n",
+                    attempt, floor_level, (double)floor_thr / 18446744073709551615.0, (long long)cap, (long long)E_all,
+                    (long long)cum, (long long)above, (unsigned long long)h2[floor_level], (long long)at_floor_emitted,
+                    (long long)sel_target, (long long)tot_target, (long long)n_nc, (int)red[0]);
         if (floor_level > min_floor && cum < tot_target) {
             // floor too high: exact full histogram, exact floor
-            ANNB_TRY(run_score(ix, min_floor, 1, false, 0, h1, c1v));
-            int64_t cum2 = 0;
-            floor_level = level_cut(h1, min_floor, tot_target, &cum2);
-            cap = cum2 + 1024;
+            ANNB_TRY(run_score(ix, min_floor, ~0ull, 1, false, 0, h1, c1v));
+            plan(h1, min_floor, 1.0, 1.0);
             continue;
         }
         if (cum < tot_target) {  // large problem, not enough positive-probability pairs
             tot_target = cum;
             sel_target = std::min<int64_t>(sel_target, cum);
         }
+        if (above < tot_target && tot_target - above > at_floor_emitted) {
+            // the hash threshold at the floor level let too few pairs through: scale it by the
+            // observed pass rate (+10 %), everything at the floor level on the last attempts
+            const double need = (double)(tot_target - above);
+            const double frac = (double)floor_thr / 18446744073709551615.0;
+            const double nf = frac * need / (double)std::max<int64_t>(at_floor_emitted, 1) * 1.1 + 256.0 / (double)std::max<uint64_t>(h2[floor_level], 1);
+            if (nf >= 0.999 || attempt >= 2) floor_thr = ~0ull;
+            else floor_thr = (uint64_t)(nf * 18446744073709551615.0);
+            const double pass = floor_thr == ~0ull ? (double)h2[floor_level] : nf * (double)h2[floor_level];
+            cap = std::min<int64_t>((int64_t)((double)above + pass * 1.05) + 65536, n_nc + 1024);
+            continue;
+        }
         break;
     }
     // ---- cut the emitted list: level first, mixed pair key among ties (deterministic) ----
+    // he[L] = emitted pairs at level L
+    std::vector<uint64_t> he(h2);
+    he[floor_level] = (uint64_t)std::max<int64_t>(at_floor_emitted, 0);
     int cl1 = ix->nlevels, cl2 = ix->nlevels;
     int64_t t1 = 0, t2 = 0;
     {
@@ -1684,8 +1878,8 @@ ANNB_API int annb_index_select(annb_index *ix, int64_t n_refine, int64_t lookahe
                      (long long)tot_target, (long long)n_nc);
     }
     uint64_t thr1 = ~0ull, thr2 = ~0ull;
-    if (cl1 < ix->nlevels && t1 < (int64_t)h2[cl1]) ANNB_TRY(tie_threshold(ix, E, cl1, h2[cl1], t1, &thr1));
-    if (cl2 < ix->nlevels && t2 < (int64_t)h2[cl2]) ANNB_TRY(tie_threshold(ix, E, cl2, h2[cl2], t2, &thr2));
+    if (cl1 < ix->nlevels && t1 < (int64_t)he[cl1]) ANNB_TRY(tie_threshold(ix, E, cl1, he[cl1], t1, &thr1));
+    if (cl2 < ix->nlevels && t2 < (int64_t)he[cl2]) ANNB_TRY(tie_threshold(ix, E, cl2, he[cl2], t2, &thr2));
     const int64_t cap_sel = std::min<int64_t>(sel_target, E) + 16;
     const int64_t cap_next = std::min<int64_t>(tot_target - sel_target, E) + 16;
     ANNB_TRY(ix->sel_i.ensure((size_t)cap_sel * 4));
@@ -1694,8 +1888,8 @@ ANNB_API int annb_index_select(annb_index *ix, int64_t n_refine, int64_t lookahe
     ANNB_TRY(ix->nxt_j.ensure((size_t)cap_next * 4));
     ANNB_CUDA(cudaMemsetAsync(ix->counters.p, 0, 64, c->stream));
     if (E > 0)
-        ANNB_LAUNCH(partition_emitted_kernel, grid_for_n(c, E), 256, 0, c->stream,
-                    ix->emit_key.as<uint64_t>(), ix->emit_lvl.as<uint16_t>(), E, cl1, thr1, cl2, thr2,
+        ANNB_LAUNCH(partition_emitted_kernel, grid_for_n(c, E, 256 * PE_ITEMS), 256, 0, c->stream,
+                    ix->emit_key.as<uint64_t>(), ix->emit_lvl.as<uint16_t>(), E, ix->tie_salt, cl1, thr1, cl2, thr2,
                     ix->sel_i.as<int32_t>(), ix->sel_j.as<int32_t>(), ix->nxt_i.as<int32_t>(),
                     ix->nxt_j.as<int32_t>(), ix->counters.as<unsigned long long>(), cap_sel, cap_next);
     unsigned long long pc[2] = {0, 0};
@@ -1716,6 +1910,7 @@ ANNB_API int annb_index_select(annb_index *ix, int64_t n_refine, int64_t lookahe
 
 ANNB_API int annb_index_get_selected(annb_index *ix, int64_t *ij_sel, int64_t *ij_next)
 {
+    TraceScope _ts("annb_index_get_selected");
     ANNB_REQUIRE(ix != nullptr, ANNB_EINVAL, "index is NULL");
     annb_ctx *c = ix->ctx;
     ANNB_CUDA(cudaSetDevice(c->device));
@@ -1738,6 +1933,7 @@ ANNB_API int annb_index_get_selected(annb_index *ix, int64_t *ij_sel, int64_t *i
 
 ANNB_API int annb_index_refine_selected(annb_index *ix, int64_t *n_evals)
 {
+    TraceScope _ts("annb_index_refine_selected");
     ANNB_REQUIRE(ix != nullptr, ANNB_EINVAL, "index is NULL");
     annb_ctx *c = ix->ctx;
     ANNB_CUDA(cudaSetDevice(c->device));
@@ -1783,14 +1979,13 @@ static int build_known_csr(annb_index *ix)
     ANNB_LAUNCH(known_fill_kernel, grid_for_n(c, (int64_t)ix->hcap), 256, 0, c->stream,
                 ix->htab.as<HashSlot>(), ix->hcap, ix->kptr.as<int64_t>(), ix->kdeg.as<int32_t>(),
                 ix->kids.as<int32_t>(), ix->kds.as<float>());
-    const int grid = (int)std::min<int64_t>(n, (int64_t)c->num_sms * 8);
-    ANNB_LAUNCH(sort_rows_kernel, grid, 256, 0, c->stream, ix->kptr.as<int64_t>(), n,
-                ix->kids.as<int32_t>(), ix->kds.as<float>());
+    // rows stay unsorted: the tightening kernel hashes / streams them and the top-k is order-free
     return ANNB_OK;
 }
 
 ANNB_API int annb_index_update_bounds(annb_index *ix, int64_t *n_updated)
 {
+    TraceScope _ts("annb_index_update_bounds");
     ANNB_REQUIRE(ix != nullptr, ANNB_EINVAL, "index is NULL");
     annb_ctx *c = ix->ctx;
     ANNB_CUDA(cudaSetDevice(c->device));
@@ -1880,12 +2075,29 @@ ANNB_API int annb_index_update_bounds(annb_index *ix, int64_t *n_updated)
         ANNB_LAUNCH(cA_scatter_kernel, grid_for_n(c, n), 256, 0, c->stream, ix->meta.as<PointMeta>(), n,
                     ix->counters.as<int32_t>(), ix->row_order.as<int32_t>());
     }
+    // per-row streaming work -> heavy rows first, then closest-anchor order, fetched dynamically
+    ANNB_TRY(ix->twork.ensure((size_t)n * 8));
+    ANNB_TRY(ix->theavy.ensure((size_t)n * 4));
+    ANNB_CUDA(cudaMemsetAsync(ix->counters.p, 0, 64, c->stream));
+    ANNB_LAUNCH(tighten_work_kernel, grid_for_n(c, n), 256, 0, c->stream, ix->kptr.as<int64_t>(),
+                ix->gptr.as<int64_t>(), ix->gJ.as<int32_t>(), n, ix->counters.as<unsigned long long>(),
+                ix->twork.as<unsigned long long>());
+    unsigned long long wsum[3] = {0, 0, 0};
+    ANNB_CUDA(cudaMemcpyAsync(wsum, ix->counters.p, 24, cudaMemcpyDeviceToHost, c->stream));
+    ANNB_CUDA(cudaStreamSynchronize(c->stream));
+    const int tg_grid = c->num_sms * 3;
+    // a row is "heavy" when it is more than 1/16 of a CTA's fair share of the streamed entries
+    const unsigned long long heavy_thr = std::max<unsigned long long>(wsum[0] / ((unsigned long long)tg_grid * 16), 1);
+    ANNB_CUDA(cudaMemsetAsync(ix->counters.p, 0, 64, c->stream));
+    ANNB_LAUNCH(tighten_heavy_kernel, grid_for_n(c, n), 256, 0, c->stream, ix->twork.as<unsigned long long>(), n,
+                heavy_thr, ix->theavy.as<int32_t>(), ix->counters.as<unsigned long long>() + 4);
     ANNB_CUDA(cudaFuncSetAttribute(tighten_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    TG_SLOTS * 8));
-    ANNB_LAUNCH(tighten_grouped_kernel, c->num_sms * 3, 256, TG_SLOTS * 8, c->stream, V, ix->kptr.as<int64_t>(),
+    ANNB_LAUNCH(tighten_grouped_kernel, tg_grid, 256, TG_SLOTS * 8, c->stream, V, ix->kptr.as<int64_t>(),
                 ix->kids.as<int32_t>(), ix->kds.as<float>(), ix->gptr.as<int64_t>(), ix->gJ.as<int32_t>(),
-                ix->gsrc.as<int32_t>(), ix->row_order.as<int32_t>(), ix->t0.as<float>(),
-                ix->t1.as<float>(), ix->t2.as<uint8_t>());
+                ix->gsrc.as<int32_t>(), ix->row_order.as<int32_t>(), ix->theavy.as<int32_t>(),
+                ix->counters.as<unsigned long long>() + 4, ix->twork.as<unsigned long long>(), heavy_thr,
+                ix->n_tight > 0 ? 1 : 0, ix->t0.as<float>(), ix->t1.as<float>(), ix->t2.as<uint8_t>());
     ANNB_CUDA(cudaMemsetAsync(ix->counters.p, 0, 64, c->stream));
     ANNB_LAUNCH(compact_improved_kernel, grid_for_n(c, m), 256, 0, c->stream, ix->nxt_i.as<int32_t>(),
                 ix->nxt_j.as<int32_t>(), ix->t0.as<float>(), ix->t1.as<float>(), ix->t2.as<uint8_t>(), m,
@@ -1905,6 +2117,7 @@ ANNB_API int annb_index_update_bounds(annb_index *ix, int64_t *n_updated)
 
 ANNB_API int annb_index_neighbor_graph(annb_index *ix, int64_t *idx, double *dist)
 {
+    TraceScope _ts("annb_index_neighbor_graph");
     ANNB_REQUIRE(ix && idx && dist, ANNB_EINVAL, "NULL argument");
     ANNB_REQUIRE(ix->have_anchors, ANNB_ESTATE, "anchors not computed yet");
     annb_ctx *c = ix->ctx;
@@ -1928,6 +2141,7 @@ ANNB_API int annb_index_neighbor_graph(annb_index *ix, int64_t *idx, double *dis
 
 ANNB_API int annb_index_stats(annb_index *ix, int64_t *out, int64_t m)
 {
+    TraceScope _ts("annb_index_stats");
     ANNB_REQUIRE(ix && out, ANNB_EINVAL, "NULL argument");
     const int64_t v[8] = {ix->pairs_swept, ix->n_known,        ix->n_tight,        ix->sweeps,
                           ix->n_candidates, (int64_t)ix->hcap, ix->n_anchor_pairs, ix->n_not_computed()};
@@ -1937,6 +2151,7 @@ ANNB_API int annb_index_stats(annb_index *ix, int64_t *out, int64_t m)
 
 ANNB_API int annb_index_last_sweep(annb_index *ix, float *ms, int64_t *pairs)
 {
+    TraceScope _ts("annb_index_last_sweep");
     ANNB_REQUIRE(ix != nullptr, ANNB_EINVAL, "index is NULL");
     if (ms) *ms = ix->last_sweep_ms;
     if (pairs) *pairs = ix->last_sweep_pairs;
@@ -1952,6 +2167,7 @@ ANNB_API int annb_index_last_sweep(annb_index *ix, float *ms, int64_t *pairs)
 ANNB_API int annb_index_sample_pool(annb_index *ix, uint64_t seed, int64_t max_pool, int64_t *n_pool,
                                     int64_t *n_not_computed, int *exact)
 {
+    TraceScope _ts("annb_index_sample_pool");
     ANNB_REQUIRE(ix && n_pool, ANNB_EINVAL, "NULL argument");
     ANNB_REQUIRE(ix->have_locality, ANNB_ESTATE, "locality must run before sampling");
     ANNB_REQUIRE(max_pool >= 1024, ANNB_EINVAL, "max_pool too small");
@@ -2004,6 +2220,7 @@ ANNB_API int annb_index_sample_pool(annb_index *ix, uint64_t seed, int64_t max_p
 
 ANNB_API int annb_index_get_pool(annb_index *ix, int64_t *ij, double *dad)
 {
+    TraceScope _ts("annb_index_get_pool");
     ANNB_REQUIRE(ix && ij && dad, ANNB_EINVAL, "NULL argument");
     annb_ctx *c = ix->ctx;
     ANNB_CUDA(cudaSetDevice(c->device));
@@ -2027,6 +2244,7 @@ ANNB_API int annb_index_get_pool(annb_index *ix, int64_t *ij, double *dad)
 // ---------------------------------------------------------------------------------------------
 ANNB_API int annb_index_set_reducer(annb_index *ix, annb_reduce_fn fn, void *user)
 {
+    TraceScope _ts("annb_index_set_reducer");
     ANNB_REQUIRE(ix != nullptr, ANNB_EINVAL, "index is NULL");
     ix->reducer = fn;
     ix->reducer_user = user;
@@ -2036,6 +2254,7 @@ ANNB_API int annb_index_set_reducer(annb_index *ix, annb_reduce_fn fn, void *use
 ANNB_API int annb_index_export_refined(annb_index *ix, int32_t *i_dev, int32_t *j_dev, float *d_dev,
                                        int64_t cap, int64_t *n)
 {
+    TraceScope _ts("annb_index_export_refined");
     ANNB_REQUIRE(ix && n, ANNB_EINVAL, "NULL argument");
     annb_ctx *c = ix->ctx;
     ANNB_CUDA(cudaSetDevice(c->device));
@@ -2053,6 +2272,7 @@ ANNB_API int annb_index_export_refined(annb_index *ix, int32_t *i_dev, int32_t *
 ANNB_API int annb_index_export_tightened(annb_index *ix, int32_t *i_dev, int32_t *j_dev, float *lb_dev,
                                          float *ub_dev, int64_t cap, int64_t *n)
 {
+    TraceScope _ts("annb_index_export_tightened");
     ANNB_REQUIRE(ix && n, ANNB_EINVAL, "NULL argument");
     annb_ctx *c = ix->ctx;
     ANNB_CUDA(cudaSetDevice(c->device));
@@ -2072,6 +2292,7 @@ ANNB_API int annb_index_export_tightened(annb_index *ix, int32_t *i_dev, int32_t
 ANNB_API int annb_index_import_dev(annb_index *ix, int kind, const int32_t *i_dev, const int32_t *j_dev,
                                    const float *a_dev, const float *b_dev, int64_t n)
 {
+    TraceScope _ts("annb_index_import_dev");
     ANNB_REQUIRE(ix != nullptr, ANNB_EINVAL, "index is NULL");
     ANNB_REQUIRE(kind == (int)KIND_KNOWN || kind == (int)KIND_TIGHT, ANNB_EINVAL, "kind must be 1 or 2");
     if (n == 0) return ANNB_OK;

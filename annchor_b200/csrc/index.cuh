@@ -50,6 +50,8 @@ struct __align__(16) PointMeta {
 struct Model {
     int nb;
     float edge[MAX_BINS + 1];  // edge[0] = -inf, edge[nb] = +inf (annchor/samplers.py:138-139)
+    float e2[MAX_BINS];        // 2 * edge[k] for the interior edges k = 1..nb-1, +inf otherwise (sweeps
+                               // compare against 2 * dad)
     float c0[MAX_BINS], c1[MAX_BINS], c2[MAX_BINS], ic[MAX_BINS];  // regressors.py:39-67
     int eoff[MAX_BINS + 1];    // offsets of the per-label sorted error tables (error_predictors.py:47-54)
 };

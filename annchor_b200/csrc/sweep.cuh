@@ -23,12 +23,28 @@
 
 namespace annb {
 
-constexpr int QCAP = 256;  // survivors per warp per step: 8 pairs x 32 lanes (one micro-tile row)
+constexpr int QCAP = 512;   // per-warp survivor queue; drained when a row step (<= 256 new) might overflow it
+constexpr int QROW = 256;   // survivors one micro-tile row step can add: 8 pairs x 32 lanes
 
-struct __align__(4) Survivor {
+struct __align__(16) Survivor {
     float lb, ub;
     uint32_t ids;  // li | lj << 8
+    uint32_t pad;
 };
+
+// 3-input min / max (FMNMX3 on sm_100a: two anchors per min/max instruction)
+__device__ __forceinline__ float fmax3abs(float a, float b, float c)
+{
+    float d;
+    asm("max.abs.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+__device__ __forceinline__ float fmin3(float a, float b, float c)
+{
+    float d;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
 {
@@ -61,28 +77,51 @@ __device__ __forceinline__ int micro_off(int t4, int k)  // local index of the k
     return (k < 4) ? (t4 * 4 + k) : (64 + t4 * 4 + (k - 4));
 }
 
-// triangle-inequality bounds for the 8 x 8 micro-tile (get_bounds_njit_ijs, utils.py:274-301)
-__device__ __forceinline__ void bounds_microtile(const float *__restrict__ sDi,
-                                                 const float *__restrict__ sDj, int na, int ty,
-                                                 int tx, float (&lb)[8][8], float (&ub)[8][8])
+// triangle-inequality bounds (get_bounds_njit_ijs, utils.py:274-301) for HALF of the 8 x 8
+// micro-tile: 4 rows (local rows row0..row0+3) x 8 columns.  The tile is processed in two such
+// passes so that the 64 accumulators, the 24 staged anchor distances and the kernel state fit the
+// register file without spills.  Two anchors per step: 4 FADD + 2 FMNMX3 per pair (max / min are
+// exact and order-free, so the result equals the reference's sequential loop in float32).
+__device__ __forceinline__ void bounds_half(const float *__restrict__ sDi, const float *__restrict__ sDj,
+                                            int na, int row0, int tx, float (&lb)[4][8], float (&ub)[4][8])
 {
 #pragma unroll
-    for (int r = 0; r < 8; ++r)
+    for (int r = 0; r < 4; ++r)
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
             lb[r][c] = 0.0f;
             ub[r][c] = INFINITY;
         }
-#pragma unroll 2
-    for (int a = 0; a < na; ++a) {
-        const float4 i0 = *reinterpret_cast<const float4 *>(sDi + a * SROW + ty * 4);
-        const float4 i1 = *reinterpret_cast<const float4 *>(sDi + a * SROW + 64 + ty * 4);
+    int a = 0;
+#pragma unroll 1
+    for (; a + 2 <= na; a += 2) {
+        const float *pi = sDi + a * SROW + row0, *pj = sDj + a * SROW + tx * 4;
+        const float4 i0 = *reinterpret_cast<const float4 *>(pi);
+        const float4 k0 = *reinterpret_cast<const float4 *>(pi + SROW);
+        const float4 j0 = *reinterpret_cast<const float4 *>(pj);
+        const float4 j1 = *reinterpret_cast<const float4 *>(pj + 64);
+        const float4 l0 = *reinterpret_cast<const float4 *>(pj + SROW);
+        const float4 l1 = *reinterpret_cast<const float4 *>(pj + SROW + 64);
+        const float di[4] = {i0.x, i0.y, i0.z, i0.w};
+        const float ei[4] = {k0.x, k0.y, k0.z, k0.w};
+        const float dj[8] = {j0.x, j0.y, j0.z, j0.w, j1.x, j1.y, j1.z, j1.w};
+        const float ej[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                lb[r][c] = fmax3abs(lb[r][c], di[r] - dj[c], ei[r] - ej[c]);
+                ub[r][c] = fmin3(ub[r][c], di[r] + dj[c], ei[r] + ej[c]);
+            }
+    }
+    if (a < na) {
+        const float4 i0 = *reinterpret_cast<const float4 *>(sDi + a * SROW + row0);
         const float4 j0 = *reinterpret_cast<const float4 *>(sDj + a * SROW + tx * 4);
         const float4 j1 = *reinterpret_cast<const float4 *>(sDj + a * SROW + 64 + tx * 4);
-        const float di[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+        const float di[4] = {i0.x, i0.y, i0.z, i0.w};
         const float dj[8] = {j0.x, j0.y, j0.z, j0.w, j1.x, j1.y, j1.z, j1.w};
 #pragma unroll
-        for (int r = 0; r < 8; ++r)
+        for (int r = 0; r < 4; ++r)
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 lb[r][c] = fmaxf(lb[r][c], fabsf(di[r] - dj[c]));
@@ -91,10 +130,29 @@ __device__ __forceinline__ void bounds_microtile(const float *__restrict__ sDi,
     }
 }
 
-// shared-memory copy of the regression model in the form phase 1 consumes
+// pairs of the half micro-tile that must not take part (diagonal tiles: li >= lj for the
+// upper-triangle sweeps, li == lj for the row sweeps) get lb = ub = +inf: their clipped prediction is
+// +inf (or NaN -> compares false), so phase 1 drops them without a per-pair test
+template <bool STRICT_UPPER>
+__device__ __forceinline__ void mask_diagonal(int row0, int tx, float (&lb)[4][8], float (&ub)[4][8])
+{
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const int li = row0 + r;
+            const int lj = (c < 4) ? (tx * 4 + c) : (64 + tx * 4 + (c - 4));
+            if (STRICT_UPPER ? (li >= lj) : (li == lj)) {
+                lb[r][c] = INFINITY;
+                ub[r][c] = INFINITY;
+            }
+        }
+}
+
+// shared-memory copy of the regression model in the form phase 1 consumes.  The (doubled) bin
+// edges are read straight from the kernel parameters (constant bank operands: no load, no register).
 struct __align__(16) TileModel {
     float4 cf[MAX_BINS];   // (c0, c1, c2 / 2, intercept) per bin (regressors.py:39-67)
-    float e2[MAX_BINS];    // 2 * interior edge k (k = 1..nb-1), +inf beyond: compared against 2 * dad
     float mg[MAX_BINS];    // scoring only: conservative per-bin margin min(efloor[b], efloor[b+1])
 };
 
@@ -104,35 +162,35 @@ __device__ __forceinline__ void build_tile_model(const Model &M, TileModel *tm)
     if (t < MAX_BINS) {
         const bool live = t < M.nb;
         tm->cf[t] = live ? make_float4(M.c0[t], M.c1[t], 0.5f * M.c2[t], M.ic[t]) : make_float4(0, 0, 0, 0);
-        tm->e2[t] = (t >= 1 && t < M.nb) ? 2.0f * M.edge[t] : INFINITY;
         tm->mg[t] = 0.0f;
     }
 }
 
 // s = 2 * dad.  Regression bin (lo, hi]: number of interior edges strictly below dad
-// (regressors.py:85-87), found with a 3-level compare tree over the 7 (padded) edges.
-__device__ __forceinline__ int reg_bin2(const TileModel *tm, float s)
+// (regressors.py:85-87), found with a 3-level compare tree over the 7 (padded) doubled edges M.e2.
+__device__ __forceinline__ int reg_bin2(const Model &M, float s)
 {
-    const bool p4 = s > tm->e2[4];
-    const bool p2 = s > (p4 ? tm->e2[6] : tm->e2[2]);
-    const float lo = p2 ? tm->e2[3] : tm->e2[1], hi = p2 ? tm->e2[7] : tm->e2[5];
+    const bool p4 = s > M.e2[4];
+    const bool p2 = s > (p4 ? M.e2[6] : M.e2[2]);
+    const float lo = p2 ? M.e2[3] : M.e2[1], hi = p2 ? M.e2[7] : M.e2[5];
     const bool p1 = s > (p4 ? hi : lo);
     return (p4 ? 4 : 0) + (p2 ? 2 : 0) + (p1 ? 1 : 0);
 }
 // error label / sampler bin: closed [lo, hi] with later bins winning (error_predictors.py:63-66):
 // number of interior edges <= dad
-__device__ __forceinline__ int err_label2(const TileModel *tm, float s)
+__device__ __forceinline__ int err_label2(const Model &M, float s)
 {
-    const bool p4 = s >= tm->e2[4];
-    const bool p2 = s >= (p4 ? tm->e2[6] : tm->e2[2]);
-    const float lo = p2 ? tm->e2[3] : tm->e2[1], hi = p2 ? tm->e2[7] : tm->e2[5];
+    const bool p4 = s >= M.e2[4];
+    const bool p2 = s >= (p4 ? M.e2[6] : M.e2[2]);
+    const float lo = p2 ? M.e2[3] : M.e2[1], hi = p2 ? M.e2[7] : M.e2[5];
     const bool p1 = s >= (p4 ? hi : lo);
     return (p4 ? 4 : 0) + (p2 ? 2 : 0) + (p1 ? 1 : 0);
 }
 // clip(lb*c0 + ub*c1 + dad*c2 + icpt, lb, ub)  (annchor.py:356-363); identical code in both phases
-__device__ __forceinline__ float predict_clip2(const TileModel *tm, float lb, float ub, float s, int &bin)
+__device__ __forceinline__ float predict_clip2(const TileModel *tm, const Model &M, float lb, float ub,
+                                               float s, int &bin)
 {
-    bin = reg_bin2(tm, s);
+    bin = reg_bin2(M, s);
     const float4 cf = tm->cf[bin];
     const float y = fmaf(lb, cf.x, fmaf(ub, cf.y, fmaf(s, cf.z, cf.w)));
     return fminf(fmaxf(y, lb), ub);
@@ -161,27 +219,23 @@ __device__ __forceinline__ void transpose_bitmap(const uint32_t *src, uint32_t *
     }
 }
 
-// ballot-compact one micro-tile row's survivors into the warp queue; returns the new queue length
-__device__ __forceinline__ int stage_row(Survivor *q, int qn, const float (&lb)[8], const float (&ub)[8],
-                                         const bool (&keep)[8], int li, int tx, int lane)
+// append one micro-tile row's survivors (bit c of km = column c survives) to the warp queue: one
+// shared-memory atomic per thread that has any, then predicated 128-bit stores
+__device__ __forceinline__ void stage_row(Survivor *q, int *qcnt, const float (&lb)[8], const float (&ub)[8],
+                                          uint32_t km, int li, int tx)
 {
-    bool any = false;
+    if (km == 0) return;
+    int pos = atomicAdd(qcnt, __popc(km));
 #pragma unroll
-    for (int c = 0; c < 8; ++c) any |= keep[c];
-    if (!__any_sync(0xffffffffu, any)) return qn;  // common case: nothing in this row step survives
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const unsigned m = __ballot_sync(0xffffffffu, keep[c]);
-        if (keep[c]) {
+    for (int c = 0; c < 8; ++c)
+        if ((km >> c) & 1u) {
             Survivor s;
             s.lb = lb[c];
             s.ub = ub[c];
             s.ids = (uint32_t)li | ((uint32_t)micro_off(tx, c) << 8);
-            q[qn + __popc(m & ((1u << lane) - 1))] = s;
+            s.pad = 0;
+            q[pos++] = s;
         }
-        qn += __popc(m);
-    }
-    return qn;
 }
 
 // candidate test (get_check / adjust_check, utils.py:437-491): shared nearest-anchor count
@@ -207,7 +261,7 @@ struct PairVal {
 };
 
 // RefineApprox of one candidate pair as annchor.py:345-380 leaves it.
-__device__ __forceinline__ PairVal pair_value(const View &V, const TileModel *tm, float lb, float ub,
+__device__ __forceinline__ PairVal pair_value(const View &V, const TileModel *tm, const Model &M, float lb, float ub,
                                               int li, int lj, int gi, int gj, const PointMeta &pi,
                                               const PointMeta &pj, const float *sDi, const float *sDj,
                                               bool flagged)
@@ -235,7 +289,7 @@ __device__ __forceinline__ PairVal pair_value(const View &V, const TileModel *tm
         }
     }
     int bin;
-    out.v = predict_clip2(tm, lb, ub, s, bin);
+    out.v = predict_clip2(tm, M, lb, ub, s, bin);
     if (!V.is_metric && anchorpair) {
         // annchor.py:368-372: anchor distances written explicitly; the later anchor in A wins
         out.v = (pj.slot > pi.slot) ? sDi[pj.slot * SROW + li] : sDj[pi.slot * SROW + lj];

@@ -13,6 +13,7 @@ struct ThreshArgs {
     float *l2val;      // [n * k2]
     int32_t *l2id;     // [n * k2]
     int rank, world;
+    int qcap;          // set by the launcher: per-warp survivor queue capacity
 };
 
 struct ScoreArgs {
@@ -21,8 +22,13 @@ struct ScoreArgs {
     const float *thresh;      // [npad]
     const float *errs;        // concatenated sorted error tables (global, L1-resident)
     const uint16_t *ranktab;  // level of (label, r): ranktab[eoff[label] + label + r], r in [0, len]
+    int n_errs;               // total entries of errs (ranktab has n_errs + nb)
+    int tables_in_smem;       // set by the launcher: errs + ranktab are staged in shared memory
+    int qcap;                 // set by the launcher: per-warp survivor queue capacity
     int nlevels;
     int floor_level;          // histogram / emit only levels >= floor_level
+    uint64_t floor_mix_thr;   // AT the floor level emit only pairs with splitmix64(pair key ^ tie_salt) <= this
+    uint64_t tie_salt;
     float efloor[MAX_BINS];   // p > efloor[label]  <=>  level(label, p) >= floor_level
     float ef_min;             // min over labels of efloor (phase-1 margin); -inf disables the filter
     int has_forced;           // FORCED marks exist (iteration 0): flagged pairs always go to phase 2
@@ -47,8 +53,8 @@ struct SampleArgs {
     int rank, world;
 };
 
-int launch_thresh_sweep(annb_ctx *c, const ThreshArgs &A);
-int launch_score_sweep(annb_ctx *c, const ScoreArgs &A);
+int launch_thresh_sweep(annb_ctx *c, ThreshArgs &A);
+int launch_score_sweep(annb_ctx *c, ScoreArgs &A);
 int launch_sample_sweep(annb_ctx *c, const SampleArgs &A);
 
 }  // namespace annb

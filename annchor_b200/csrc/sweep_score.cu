@@ -48,10 +48,15 @@ __device__ __forceinline__ void flush_emit(const ScoreArgs &A, uint64_t *ek, uin
     en = 0;
 }
 
-__global__ void __launch_bounds__(256, 1) score_sweep_kernel(const ScoreArgs A)
+// Tile processing: phase 1 runs over the 8 micro-tile rows and appends survivors to the warp's
+// shared-memory queue; phase 2 (ONE code instance: the row steps and the end-of-tile flush are
+// cases of a rolled 9-step loop) drains the queue in full 32-lane batches when the tile is done,
+// or earlier if the next row step could overflow it.
+__global__ void __launch_bounds__(256, 1) score_sweep_kernel(const __grid_constant__ ScoreArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const View &V = A.V;
+    const Model &M = A.M;
     const int na = V.na;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ty = tid >> 4, tx = tid & 15;
@@ -66,8 +71,8 @@ __global__ void __launch_bounds__(256, 1) score_sweep_kernel(const ScoreArgs A)
     uint32_t *sB0 = reinterpret_cast<uint32_t *>(sM1j + TILE);
     uint32_t *sB1 = sB0 + BITMAP_WORDS;
     unsigned char *sp = reinterpret_cast<unsigned char *>(sB1 + BITMAP_WORDS);
-    Survivor *queue = reinterpret_cast<Survivor *>(sp) + warp * QCAP;
-    sp += 8 * QCAP * sizeof(Survivor);
+    Survivor *queue = reinterpret_cast<Survivor *>(sp) + warp * A.qcap;
+    sp += (size_t)8 * A.qcap * sizeof(Survivor);
     uint64_t *ek = reinterpret_cast<uint64_t *>(sp) + warp * EMIT_CAP;  // per-warp emission staging
     sp += 8 * EMIT_CAP * sizeof(uint64_t);
     uint16_t *el = reinterpret_cast<uint16_t *>(sp) + warp * EMIT_CAP;
@@ -75,17 +80,26 @@ __global__ void __launch_bounds__(256, 1) score_sweep_kernel(const ScoreArgs A)
     float *thI = reinterpret_cast<float *>(sp);  // [2][128] thresh of the row tile (double-buffered)
     float *thJ = thI + 2 * TILE;                 // [2][128] thresh of the column tile
     TileModel *tm = reinterpret_cast<TileModel *>(thJ + 2 * TILE);
-    uint32_t *sHist = reinterpret_cast<uint32_t *>(tm + 1);
-    build_tile_model(A.M, tm);
+    int *qcnt = reinterpret_cast<int *>(tm + 1) + warp;  // [8] queue lengths
+    uint32_t *sHist = reinterpret_cast<uint32_t *>(reinterpret_cast<int *>(tm + 1) + 8);
+    float *sErr = reinterpret_cast<float *>(sHist + A.nlevels);       // error tables + level ranks, if they fit
+    uint16_t *sRank = reinterpret_cast<uint16_t *>(sErr + A.n_errs);
+    const float *errs = A.tables_in_smem ? sErr : A.errs;
+    const uint16_t *ranktab = A.tables_in_smem ? sRank : A.ranktab;
+    build_tile_model(M, tm);
     if (tid < MAX_BINS) {
         // the error label of a pair is its regression bin b, or b + 1 when dad sits exactly on an edge
-        const int t1 = tid + 1 < A.M.nb ? tid + 1 : (A.M.nb > 0 ? A.M.nb - 1 : 0);
-        float m = tid < A.M.nb ? fminf(A.efloor[tid], A.efloor[t1]) : INFINITY;
+        const int t1 = tid + 1 < M.nb ? tid + 1 : (M.nb > 0 ? M.nb - 1 : 0);
+        float m = tid < M.nb ? fminf(A.efloor[tid], A.efloor[t1]) : INFINITY;
         if (A.ef_min == -INFINITY) m = -INFINITY;  // filter off (floor 0 or non-metric)
         tm->mg[tid] = m;
     }
-
+    if (lane == 0) *qcnt = 0;
     for (int k = tid; k < A.nlevels; k += blockDim.x) sHist[k] = 0;
+    if (A.tables_in_smem) {
+        for (int k = tid; k < A.n_errs; k += blockDim.x) sErr[k] = A.errs[k];
+        for (int k = tid; k < A.n_errs + M.nb; k += blockDim.x) sRank[k] = A.ranktab[k];
+    }
 
     // this CTA's contiguous slice of the rank's tile sequence
     const int64_t nq = (A.q_end - A.q_begin + A.q_stride - 1) / A.q_stride;
@@ -133,8 +147,6 @@ __global__ void __launch_bounds__(256, 1) score_sweep_kernel(const ScoreArgs A)
         const uint32_t *bm = buf ? sB1 : sB0;
         const float *tI = thI + buf * TILE, *tJ = thJ + buf * TILE;
         // ---- phase 1: bounds + clipped prediction; keep (pred < cut-off) | flagged ----
-        float lb[8][8], ub[8][8];
-        bounds_microtile(sDi, sDj, na, ty, tx, lb, ub);
         float cj[8];
         int cAj[8];
 #pragma unroll
@@ -142,28 +154,43 @@ __global__ void __launch_bounds__(256, 1) score_sweep_kernel(const ScoreArgs A)
             cj[c] = tJ[micro_off(tx, c)];
             cAj[c] = sMj[micro_off(tx, c)].cA * SROW;
         }
-        const bool diag = ti == tj;
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            const int li = micro_off(ty, r);
-            const float ci = tI[li];
-            const float *dj_row = sDj + sMi[li].cA * SROW;
-            uint32_t w0, w1;
-            flag_words(bm, li, tx, w0, w1);
-            bool keep[8];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const int lj = micro_off(tx, c);
-                const float s2 = sDi[cAj[c] + li] + dj_row[lj];
-                int bin;
-                const float y = predict_clip2(tm, lb[r][c], ub[r][c], s2, bin);
-                const uint32_t fl = c < 4 ? (w0 >> c) : (w1 >> (c - 4));
-                // level >= floor needs  max(th_i, th_j) - RefineApprox > efloor[label]
-                keep[c] = ((y + tm->mg[bin] < fmaxf(ci, cj[c])) | (fl & 1u)) && (!diag || li < lj);
+        float lb[4][8], ub[4][8];
+#pragma unroll 1
+        for (int pass = 0; pass < 10; ++pass) {  // 2 x (4 row steps + 1 drain-only step)
+            const int h = pass >= 5 ? 1 : 0, step = pass - 5 * h;
+            const int row0 = h * 64 + ty * 4;
+            if (step == 0) {
+                bounds_half(sDi, sDj, na, row0, tx, lb, ub);
+                if (ti == tj) mask_diagonal<true>(row0, tx, lb, ub);
             }
-            const int qn = stage_row(queue, 0, lb[r], ub[r], keep, li, tx, lane);
+            auto row_step = [&](const float (&lbr)[8], const float (&ubr)[8], int r) {
+                const int li = row0 + r;
+                const float ci = tI[li];
+                const float *dj_row = sDj + sMi[li].cA * SROW;
+                uint32_t w0, w1;
+                flag_words(bm, li, tx, w0, w1);
+                uint32_t km = (w0 & 0xfu) | ((w1 & 0xfu) << 4);  // flagged pairs always go to phase 2
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float s2 = sDi[cAj[c] + li] + dj_row[micro_off(tx, c)];
+                    int bin;
+                    const float y = predict_clip2(tm, M, lbr[c], ubr[c], s2, bin);
+                    // level >= floor needs  max(th_i, th_j) - RefineApprox > efloor[label]
+                    km |= (y + tm->mg[bin] < fmaxf(ci, cj[c])) ? (1u << c) : 0u;
+                }
+                stage_row(queue, qcnt, lbr, ubr, km, li, tx);
+            };
+            switch (step) {
+                case 0: row_step(lb[0], ub[0], 0); break;
+                case 1: row_step(lb[1], ub[1], 1); break;
+                case 2: row_step(lb[2], ub[2], 2); break;
+                case 3: row_step(lb[3], ub[3], 3); break;
+                default: break;
+            }
             __syncwarp();
-            // ---- phase 2 ----
+            const int qn = *reinterpret_cast<volatile int *>(qcnt);
+            if (pass < 9 && qn <= A.qcap - QROW) continue;  // room for another row step
+            // ---- phase 2: drain the queue, one survivor per lane ----
             for (int e0 = 0; e0 < qn; e0 += 32) {
                 if (en > EMIT_CAP - 32) flush_emit(A, ek, el, en, lane);
                 const int e = e0 + lane;
@@ -173,28 +200,28 @@ __global__ void __launch_bounds__(256, 1) score_sweep_kernel(const ScoreArgs A)
                     const Survivor s = queue[e];
                     const int li2 = s.ids & 0xff, lj = s.ids >> 8;
                     const int gi = ti * TILE + li2, gj = tj * TILE + lj;
-                    if (gj < V.n) {  // gi < gj by construction
+                    if (gj < V.n && s.lb < INFINITY) {  // gi < gj by construction (diagonal masked to +inf)
                         const PointMeta pi = sMi[li2], pj = sMj[lj];
                         if (is_candidate(pi, pj)) {
-                            const PairVal pv = pair_value(V, tm, s.lb, s.ub, li2, lj, gi, gj, pi, pj, sDi,
+                            const PairVal pv = pair_value(V, tm, M, s.lb, s.ub, li2, lj, gi, gj, pi, pj, sDi,
                                                           sDj, flag_bit(bm, gi, gj));
                             if (!pv.computed) {
                                 ++n_nc;
                                 const float p = fmaxf(tI[li2], tJ[lj]) - pv.v;
-                                const int label = err_label2(tm, pv.dad);
+                                const int label = err_label2(M, pv.dad);
                                 if (p > A.efloor[label]) {
-                                    const float *er = A.errs + A.M.eoff[label];
-                                    int lo = 0, hi = A.M.eoff[label + 1] - A.M.eoff[label];
+                                    const float *er = errs + M.eoff[label];
+                                    int lo = 0, hi = M.eoff[label + 1] - M.eoff[label];
                                     while (lo < hi) {  // np.searchsorted(errs[label], p, 'left')
                                         const int mid = (lo + hi) >> 1;
-                                        if (__ldg(er + mid) < p) lo = mid + 1;
+                                        if (er[mid] < p) lo = mid + 1;
                                         else hi = mid;
                                     }
-                                    const int l = __ldg(A.ranktab + A.M.eoff[label] + label + lo);
+                                    const int l = ranktab[M.eoff[label] + label + lo];
                                     if (l >= A.floor_level) {
-                                        lvl = l;
-                                        key = pair_key((uint32_t)gi, (uint32_t)gj);
                                         atomicAdd(&sHist[l], 1u);
+                                        key = pair_key((uint32_t)gi, (uint32_t)gj);
+                                        if (l > A.floor_level || mix64(key ^ A.tie_salt) <= A.floor_mix_thr) lvl = l;
                                     }
                                 }
                             }
@@ -212,6 +239,8 @@ __global__ void __launch_bounds__(256, 1) score_sweep_kernel(const ScoreArgs A)
                     __syncwarp();
                 }
             }
+            __syncwarp();
+            if (lane == 0) *qcnt = 0;
             __syncwarp();
         }
         n_swept += 64;
@@ -231,15 +260,23 @@ __global__ void __launch_bounds__(256, 1) score_sweep_kernel(const ScoreArgs A)
     }
 }
 
-int launch_score_sweep(annb_ctx *c, const ScoreArgs &A)
+int launch_score_sweep(annb_ctx *c, ScoreArgs &A)
 {
-    const size_t smem = (size_t)4 * A.V.na * SROW * 4 + 4 * TILE * sizeof(PointMeta) +
-                        2 * BITMAP_WORDS * 4 + (size_t)8 * QCAP * sizeof(Survivor) +
-                        (size_t)8 * EMIT_CAP * 10 + 4 * TILE * 4 + sizeof(TileModel) +
-                        (size_t)A.nlevels * 4 + 64;
-    ANNB_REQUIRE(smem <= 227 * 1024, ANNB_ERANGE,
-                 "score sweep needs %zu bytes of shared memory (n_anchors=%d, %d levels)", smem,
+    const size_t lim = 227 * 1024;
+    const size_t base = (size_t)4 * A.V.na * SROW * 4 + 4 * TILE * sizeof(PointMeta) +
+                        2 * BITMAP_WORDS * 4 + (size_t)8 * EMIT_CAP * 10 + 4 * TILE * 4 + sizeof(TileModel) +
+                        8 * 4 + (size_t)A.nlevels * 4 + 64;
+    const size_t tables = ((size_t)A.n_errs * 4 + (size_t)(A.n_errs + A.M.nb) * 2 + 15) & ~(size_t)15;
+    const size_t qmin = (size_t)8 * (QROW + 32) * sizeof(Survivor);
+    ANNB_REQUIRE(base + qmin <= lim, ANNB_ERANGE,
+                 "score sweep needs %zu bytes of shared memory (n_anchors=%d, %d levels)", base + qmin,
                  A.V.na, A.nlevels);
+    A.tables_in_smem = base + qmin + tables <= lim ? 1 : 0;
+    size_t avail = lim - base - (A.tables_in_smem ? tables : 0);
+    int qcap = (int)(avail / (8 * sizeof(Survivor))) / 32 * 32;
+    if (qcap > QCAP) qcap = QCAP;
+    A.qcap = qcap;
+    const size_t smem = base + (A.tables_in_smem ? tables : 0) + (size_t)8 * qcap * sizeof(Survivor);
     ANNB_CUDA(cudaFuncSetAttribute(score_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)smem));
     const int64_t nq = (A.q_end - A.q_begin + A.q_stride - 1) / A.q_stride;

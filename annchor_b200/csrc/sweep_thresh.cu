@@ -55,10 +55,11 @@ struct SortedRow {
 };
 
 template <bool L2ON>
-__global__ void __launch_bounds__(256, 1) thresh_sweep_kernel(const ThreshArgs A)
+__global__ void __launch_bounds__(256, 1) thresh_sweep_kernel(const __grid_constant__ ThreshArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const View &V = A.V;
+    const Model &M = A.M;
     const int na = V.na;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ty = tid >> 4, tx = tid & 15;
@@ -73,16 +74,18 @@ __global__ void __launch_bounds__(256, 1) thresh_sweep_kernel(const ThreshArgs A
     uint32_t *sB1 = sB0 + BITMAP_WORDS;
     uint32_t *sBT = sB1 + BITMAP_WORDS;  // flags re-oriented to (row = this CTA's point, col = column point)
     TileModel *tm = reinterpret_cast<TileModel *>(sBT + BITMAP_WORDS);
-    Survivor *queue = reinterpret_cast<Survivor *>(tm + 1) + warp * QCAP;
-    float *thr1 = reinterpret_cast<float *>(reinterpret_cast<Survivor *>(tm + 1) + 8 * QCAP);
+    Survivor *queue = reinterpret_cast<Survivor *>(tm + 1) + warp * A.qcap;
+    float *thr1 = reinterpret_cast<float *>(reinterpret_cast<Survivor *>(tm + 1) + 8 * A.qcap);
     float *thr2 = thr1 + TILE;
     float *cut = thr2 + TILE;  // max(thr1, thr2): phase-1 cut-off per row
-    float *L1 = cut + TILE;
+    int *qcnt = reinterpret_cast<int *>(cut + TILE) + warp;  // [8]
+    float *L1 = reinterpret_cast<float *>(reinterpret_cast<int *>(cut + TILE) + 8);
     float *L2v = L1 + TILE * A.k1;
     int32_t *L2i = reinterpret_cast<int32_t *>(L2v + TILE * A.k2);
     const bool filter = V.is_metric != 0;  // is_metric=False overrides anchor pairs with raw D (annchor.py:368-372)
 
-    build_tile_model(A.M, tm);
+    build_tile_model(M, tm);
+    if (lane == 0) *qcnt = 0;
     for (int rb = blockIdx.x * A.world + A.rank; rb < V.T; rb += gridDim.x * A.world) {
         // ---- init row state, stage the row tile ----
         for (int k = tid; k < TILE * A.k1; k += blockDim.x) L1[k] = INFINITY;
@@ -124,32 +127,46 @@ __global__ void __launch_bounds__(256, 1) thresh_sweep_kernel(const ThreshArgs A
                 }
                 sBF = sBT;
             }
-            // ---- phase 1: bounds + clipped prediction for all 64 pairs of the micro-tile ----
-            float lb[8][8], ub[8][8];
-            bounds_microtile(sDi, sDj, na, ty, tx, lb, ub);
+            // ---- phase 1: bounds + clipped prediction, two passes of 4 x 8 pairs per thread ----
             int cAj[8];
 #pragma unroll
             for (int c = 0; c < 8; ++c) cAj[c] = sMj[micro_off(tx, c)].cA * SROW;
-
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                const int li = micro_off(ty, r);
-                const float cr = filter ? cut[li] : INFINITY;
-                const float *dj_row = sDj + sMi[li].cA * SROW;
-                uint32_t w0, w1;
-                flag_words(sBF, li, tx, w0, w1);
-                bool keep[8];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const float s2 = sDi[cAj[c] + li] + dj_row[micro_off(tx, c)];
-                    int bin;
-                    const float y = predict_clip2(tm, lb[r][c], ub[r][c], s2, bin);
-                    const uint32_t fl = c < 4 ? (w0 >> c) : (w1 >> (c - 4));
-                    keep[c] = (y < cr) | (fl & 1u);
+            float lb[4][8], ub[4][8];
+#pragma unroll 1
+            for (int pass = 0; pass < 10; ++pass) {  // 2 x (4 row steps + 1 drain-only step)
+                const int h = pass >= 5 ? 1 : 0, step = pass - 5 * h;
+                const int row0 = h * 64 + ty * 4;
+                if (step == 0) {
+                    bounds_half(sDi, sDj, na, row0, tx, lb, ub);
+                    if (tc == rb) mask_diagonal<false>(row0, tx, lb, ub);
                 }
-                const int qn = stage_row(queue, 0, lb[r], ub[r], keep, li, tx, lane);
+                auto row_step = [&](const float (&lbr)[8], const float (&ubr)[8], int r) {
+                    const int li = row0 + r;
+                    const float cr = filter ? cut[li] : INFINITY;
+                    const float *dj_row = sDj + sMi[li].cA * SROW;
+                    uint32_t w0, w1;
+                    flag_words(sBF, li, tx, w0, w1);
+                    uint32_t km = (w0 & 0xfu) | ((w1 & 0xfu) << 4);  // flagged pairs always go to phase 2
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const float s2 = sDi[cAj[c] + li] + dj_row[micro_off(tx, c)];
+                        int bin;
+                        const float y = predict_clip2(tm, M, lbr[c], ubr[c], s2, bin);
+                        km |= (y < cr) ? (1u << c) : 0u;
+                    }
+                    stage_row(queue, qcnt, lbr, ubr, km, li, tx);
+                };
+                switch (step) {
+                    case 0: row_step(lb[0], ub[0], 0); break;
+                    case 1: row_step(lb[1], ub[1], 1); break;
+                    case 2: row_step(lb[2], ub[2], 2); break;
+                    case 3: row_step(lb[3], ub[3], 3); break;
+                    default: break;
+                }
                 __syncwarp();
-                // ---- phase 2: survivors of this row step, one per lane ----
+                const int qn = *reinterpret_cast<volatile int *>(qcnt);
+                if (pass < 9 && qn <= A.qcap - QROW) continue;  // room for another row step
+                // ---- phase 2: drain the queue, one survivor per lane ----
                 for (int e0 = 0; e0 < qn; e0 += 32) {
                     const int e = e0 + lane;
                     bool w1b = false, w2b = false;
@@ -164,7 +181,7 @@ __global__ void __launch_bounds__(256, 1) thresh_sweep_kernel(const ThreshArgs A
                         const PointMeta pi = sMi[row], pj = sMj[lj];
                         if (gi < V.n && gj < V.n && gi != gj && is_candidate(pi, pj)) {
                             const bool fl = (sBF[row * 4 + (lj >> 5)] >> (lj & 31)) & 1u;
-                            const PairVal pv = pair_value(V, tm, sv.lb, sv.ub, row, lj, gi, gj, pi, pj, sDi,
+                            const PairVal pv = pair_value(V, tm, M, sv.lb, sv.ub, row, lj, gi, gj, pi, pj, sDi,
                                                           sDj, fl);
                             v = pv.v;
                             w1b = v < thr1[row];
@@ -192,8 +209,12 @@ __global__ void __launch_bounds__(256, 1) thresh_sweep_kernel(const ThreshArgs A
                     }
                 }
                 __syncwarp();
-                // refresh the phase-1 cut-off of the two rows this warp just processed (warp-private rows)
-                if ((lane & 15) == 0) cut[li] = fmaxf(thr1[li], thr2[li]);
+                // refresh the phase-1 cut-offs of this warp's 16 rows ({8w..8w+7} U {64+8w..})
+                if (lane < 16) {
+                    const int row = (lane < 8) ? (warp * 8 + lane) : (64 + warp * 8 + (lane - 8));
+                    cut[row] = fmaxf(thr1[row], thr2[row]);
+                }
+                if (lane == 0) *qcnt = 0;
                 __syncwarp();
             }
         }
@@ -214,22 +235,26 @@ __global__ void __launch_bounds__(256, 1) thresh_sweep_kernel(const ThreshArgs A
     }
 }
 
-size_t thresh_smem_bytes(int na, int k1, int k2)
+static size_t thresh_smem_base(int na, int k1, int k2)
 {
     return (size_t)3 * na * SROW * 4 + 3 * TILE * sizeof(PointMeta) + 3 * BITMAP_WORDS * 4 +
-           sizeof(TileModel) + (size_t)8 * QCAP * sizeof(Survivor) + 3 * TILE * 4 +
-           (size_t)TILE * k1 * 4 + (size_t)TILE * k2 * 8 + 64;
+           sizeof(TileModel) + 3 * TILE * 4 + 8 * 4 + (size_t)TILE * k1 * 4 + (size_t)TILE * k2 * 8 + 64;
 }
 
-int launch_thresh_sweep(annb_ctx *c, const ThreshArgs &A)
+int launch_thresh_sweep(annb_ctx *c, ThreshArgs &A)
 {
-    const size_t smem = thresh_smem_bytes(A.V.na, A.k1, A.k2);
-    ANNB_REQUIRE(smem <= 227 * 1024, ANNB_ERANGE,
-                 "thresh sweep needs %zu bytes of shared memory (n_anchors=%d, lists %d/%d)", smem,
-                 A.V.na, A.k1, A.k2);
+    const size_t lim = 227 * 1024;
+    const size_t base = thresh_smem_base(A.V.na, A.k1, A.k2);
+    ANNB_REQUIRE(base + (size_t)8 * (QROW + 32) * sizeof(Survivor) <= lim, ANNB_ERANGE,
+                 "thresh sweep needs %zu bytes of shared memory (n_anchors=%d, lists %d/%d)",
+                 base + (size_t)8 * (QROW + 32) * sizeof(Survivor), A.V.na, A.k1, A.k2);
     ANNB_REQUIRE(A.k1 <= MAX_LIST && A.k2 <= MAX_LIST, ANNB_ERANGE,
                  "n_neighbors too large for the device row lists (k1=%d, k2=%d, max %d)", A.k1, A.k2,
                  MAX_LIST);
+    int qcap = (int)((lim - base) / (8 * sizeof(Survivor))) / 32 * 32;
+    if (qcap > QCAP) qcap = QCAP;
+    A.qcap = qcap;
+    const size_t smem = base + (size_t)8 * qcap * sizeof(Survivor);
     const int rows_here = (A.V.T - A.rank + A.world - 1) / A.world;
     const int grid = rows_here < 1 ? 1 : rows_here;
     if (A.k2 > 0) {

@@ -106,7 +106,7 @@ class SimpleStratifiedSampler:
         the reference's draw needs the materialised Theta(N^2) pair list."""
 
     def __init__(self, partition_feature_name="double anchor distance", n_partitions=7,
-                 exact_limit=4_000_000, pool_size=1_000_000):
+                 exact_limit=4_000_000, pool_size=1 << 18):
         self.partition_feature_name = partition_feature_name
         self.n_partitions = n_partitions
         self.exact_limit = exact_limit   # at most this many not-computed candidates -> exact mode

@@ -204,6 +204,9 @@ def run_ours(args, w):
         ann.fit()
         ms = ctx.timer_stop()
         barrier()
+        if os.environ.get("ANNB_BENCH_VERBOSE"):
+            sys.stderr.write("[bench] step %d: %.1f ms device-timed; stages %s\n"
+                             % (it, ms, {k: round(v * 1e3, 1) for k, v in ann.stage_times.items()}))
         if it >= args.warmup:
             times.append(ms)
             sweeps.append(ann._index.last_sweep())

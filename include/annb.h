@@ -59,6 +59,9 @@ int64_t annb_launch_count(void);
 /* ---- context ------------------------------------------------------------ */
 int annb_ctx_create(int device, annb_ctx **out);
 int annb_ctx_destroy(annb_ctx *ctx);
+/* device buffers released by indexes / datasets are cached for reuse by later fits; this returns
+ * the cached blocks to the driver (also done by annb_ctx_destroy) */
+int annb_pool_trim(void);
 int annb_sync(annb_ctx *ctx);
 /* cudaStream_t of the context, as an integer (for torch.cuda.ExternalStream / events) */
 int annb_ctx_stream(annb_ctx *ctx, uint64_t *stream);
@@ -150,6 +153,9 @@ typedef struct annb_index_params {
 int annb_index_create(annb_ctx *ctx, const annb_dataset *ds, int metric,
                       const annb_index_params *params, annb_index **out);
 int annb_index_destroy(annb_index *ix);
+/* optional: size the known-pair store for n_pairs entries up front (exact evaluations, i.e.
+ * p_work * N(N-1)/2 of annchor/annchor.py:100,440, plus look-ahead pairs that may be tightened) */
+int annb_index_reserve_pairs(annb_index *ix, int64_t n_pairs);
 /* stage 1: run the MaxMin picker into the index (or load caller-provided anchors) */
 int annb_index_maxmin(annb_index *ix, int64_t first, int64_t *A);
 int annb_index_set_anchors(annb_index *ix, const int64_t *A, int64_t nA, const double *D);
