@@ -329,7 +329,7 @@ partition_emitted_kernel(const uint64_t *__restrict__ keys, const uint16_t *__re
             if (p < E) {
                 const int l = lvl[p];
                 key[k] = keys[p];
-                const uint64_t mk = mix64(key[k] ^ salt);
+                const uint64_t mk = tie_key((uint32_t)(key[k] >> 32), (uint32_t)key[k], salt);
                 const bool sel = l > c1 || (l == c1 && mk <= thr1);
                 const bool nxt = !sel && (l > c2 || (l == c2 && mk <= thr2));
                 cls[k] = sel ? 1 : (nxt ? 2 : 0);
@@ -578,7 +578,9 @@ __global__ void tighten_work_kernel(const int64_t *__restrict__ kptr, const int6
     }
 }
 
-constexpr int TG_SLOTS = 8192;   // shared-memory table slots: 2048 buckets of 4 ids (+ 4 values)
+constexpr int TG_SLOTS = 8192;   // shared-memory table slots: 2048 buckets of 4 ids (+ 4 values), 64 KB -> 3 CTAs / SM
+                                 // (a 4096-slot table at 6 CTAs / SM is 2.3x slower: hub rows then need several
+                                 // chunks and every chunk re-streams all partner lists)
 constexpr int TG_CHUNK = 4096;   // entries of N(i) hashed at a time (load factor <= 0.5)
 
 // rows whose group streams more than `thr` list entries are queued first (longest-processing-time
@@ -902,7 +904,10 @@ compact_level_kernel(const uint64_t *__restrict__ keys, const uint16_t *__restri
 #pragma unroll
         for (int k = 0; k < PE_ITEMS; ++k)
             if (hit[k]) {
-                if ((int64_t)pos < out_cap) out[pos] = mix64(keys[b0 + k * 256 + threadIdx.x] ^ salt);
+                if ((int64_t)pos < out_cap) {
+                    const uint64_t kk = keys[b0 + k * 256 + threadIdx.x];
+                    out[pos] = tie_key((uint32_t)(kk >> 32), (uint32_t)kk, salt);
+                }
                 ++pos;
             }
     }
@@ -1613,7 +1618,7 @@ static void fill_efloor(const annb_index *ix, int floor_level, float *efloor, fl
 }
 
 static int run_score(annb_index *ix, int floor_level, uint64_t floor_mix_thr, int stride, bool emit,
-                     int64_t emit_cap, std::vector<uint64_t> &hist, unsigned long long cnt[3])
+                     int64_t emit_cap, std::vector<uint64_t> &hist, unsigned long long cnt[5])
 {
     annb_ctx *c = ix->ctx;
     ScoreArgs A;
@@ -1628,6 +1633,11 @@ static int run_score(annb_index *ix, int floor_level, uint64_t floor_mix_thr, in
     A.floor_mix_thr = floor_mix_thr;
     A.tie_salt = ix->tie_salt;
     fill_efloor(ix, floor_level, A.efloor, &A.ef_min);
+    {
+        float dummy;
+        fill_efloor(ix, floor_level + 1, A.efloor_hi, &dummy);
+    }
+    A.wide_floor = floor_mix_thr != ~0ull ? 1 : 0;
     A.has_forced = ix->has_forced ? 1 : 0;
     A.hist = ix->hist.as<uint32_t>();
     A.counters = ix->counters.as<unsigned long long>();
@@ -1654,9 +1664,12 @@ static int run_score(annb_index *ix, int floor_level, uint64_t floor_mix_thr, in
     ANNB_CUDA(cudaEventRecord(c->ev1, c->stream));
     std::vector<uint32_t> h32(ix->nlevels);
     ANNB_CUDA(cudaMemcpyAsync(h32.data(), ix->hist.p, (size_t)ix->nlevels * 4, cudaMemcpyDeviceToHost, c->stream));
-    ANNB_CUDA(cudaMemcpyAsync(cnt, ix->counters.p, 24, cudaMemcpyDeviceToHost, c->stream));
+    ANNB_CUDA(cudaMemcpyAsync(cnt, ix->counters.p, 40, cudaMemcpyDeviceToHost, c->stream));
     ANNB_CUDA(cudaStreamSynchronize(c->stream));
     hist.assign(h32.begin(), h32.end());
+    if (g_trace)
+        fprintf(stderr, "[annb-trace]   score sweep: stride %d floor %d pairs-in-phase2 %llu (flagged %llu) not-computed %llu emitted %llu\n",
+                stride, floor_level, cnt[3], cnt[4], cnt[1], cnt[0]);
     ANNB_TRY(ix->reduce(hist.data(), (int64_t)hist.size(), ANNB_RED_U64));  // global level counts
     float ms = 0;
     ANNB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
@@ -1753,7 +1766,7 @@ ANNB_API int annb_index_select(annb_index *ix, int64_t n_refine, int64_t lookahe
     int64_t tot_target = want1 >= n_nc ? n_nc : std::min<int64_t>(want2, n_nc);
 
     std::vector<uint64_t> h1, h2;
-    unsigned long long c1v[3] = {0, 0, 0}, c2v[3] = {0, 0, 0};
+    unsigned long long c1v[5] = {0, 0, 0, 0, 0}, c2v[5] = {0, 0, 0, 0, 0};
     // Level 0 is probability 0.  On small problems it takes part like any other level (the
     // reference's argpartition then picks arbitrary probability-0 pairs).  On large problems
     // emitting the probability-0 bulk is pointless and Theta(N^2): the cut never goes below level 1,
@@ -1816,20 +1829,42 @@ ANNB_API int annb_index_select(annb_index *ix, int64_t n_refine, int64_t lookahe
         int64_t cum = 0;
         for (int L = floor_level; L < ix->nlevels; ++L) cum += h2[L];
         const int64_t above = cum - (int64_t)h2[floor_level];
+        const bool wide = floor_thr != ~0ull;  // h2[floor] then counts only the pairs that passed the hash
+        const double frac = (double)floor_thr / 18446744073709551615.0;
         if (red[0]) {
             if (g_trace) fprintf(stderr, "[annb-trace]   select attempt %d: overflow E %lld cap %lld floor %d\n", attempt,
                                  (long long)E_all, (long long)cap, floor_level);
-            // more pairs emitted than planned: the histogram above the floor is exact, re-plan exactly
-            plan(h2, floor_level, 1.0, 1.0);
+            // more pairs emitted than planned: the histogram above the floor is exact, re-plan from it
+            // (the floor level's population is extrapolated from the observed hash pass rate)
+            std::vector<uint64_t> hc(h2);
+            if (wide) hc[floor_level] = (uint64_t)((double)h2[floor_level] / std::max(frac, 1e-12));
+            plan(hc, floor_level, wide ? 1.0000001 : 1.0, 1.0);
             continue;
         }
         at_floor_emitted = E_all - above;
         if (g_trace)
             fprintf(stderr, "[annb-trace]   select attempt %d: floor %d thr %.6f cap %lld E %lld cum %lld above %lld "
-                            "at_floor %llu emitted_at_floor %lld targets %lld/%lld n_nc %lld overflow %d\n",
-                    attempt, floor_level, (double)floor_thr / 18446744073709551615.0, (long long)cap, (long long)E_all,
-                    (long long)cum, (long long)above, (unsigned long long)h2[floor_level], (long long)at_floor_emitted,
-                    (long long)sel_target, (long long)tot_target, (long long)n_nc, (int)red[0]);
+                            "at_floor %llu emitted_at_floor %lld targets %lld/%lld n_nc %lld\n",
+                    attempt, floor_level, frac, (long long)cap, (long long)E_all, (long long)cum, (long long)above,
+                    (unsigned long long)h2[floor_level], (long long)at_floor_emitted, (long long)sel_target,
+                    (long long)tot_target, (long long)n_nc);
+        if (wide && above < tot_target && tot_target - above > at_floor_emitted) {
+            // the hash threshold at the floor level let too few pairs through: scale it by the
+            // observed pass rate (+10 %), everything at the floor level on the last attempts
+            const double need = (double)(tot_target - above);
+            const double nf = frac * need / (double)std::max<int64_t>(at_floor_emitted, 1) * 1.1 +
+                              256.0 * frac / (double)std::max<int64_t>(at_floor_emitted, 1);
+            const double pass_est = need * 1.1 + 256.0;
+            if (nf >= 0.999 || attempt >= 2) {
+                floor_thr = ~0ull;
+                cap = n_nc + 1024;  // population at the floor level unknown: worst case
+                cap = std::min<int64_t>(cap, (int64_t)((double)above + (double)at_floor_emitted / std::max(frac, 1e-12) * 1.2) + (1 << 20));
+            } else {
+                floor_thr = (uint64_t)(nf * 18446744073709551615.0);
+                cap = std::min<int64_t>((int64_t)((double)above + pass_est * 1.1) + 65536, n_nc + 1024);
+            }
+            continue;
+        }
         if (floor_level > min_floor && cum < tot_target) {
             // floor too high: exact full histogram, exact floor
             ANNB_TRY(run_score(ix, min_floor, ~0ull, 1, false, 0, h1, c1v));
@@ -1839,18 +1874,6 @@ ANNB_API int annb_index_select(annb_index *ix, int64_t n_refine, int64_t lookahe
         if (cum < tot_target) {  // large problem, not enough positive-probability pairs
             tot_target = cum;
             sel_target = std::min<int64_t>(sel_target, cum);
-        }
-        if (above < tot_target && tot_target - above > at_floor_emitted) {
-            // the hash threshold at the floor level let too few pairs through: scale it by the
-            // observed pass rate (+10 %), everything at the floor level on the last attempts
-            const double need = (double)(tot_target - above);
-            const double frac = (double)floor_thr / 18446744073709551615.0;
-            const double nf = frac * need / (double)std::max<int64_t>(at_floor_emitted, 1) * 1.1 + 256.0 / (double)std::max<uint64_t>(h2[floor_level], 1);
-            if (nf >= 0.999 || attempt >= 2) floor_thr = ~0ull;
-            else floor_thr = (uint64_t)(nf * 18446744073709551615.0);
-            const double pass = floor_thr == ~0ull ? (double)h2[floor_level] : nf * (double)h2[floor_level];
-            cap = std::min<int64_t>((int64_t)((double)above + pass * 1.05) + 65536, n_nc + 1024);
-            continue;
         }
         break;
     }

@@ -90,6 +90,25 @@ __host__ __device__ __forceinline__ uint64_t mix64(uint64_t x)
     return x;
 }
 
+// 32-bit pair hash (cheap enough for phase 1 of the sweeps)
+__host__ __device__ __forceinline__ uint32_t hash_pair32(uint32_t i, uint32_t j, uint32_t seed)
+{
+    uint32_t h = (i * 0x9E3779B1u) ^ (j * 0x85EBCA77u) ^ seed;
+    h ^= h >> 15;
+    h *= 0x2C1B3C6Du;
+    h ^= h >> 12;
+    h *= 0x297A2D39u;
+    h ^= h >> 15;
+    return h;
+}
+
+// tie-break key of a pair at a selection cut (smaller wins): the top 32 bits are the cheap pair hash,
+// so phase 1 can pre-filter on them; the low 32 bits make the order total
+__host__ __device__ __forceinline__ uint64_t tie_key(uint32_t lo, uint32_t hi, uint64_t salt)
+{
+    return ((uint64_t)hash_pair32(lo, hi, (uint32_t)salt) << 32) | (uint32_t)mix64(pair_key(lo, hi) ^ salt);
+}
+
 // one 16-byte load per probe; returns the kind (KIND_NONE if absent) and fills (a, b)
 __device__ __forceinline__ uint32_t hash_lookup(const View &V, uint64_t key, float &a, float &b)
 {

@@ -153,7 +153,8 @@ __device__ __forceinline__ void mask_diagonal(int row0, int tx, float (&lb)[4][8
 // edges are read straight from the kernel parameters (constant bank operands: no load, no register).
 struct __align__(16) TileModel {
     float4 cf[MAX_BINS];   // (c0, c1, c2 / 2, intercept) per bin (regressors.py:39-67)
-    float mg[MAX_BINS];    // scoring only: conservative per-bin margin min(efloor[b], efloor[b+1])
+    float4 mx[MAX_BINS];   // scoring only: error-floor margins of labels (b, b+1): level >= floor, level > floor
+    float en[MAX_BINS];    // scoring only: doubled edge b + 1 (the pair's label is b + 1 iff 2*dad equals it)
 };
 
 __device__ __forceinline__ void build_tile_model(const Model &M, TileModel *tm)
@@ -162,7 +163,8 @@ __device__ __forceinline__ void build_tile_model(const Model &M, TileModel *tm)
     if (t < MAX_BINS) {
         const bool live = t < M.nb;
         tm->cf[t] = live ? make_float4(M.c0[t], M.c1[t], 0.5f * M.c2[t], M.ic[t]) : make_float4(0, 0, 0, 0);
-        tm->mg[t] = 0.0f;
+        tm->mx[t] = make_float4(0, 0, 0, 0);
+        tm->en[t] = INFINITY;
     }
 }
 

@@ -30,6 +30,8 @@ struct ScoreArgs {
     uint64_t floor_mix_thr;   // AT the floor level emit only pairs with splitmix64(pair key ^ tie_salt) <= this
     uint64_t tie_salt;
     float efloor[MAX_BINS];   // p > efloor[label]  <=>  level(label, p) >= floor_level
+    float efloor_hi[MAX_BINS];  // p > efloor_hi[label]  <=>  level(label, p) >= floor_level + 1
+    int wide_floor;           // phase 1 pre-filters floor-level pairs on the tie-break hash (floor_mix_thr < all)
     float ef_min;             // min over labels of efloor (phase-1 margin); -inf disables the filter
     int has_forced;           // FORCED marks exist (iteration 0): flagged pairs always go to phase 2
     uint32_t *hist;           // [nlevels]

@@ -88,11 +88,16 @@ __global__ void __launch_bounds__(256, 1) score_sweep_kernel(const __grid_consta
     const uint16_t *ranktab = A.tables_in_smem ? sRank : A.ranktab;
     build_tile_model(M, tm);
     if (tid < MAX_BINS) {
-        // the error label of a pair is its regression bin b, or b + 1 when dad sits exactly on an edge
+        // the error label of a pair is its regression bin b, or b + 1 when 2*dad sits exactly on edge
+        // b + 1 (closed [lo, hi] labels vs (lo, hi] bins): mx = margins of (b, b+1) for level >= floor
+        // (.x, .y) and for level > floor (.z, .w); en = that edge
         const int t1 = tid + 1 < M.nb ? tid + 1 : (M.nb > 0 ? M.nb - 1 : 0);
-        float m = tid < M.nb ? fminf(A.efloor[tid], A.efloor[t1]) : INFINITY;
-        if (A.ef_min == -INFINITY) m = -INFINITY;  // filter off (floor 0 or non-metric)
-        tm->mg[tid] = m;
+        const bool live = tid < M.nb, off = A.ef_min == -INFINITY;  // off: floor 0 or non-metric
+        tm->mx[tid] = make_float4(off ? -INFINITY : (live ? A.efloor[tid] : INFINITY),
+                                  off ? -INFINITY : (live ? A.efloor[t1] : INFINITY),
+                                  off ? -INFINITY : (live ? A.efloor_hi[tid] : INFINITY),
+                                  off ? -INFINITY : (live ? A.efloor_hi[t1] : INFINITY));
+        tm->en[tid] = (tid + 1 < M.nb) ? M.e2[tid + 1] : INFINITY;
     }
     if (lane == 0) *qcnt = 0;
     for (int k = tid; k < A.nlevels; k += blockDim.x) sHist[k] = 0;
@@ -105,7 +110,7 @@ __global__ void __launch_bounds__(256, 1) score_sweep_kernel(const __grid_consta
     const int64_t nq = (A.q_end - A.q_begin + A.q_stride - 1) / A.q_stride;
     const int64_t per = (nq + gridDim.x - 1) / gridDim.x;
     const int64_t m0 = (int64_t)blockIdx.x * per, m1 = min(nq, m0 + per);
-    unsigned long long n_nc = 0, n_swept = 0;
+    unsigned long long n_nc = 0, n_swept = 0, n_staged = 0, n_flagged = 0;
     int en = 0;  // staged emissions of this warp
 
     auto tile_of = [&](int64_t m, int &ti, int &tj) {
@@ -149,10 +154,13 @@ __global__ void __launch_bounds__(256, 1) score_sweep_kernel(const __grid_consta
         // ---- phase 1: bounds + clipped prediction; keep (pred < cut-off) | flagged ----
         float cj[8];
         int cAj[8];
+        uint32_t hj[8];  // column part of the pair hash (hash_pair32)
+        const uint32_t thr_hi = (uint32_t)(A.floor_mix_thr >> 32);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
             cj[c] = tJ[micro_off(tx, c)];
             cAj[c] = sMj[micro_off(tx, c)].cA * SROW;
+            hj[c] = (uint32_t)(tj * TILE + micro_off(tx, c)) * 0x85EBCA77u;
         }
         float lb[4][8], ub[4][8];
 #pragma unroll 1
@@ -170,13 +178,40 @@ __global__ void __launch_bounds__(256, 1) score_sweep_kernel(const __grid_consta
                 uint32_t w0, w1;
                 flag_words(bm, li, tx, w0, w1);
                 uint32_t km = (w0 & 0xfu) | ((w1 & 0xfu) << 4);  // flagged pairs always go to phase 2
+                // level >= floor needs  max(th_i, th_j) - RefineApprox > efloor[label]
+                if (!A.wide_floor) {
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const float s2 = sDi[cAj[c] + li] + dj_row[micro_off(tx, c)];
-                    int bin;
-                    const float y = predict_clip2(tm, M, lbr[c], ubr[c], s2, bin);
-                    // level >= floor needs  max(th_i, th_j) - RefineApprox > efloor[label]
-                    km |= (y + tm->mg[bin] < fmaxf(ci, cj[c])) ? (1u << c) : 0u;
+                    for (int c = 0; c < 8; ++c) {
+                        const float s2 = sDi[cAj[c] + li] + dj_row[micro_off(tx, c)];
+                        int bin;
+                        const float y = predict_clip2(tm, M, lbr[c], ubr[c], s2, bin);
+                        const float4 mx = tm->mx[bin];
+                        const float mg = (s2 == tm->en[bin]) ? mx.y : mx.x;
+                        km |= (y + mg < fmaxf(ci, cj[c])) ? (1u << c) : 0u;
+                    }
+                } else {
+                    // many more pairs tie AT the floor level than the cut can take: of those, only the
+                    // ones whose tie-break hash can pass the emission threshold go on (levels above the
+                    // floor always do)
+                    const uint32_t hi_row = ((uint32_t)(ti * TILE + li) * 0x9E3779B1u) ^ (uint32_t)A.tie_salt;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const float s2 = sDi[cAj[c] + li] + dj_row[micro_off(tx, c)];
+                        int bin;
+                        const float y = predict_clip2(tm, M, lbr[c], ubr[c], s2, bin);
+                        const float4 mx = tm->mx[bin];
+                        const bool eq = s2 == tm->en[bin];
+                        const float cut = fmaxf(ci, cj[c]);
+                        uint32_t h = hi_row ^ hj[c];
+                        h ^= h >> 15;
+                        h *= 0x2C1B3C6Du;
+                        h ^= h >> 12;
+                        h *= 0x297A2D39u;
+                        h ^= h >> 15;
+                        const bool above = y + (eq ? mx.w : mx.z) < cut;
+                        const bool atfl = (y + (eq ? mx.y : mx.x) < cut) && h <= thr_hi;
+                        km |= (above | atfl) ? (1u << c) : 0u;
+                    }
                 }
                 stage_row(queue, qcnt, lbr, ubr, km, li, tx);
             };
@@ -191,6 +226,7 @@ __global__ void __launch_bounds__(256, 1) score_sweep_kernel(const __grid_consta
             const int qn = *reinterpret_cast<volatile int *>(qcnt);
             if (pass < 9 && qn <= A.qcap - QROW) continue;  // room for another row step
             // ---- phase 2: drain the queue, one survivor per lane ----
+            if (lane == 0) n_staged += qn;
             for (int e0 = 0; e0 < qn; e0 += 32) {
                 if (en > EMIT_CAP - 32) flush_emit(A, ek, el, en, lane);
                 const int e = e0 + lane;
@@ -203,25 +239,33 @@ __global__ void __launch_bounds__(256, 1) score_sweep_kernel(const __grid_consta
                     if (gj < V.n && s.lb < INFINITY) {  // gi < gj by construction (diagonal masked to +inf)
                         const PointMeta pi = sMi[li2], pj = sMj[lj];
                         if (is_candidate(pi, pj)) {
+                            const bool fl = flag_bit(bm, gi, gj);
+                            n_flagged += fl ? 1 : 0;
                             const PairVal pv = pair_value(V, tm, M, s.lb, s.ub, li2, lj, gi, gj, pi, pj, sDi,
-                                                          sDj, flag_bit(bm, gi, gj));
+                                                          sDj, fl);
                             if (!pv.computed) {
                                 ++n_nc;
                                 const float p = fmaxf(tI[li2], tJ[lj]) - pv.v;
                                 const int label = err_label2(M, pv.dad);
                                 if (p > A.efloor[label]) {
-                                    const float *er = errs + M.eoff[label];
-                                    int lo = 0, hi = M.eoff[label + 1] - M.eoff[label];
-                                    while (lo < hi) {  // np.searchsorted(errs[label], p, 'left')
-                                        const int mid = (lo + hi) >> 1;
-                                        if (er[mid] < p) lo = mid + 1;
-                                        else hi = mid;
+                                    int l = A.floor_level;
+                                    if (p > A.efloor_hi[label]) {  // above the floor level: rank it
+                                        const float *er = errs + M.eoff[label];
+                                        int lo = 0, hi = M.eoff[label + 1] - M.eoff[label];
+                                        while (lo < hi) {  // np.searchsorted(errs[label], p, 'left')
+                                            const int mid = (lo + hi) >> 1;
+                                            if (er[mid] < p) lo = mid + 1;
+                                            else hi = mid;
+                                        }
+                                        l = ranktab[M.eoff[label] + label + lo];
                                     }
-                                    const int l = ranktab[M.eoff[label] + label + lo];
                                     if (l >= A.floor_level) {
-                                        atomicAdd(&sHist[l], 1u);
                                         key = pair_key((uint32_t)gi, (uint32_t)gj);
-                                        if (l > A.floor_level || mix64(key ^ A.tie_salt) <= A.floor_mix_thr) lvl = l;
+                                        if (l > A.floor_level ||
+                                            tie_key((uint32_t)gi, (uint32_t)gj, A.tie_salt) <= A.floor_mix_thr) {
+                                            lvl = l;
+                                            atomicAdd(&sHist[l], 1u);  // at the floor level: emitted pairs only
+                                        }
                                     }
                                 }
                             }
@@ -253,10 +297,13 @@ __global__ void __launch_bounds__(256, 1) score_sweep_kernel(const __grid_consta
     for (int o = 16; o > 0; o >>= 1) {
         n_nc += __shfl_xor_sync(0xffffffffu, n_nc, o);
         n_swept += __shfl_xor_sync(0xffffffffu, n_swept, o);
+        n_flagged += __shfl_xor_sync(0xffffffffu, n_flagged, o);
     }
     if (lane == 0) {
         atomicAdd(&A.counters[1], n_nc);
         atomicAdd(&A.counters[2], n_swept);
+        atomicAdd(&A.counters[3], n_staged);   // phase-1 survivors handed to phase 2
+        atomicAdd(&A.counters[4], n_flagged);  // of which carried a flag bit (known / tightened / forced)
     }
 }
 
@@ -292,17 +339,6 @@ int launch_score_sweep(annb_ctx *c, ScoreArgs &A)
 // hash32(pair, seed) <= thr -- thr = 0xffffffff enumerates every pair (exact mode, small
 // problems).  No anchor loop: ~a dozen issue slots per pair; phase 2 handles the sub-sample.
 // ---------------------------------------------------------------------------------------------
-
-__device__ __forceinline__ uint32_t hash_pair32(uint32_t i, uint32_t j, uint32_t seed)
-{
-    uint32_t h = (i * 0x9E3779B1u) ^ (j * 0x85EBCA77u) ^ seed;
-    h ^= h >> 15;
-    h *= 0x2C1B3C6Du;
-    h ^= h >> 12;
-    h *= 0x297A2D39u;
-    h ^= h >> 15;
-    return h;
-}
 
 __global__ void __launch_bounds__(256, 2) sample_sweep_kernel(const SampleArgs A)
 {

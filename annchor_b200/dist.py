@@ -108,6 +108,12 @@ class Comm:
     def barrier(self):
         self.dist.barrier(group=self.group)
 
+    def sync(self):
+        """Wait for the collectives enqueued on torch's streams: libannb works on its own stream."""
+        if self.device is not None:
+            import torch
+            torch.cuda.synchronize(self.device)
+
     # -- variable-length all-gather ----------------------------------------------------------
     def all_gather_var(self, columns):
         """columns: list of 1-D tensors of equal length n_r on this rank (different per rank).
@@ -134,6 +140,7 @@ def exchange(comm, local_columns, import_fn):
     """All-gather this rank's result columns and hand every OTHER rank's rows to import_fn(cols).
     Returns the number of rows imported."""
     gathered = comm.all_gather_var(local_columns)
+    comm.sync()  # the gathered columns are read next by kernels on the index's own stream
     imported = 0
     for r in range(comm.world):
         if r == comm.rank:

@@ -21,9 +21,10 @@ def _free_port():
 
 
 def _blobs(n, d, seed):
+    """The bench generator: 100-centre Gaussian blobs."""
     rng = np.random.default_rng(seed)
-    c = rng.normal(size=(20, d)) * (30.0 / np.sqrt(d))
-    return (c[rng.integers(0, 20, size=n)] + rng.normal(size=(n, d))).astype(np.float32)
+    c = rng.normal(size=(100, d)) * (30.0 / np.sqrt(d))
+    return (c[rng.integers(0, 100, size=n)] + rng.normal(size=(n, d))).astype(np.float32)
 
 
 def _fit(X, comm, device, **kw):
@@ -43,7 +44,7 @@ def _worker(rank, world, port, out_dir, n, kw):
     try:
         from annchor_b200.dist import Comm
         comm = Comm(device=torch.device("cuda", rank))
-        a = _fit(_blobs(n, 32, 5), comm, rank, **kw)
+        a = _fit(_blobs(n, 128, 42), comm, rank, **kw)
         np.savez(os.path.join(out_dir, "r%d.npz" % rank), idx=a.neighbor_graph[0], d=a.neighbor_graph[1],
                  A=a.A, evals=a.evals, n_tight=a.n_tightened, red=comm.n_reductions)
     finally:
@@ -60,7 +61,7 @@ def test_two_gpu_fit_equals_one_gpu(tmp_path, n, kw):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), n, kw), nprocs=world, join=True)
     r0, r1 = [np.load(os.path.join(tmp_path, "r%d.npz" % r)) for r in range(world)]
-    one = _fit(_blobs(n, 32, 5), None, 0, **kw)
+    one = _fit(_blobs(n, 128, 42), None, 0, **kw)
     for r in (r0, r1):
         assert np.array_equal(r["A"], one.A)
         assert int(r["evals"]) == one.evals
