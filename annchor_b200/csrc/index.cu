@@ -82,12 +82,24 @@ __global__ void set_slots_kernel(const int32_t *__restrict__ A, int nA, PointMet
 // utils.py:470-473), or (pass 2) the number of candidates under the relaxed thresholds
 __global__ void __launch_bounds__(256)
 locality_count_kernel(const PointMeta *__restrict__ meta, int64_t n, int loc_thresh, int pass,
-                      int32_t *__restrict__ out /* pass 1: [n][8]; pass 2: [n] */)
+                      int32_t *__restrict__ out /* pass 1: [n][8]; pass 2: [n] */, int rank, int world)
 {
     __shared__ uint64_t s_mask[1024];
     __shared__ int8_t s_t[1024];
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const bool live = i < n;
+    if ((int)(blockIdx.x % world) != rank) {
+        // another rank counts this block of rows: leave zeros for the sum all-reduce
+        if (live) {
+            if (pass == 1) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) out[i * 8 + q] = 0;
+            } else {
+                out[i] = 0;
+            }
+        }
+        return;
+    }
     const PointMeta mi = live ? meta[i] : PointMeta{0, 0, 127, -1, 0};
     int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int64_t j0 = 0; j0 < n; j0 += 1024) {
@@ -1239,7 +1251,11 @@ ANNB_API int annb_index_locality(annb_index *ix, int64_t *n_candidates, int64_t 
     ANNB_TRY(ix->t0.ensure((size_t)n * 8 * 4));
     const int grid = (int)((n + 255) / 256);
     ANNB_LAUNCH(locality_count_kernel, grid, 256, 0, c->stream, ix->meta.as<PointMeta>(), n, lt, 1,
-                ix->t0.as<int32_t>());
+                ix->t0.as<int32_t>(), ix->P.rank, ix->P.world);
+    if (ix->P.world > 1) {  // row blocks are split over the ranks
+        ANNB_CUDA(cudaStreamSynchronize(c->stream));
+        ANNB_TRY(ix->reduce(ix->t0.p, n * 8, ANNB_RED_I32 | ANNB_RED_DEVICE));
+    }
     std::vector<int32_t> h((size_t)n * 8);
     ANNB_CUDA(cudaMemcpyAsync(h.data(), ix->t0.p, h.size() * 4, cudaMemcpyDeviceToHost, c->stream));
     ANNB_CUDA(cudaStreamSynchronize(c->stream));
@@ -1268,7 +1284,11 @@ ANNB_API int annb_index_locality(annb_index *ix, int64_t *n_candidates, int64_t 
         ANNB_LAUNCH(set_loc_t_kernel, grid_for_n(c, n), 256, 0, c->stream, ix->meta.as<PointMeta>(),
                     ix->t1.as<int8_t>(), n);
         ANNB_LAUNCH(locality_count_kernel, grid, 256, 0, c->stream, ix->meta.as<PointMeta>(), n, lt, 2,
-                    ix->t0.as<int32_t>());
+                    ix->t0.as<int32_t>(), ix->P.rank, ix->P.world);
+        if (ix->P.world > 1) {
+            ANNB_CUDA(cudaStreamSynchronize(c->stream));
+            ANNB_TRY(ix->reduce(ix->t0.p, n, ANNB_RED_I32 | ANNB_RED_DEVICE));
+        }
         ANNB_CUDA(cudaMemcpyAsync(ncand.data(), ix->t0.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
         ANNB_CUDA(cudaStreamSynchronize(c->stream));
     } else {
@@ -2209,7 +2229,11 @@ ANNB_API int annb_index_sample_pool(annb_index *ix, uint64_t seed, int64_t max_p
     double frac = all ? 1.0 : 0.8 * (double)max_pool / (double)n_nc;
     for (int attempt = 0;; ++attempt) {
         ANNB_REQUIRE(attempt < 4, ANNB_ESTATE, "sampler pool did not fit");
-        A.thr = frac >= 1.0 ? 0xffffffffu : (uint32_t)(frac * 4294967295.0);
+        // sparse samples visit 1 tile in 64 and take pairs there at 64x the rate
+        const double tile_frac = frac < 1.0 / 8192.0 ? 1.0 / 64.0 : 1.0;
+        A.tile_thr = tile_frac >= 1.0 ? 0xffffffffu : (uint32_t)(tile_frac * 4294967295.0);
+        const double pfrac = frac / tile_frac;
+        A.thr = pfrac >= 1.0 ? 0xffffffffu : (uint32_t)(pfrac * 4294967295.0);
         const int64_t cap = all ? n_nc + 1024 : max_pool + max_pool / 4;
         ANNB_TRY(ix->pool_key.ensure((size_t)cap * 8));
         ANNB_TRY(ix->pool_dad.ensure((size_t)cap * 4));

@@ -46,7 +46,8 @@ struct ScoreArgs {
 
 struct SampleArgs {
     View V;
-    uint32_t thr;
+    uint32_t thr;       // a pair of a visited tile takes part iff hash_pair32(i, j, seed) <= thr
+    uint32_t tile_thr;  // a tile is visited iff hash of its index <= tile_thr (0xffffffff: every tile)
     uint32_t seed;
     uint64_t *out_key;
     float *out_dad;

@@ -358,6 +358,12 @@ __global__ void __launch_bounds__(256, 2) sample_sweep_kernel(const SampleArgs A
     const int64_t per = (nq + gridDim.x - 1) / gridDim.x;
     const int64_t m0 = (int64_t)blockIdx.x * per, m1 = min(nq, m0 + per);
     for (int64_t m = m0; m < m1; ++m) {
+        // two-stage uniform sub-sample: tiles first (point ids carry no geometry, so a tile is a random
+        // block of pairs), then pairs inside the visited tiles
+        const uint64_t tix = (uint64_t)(m * A.world + A.rank);
+        if (A.tile_thr != 0xffffffffu &&
+            hash_pair32((uint32_t)tix, (uint32_t)(tix >> 32), A.seed ^ 0x5bd1e995u) > A.tile_thr)
+            continue;
         int ti, tj;
         tile_from_index(m * A.world + A.rank, V.T, ti, tj);
         __syncthreads();

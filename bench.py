@@ -283,8 +283,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--n", type=int, default=None, help="override N (debug)")
-    ap.add_argument("--p-work", type=float, default=None)
+    ap.add_argument("--points", "--n", dest="n", type=int, default=None, help="override N (debug)")
+    ap.add_argument("--pwork", "--p-work", dest="p_work", type=float, default=None)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     w = dict(WORKLOAD)
