@@ -593,7 +593,7 @@ __global__ void tighten_work_kernel(const int64_t *__restrict__ kptr, const int6
 constexpr int TG_SLOTS = 8192;   // shared-memory table slots: 2048 buckets of 4 ids (+ 4 values), 64 KB -> 3 CTAs / SM
                                  // (a 4096-slot table at 6 CTAs / SM is 2.3x slower: hub rows then need several
                                  // chunks and every chunk re-streams all partner lists)
-constexpr int TG_CHUNK = 4096;   // entries of N(i) hashed at a time (load factor <= 0.5)
+constexpr int TG_CHUNK = 2048;   // entries of N(i) hashed at a time (<= 1 key per 3-slot bucket)
 
 // rows whose group streams more than `thr` list entries are queued first (longest-processing-time
 // first keeps the dynamic row scheduler's tail short)
@@ -609,7 +609,7 @@ __global__ void tighten_heavy_kernel(const unsigned long long *__restrict__ work
 // K2b.  Dynamic row scheduling (one atomic per row), bucketed shared-memory hash (4 ids per bucket,
 // one 128-bit probe, no divergent chains at load <= 0.25), partner lists streamed with the next
 // 128 entries in flight while the current ones are probed.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 tighten_grouped_kernel(View V, const int64_t *__restrict__ kptr, const int32_t *__restrict__ kids,
                        const float *__restrict__ kds, const int64_t *__restrict__ gptr,
                        const int32_t *__restrict__ gJ, const int32_t *__restrict__ gsrc,
@@ -654,24 +654,28 @@ tighten_grouped_kernel(View V, const int64_t *__restrict__ kptr, const int32_t *
         for (int c0 = 0; c0 == 0 || c0 < mi; c0 += TG_CHUNK) {
             const int mc = min(TG_CHUNK, mi - c0);
             const bool first = c0 == 0, last = c0 + TG_CHUNK >= mi;
-            int nb = 16;  // buckets: load <= 0.25 where the table allows it
-            while (nb < mc && nb < TG_SLOTS / 4) nb <<= 1;
+            // bucket = 4 words: 3 ids + an overflow flag (set when a key that hashes here had to be placed
+            // further on), so a probe walks on only when it must -- a full bucket alone does not force it.
+            // <= 0.5 keys per bucket where the table allows it (P[overflow] = 0.2 %), <= 1 otherwise.
+            int nb = 16;
+            while (nb < 2 * mc && nb < TG_SLOTS / 4) nb <<= 1;
             const uint32_t bmask = (uint32_t)nb - 1;
             __syncthreads();
-            for (int k = threadIdx.x; k < nb * 4; k += blockDim.x) h_id[k] = -1;
+            for (int k = threadIdx.x; k < nb * 4; k += blockDim.x) h_id[k] = (k & 3) == 3 ? 0 : -1;
             if (threadIdx.x == 0) s_next = 0;
             __syncthreads();
             for (int k = threadIdx.x; k < mc; k += blockDim.x) {
                 const int32_t id = kids[bi + c0 + k];
                 uint32_t bk = ((uint32_t)id * 2654435761u >> 7) & bmask;
-                for (;;) {  // slots of a bucket fill in order 0..3
+                for (;;) {
                     int sl = 0;
-                    for (; sl < 4; ++sl)
+                    for (; sl < 3; ++sl)
                         if (atomicCAS(&h_id[bk * 4 + sl], -1, id) == -1) break;
-                    if (sl < 4) {
+                    if (sl < 3) {
                         h_d[bk * 4 + sl] = kds[bi + c0 + k];
                         break;
                     }
+                    h_id[bk * 4 + 3] = 1;  // overflowed: probes for absent ids must walk on from here
                     bk = (bk + 1) & bmask;
                 }
             }
@@ -705,23 +709,25 @@ tighten_grouped_kernel(View V, const int64_t *__restrict__ kptr, const int32_t *
                     }
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
+                        // branch-free probe of the home bucket: one 128-bit load (3 ids + overflow flag),
+                        // one load of the candidate value; padding lanes carry id = -2 and match nothing
                         const int32_t id = idv[u];
                         uint32_t bk = ((uint32_t)id * 2654435761u >> 7) & bmask;
-                        bool more = id >= 0;
-                        while (more) {
-                            const int4 t = *reinterpret_cast<const int4 *>(h_id + bk * 4);
-                            const int sl = t.x == id ? 0 : (t.y == id ? 1 : (t.z == id ? 2 : (t.w == id ? 3 : -1)));
-                            if (sl >= 0) {
-                                const float x = h_d[bk * 4 + sl];
-                                lb = fmaxf(lb, fabsf(x - yv[u]));
-                                ub = fminf(ub, x + yv[u]);
-                                more = false;
-                            } else if (t.w == -1) {
-                                more = false;  // bucket never overflowed: the id is absent
-                            } else {
+                        int4 t = *reinterpret_cast<const int4 *>(h_id + bk * 4);
+                        float x = h_d[bk * 4 + (t.y == id ? 1 : (t.z == id ? 2 : 0))];
+                        bool hit = (t.x == id) | (t.y == id) | (t.z == id);
+                        bool more = !hit && t.w != 0 && id >= 0;  // rare: the home bucket overflowed
+                        while (__any_sync(0xffffffffu, more)) {
+                            if (more) {
                                 bk = (bk + 1) & bmask;
+                                t = *reinterpret_cast<const int4 *>(h_id + bk * 4);
+                                x = h_d[bk * 4 + (t.y == id ? 1 : (t.z == id ? 2 : 0))];
+                                hit = (t.x == id) | (t.y == id) | (t.z == id);
+                                more = !hit && t.w != 0;
                             }
                         }
+                        lb = fmaxf(lb, hit ? fabsf(x - yv[u]) : 0.0f);
+                        ub = fminf(ub, hit ? x + yv[u] : INFINITY);
                     }
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
@@ -2136,7 +2142,7 @@ ANNB_API int annb_index_update_bounds(annb_index *ix, int64_t *n_updated)
                 heavy_thr, ix->theavy.as<int32_t>(), ix->counters.as<unsigned long long>() + 4);
     ANNB_CUDA(cudaFuncSetAttribute(tighten_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    TG_SLOTS * 8));
-    ANNB_LAUNCH(tighten_grouped_kernel, tg_grid, 256, TG_SLOTS * 8, c->stream, V, ix->kptr.as<int64_t>(),
+    ANNB_LAUNCH(tighten_grouped_kernel, tg_grid, 512, TG_SLOTS * 8, c->stream, V, ix->kptr.as<int64_t>(),
                 ix->kids.as<int32_t>(), ix->kds.as<float>(), ix->gptr.as<int64_t>(), ix->gJ.as<int32_t>(),
                 ix->gsrc.as<int32_t>(), ix->row_order.as<int32_t>(), ix->theavy.as<int32_t>(),
                 ix->counters.as<unsigned long long>() + 4, ix->twork.as<unsigned long long>(), heavy_thr,
