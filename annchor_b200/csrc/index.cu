@@ -954,6 +954,32 @@ __global__ void max_f32_kernel(const float *__restrict__ x, int64_t n, unsigned 
     if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));  // non-negative floats order as uints
 }
 
+// a rank's partial per-row lists as records for the cross-rank merge: k1 values (flagged computed:
+// they only feed the thresh list), then the k2 not-computed (value, id) pairs
+__global__ void pack_partial_lists_kernel(const float *__restrict__ l1last, const float *__restrict__ l2v,
+                                          const int32_t *__restrict__ l2i, const float *__restrict__ l1all,
+                                          int64_t n, int k1, int k2, uint2 *__restrict__ rec,
+                                          int32_t *__restrict__ cnt)
+{
+    const int K = k1 + k2;
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n * K;
+         q += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = q / K;
+        const int k = (int)(q % K);
+        uint2 r;
+        if (k < k1) {
+            r = make_uint2(__float_as_uint(l1all[row * k1 + k]), 0x80000000u);
+        } else {
+            const int32_t id = l2i[row * k2 + (k - k1)];
+            const float v = id < 0 ? INFINITY : l2v[row * k2 + (k - k1)];
+            r = make_uint2(__float_as_uint(v), (uint32_t)(id < 0 ? 0 : id) | 0x40000000u);  // L2-only
+        }
+        rec[q] = r;
+        if (k == 0) cnt[row] = K;
+    }
+    (void)l1last;
+}
+
 }  // namespace annb
 
 // ---------------------------------------------------------------------------------------------
@@ -1002,6 +1028,8 @@ struct annb_index {
     DevBuf t0, t1, t2, t3, t4, t5, t6;
     // CSR of known pairs
     DevBuf kptr, kids, kds, kdeg, gptr, gJ, gsrc, row_order, twork, theavy;
+    // two-stage thresholds
+    DevBuf tcut1, tcut2, trec, tcnt, tgat, tgcnt, l1part;
     int64_t csr_entries = 0;
     // stats
     int64_t pairs_swept = 0, sweeps = 0, n_tight = 0, n_known = 0;
@@ -1182,7 +1210,8 @@ ANNB_API int annb_index_destroy(annb_index *ix)
                      &ix->counters, &ix->emit_key, &ix->emit_lvl, &ix->sel_i, &ix->sel_j, &ix->nxt_i,
                      &ix->nxt_j, &ix->tiehist, &ix->tiekeys, &ix->pool_key, &ix->pool_dad, &ix->t0,
                      &ix->t1, &ix->t2, &ix->t3, &ix->t4, &ix->t5, &ix->t6, &ix->kptr, &ix->kids,
-                     &ix->kds, &ix->kdeg, &ix->gptr, &ix->gJ, &ix->gsrc, &ix->row_order, &ix->twork, &ix->theavy};
+                     &ix->kds, &ix->kdeg, &ix->gptr, &ix->gJ, &ix->gsrc, &ix->row_order, &ix->twork, &ix->theavy,
+                     &ix->tcut1, &ix->tcut2, &ix->trec, &ix->tcnt, &ix->tgat, &ix->tgcnt, &ix->l1part};
     for (DevBuf *b : all) b->release();
     delete ix;
     return ANNB_OK;
@@ -1471,7 +1500,9 @@ ANNB_API int annb_index_set_model(annb_index *ix, const double *bins, const doub
     return ANNB_OK;
 }
 
-static int run_thresh(annb_index *ix, int k2)
+// the row sweep (both triangles): all rows (split over the ranks, results summed), a column subset
+// of all rows (pre-pass of the two-stage scheme), or an explicit list of row blocks on every rank
+static int run_thresh_rows(annb_index *ix, int k2, int col_stride, float *cut2, const int32_t *rb_list, int n_rb)
 {
     annb_ctx *c = ix->ctx;
     ThreshArgs A;
@@ -1480,41 +1511,140 @@ static int run_thresh(annb_index *ix, int k2)
     A.k1 = ix->P.n_neighbors + 1;
     A.k2 = k2;
     A.thresh = ix->thresh.as<float>();
-    A.l2val = nullptr;
-    A.l2id = nullptr;
-    if (k2 > 0) {
-        ANNB_TRY(ix->l2val.ensure((size_t)ix->n * k2 * 4));
-        ANNB_TRY(ix->l2id.ensure((size_t)ix->n * k2 * 4));
-        A.l2val = ix->l2val.as<float>();
-        A.l2id = ix->l2id.as<int32_t>();
-    }
-    A.rank = ix->P.rank;
-    A.world = ix->P.world;
-    if (ix->P.world > 1) {  // rows of other ranks stay 0 so that a sum all-reduce assembles the result
+    A.l2val = k2 > 0 ? ix->l2val.as<float>() : nullptr;
+    A.l2id = k2 > 0 ? ix->l2id.as<int32_t>() : nullptr;
+    A.col_stride = col_stride;
+    A.col_phase = 0;
+    A.cut2 = cut2;
+    A.rb_list = rb_list;
+    A.n_rb = n_rb;
+    const bool split = ix->P.world > 1 && rb_list == nullptr;
+    A.rank = split ? ix->P.rank : 0;
+    A.world = split ? ix->P.world : 1;
+    if (split) {  // rows of other ranks stay 0 so that a sum all-reduce assembles the result
         ANNB_CUDA(cudaMemsetAsync(ix->thresh.p, 0, (size_t)ix->npad * 4, c->stream));
-        if (k2 > 0) {
+        if (cut2) ANNB_CUDA(cudaMemsetAsync(cut2, 0, (size_t)ix->npad * 4, c->stream));
+        if (k2 > 0 && col_stride == 1) {
             ANNB_CUDA(cudaMemsetAsync(ix->l2val.p, 0, (size_t)ix->n * k2 * 4, c->stream));
             ANNB_CUDA(cudaMemsetAsync(ix->l2id.p, 0, (size_t)ix->n * k2 * 4, c->stream));
         }
     }
-    ANNB_CUDA(cudaEventRecord(c->ev0, c->stream));
     ANNB_TRY(launch_thresh_sweep(c, A));
-    ANNB_CUDA(cudaEventRecord(c->ev1, c->stream));
-    ANNB_CUDA(cudaEventSynchronize(c->ev1));
-    float ms = 0;
-    ANNB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-    ix->pairs_swept += ix->n * (ix->n - 1) / ix->P.world;
+    const int64_t rows = rb_list ? (int64_t)n_rb * TILE : ix->n / A.world;
+    ix->pairs_swept += rows * (ix->n / col_stride);
     ix->sweeps += 1;
-    if (ix->P.world > 1) {
+    if (split) {
         // every row block was computed by exactly one rank (the others hold zeros): a sum
         // all-reduce of the device buffers assembles the full vectors on every rank
         ANNB_CUDA(cudaStreamSynchronize(c->stream));
         ANNB_TRY(ix->reduce(ix->thresh.p, ix->npad, ANNB_RED_F32 | ANNB_RED_DEVICE));
-        if (k2 > 0) {
+        if (cut2) ANNB_TRY(ix->reduce(cut2, ix->npad, ANNB_RED_F32 | ANNB_RED_DEVICE));
+        if (k2 > 0 && col_stride == 1) {
             ANNB_TRY(ix->reduce(ix->l2val.p, ix->n * k2, ANNB_RED_F32 | ANNB_RED_DEVICE));
             ANNB_TRY(ix->reduce(ix->l2id.p, ix->n * k2, ANNB_RED_I32 | ANNB_RED_DEVICE));
         }
     }
+    return ANNB_OK;
+}
+
+// thresh (annchor.py:399-404) and, with k2 > 0, the guarantee_nmin lists.  Large metric problems
+// use the two-stage scheme (sweep_thresh.cu): column-subset pre-pass -> upper bounds, one visit per
+// pair appending records to both endpoints, per-row selection; everything else the row sweep.
+static int run_thresh(annb_index *ix, int k2)
+{
+    annb_ctx *c = ix->ctx;
+    const int64_t n = ix->n;
+    const int k1 = ix->P.n_neighbors + 1;
+    if (k2 > 0) {
+        ANNB_TRY(ix->l2val.ensure((size_t)n * k2 * 4));
+        ANNB_TRY(ix->l2id.ensure((size_t)n * k2 * 4));
+    }
+    ANNB_CUDA(cudaEventRecord(c->ev0, c->stream));
+    const bool force_rows = getenv("ANNB_THRESH_ROWS") != nullptr;  // test knob: row sweep only
+    const int S = 8;  // pre-pass visits every S-th column tile
+    const bool two_stage = ix->P.is_metric && ix->T >= 16 * S && n < (1 << 30) && !force_rows;
+    if (!two_stage) {
+        ANNB_TRY(run_thresh_rows(ix, k2, 1, nullptr, nullptr, 0));
+    } else {
+        // 1. upper bounds from a column subset
+        ANNB_TRY(ix->tcut1.ensure((size_t)ix->npad * 4));
+        float *cut2 = nullptr;
+        if (k2 > 0) {
+            ANNB_TRY(ix->tcut2.ensure((size_t)ix->npad * 4));
+            cut2 = ix->tcut2.as<float>();
+        }
+        ANNB_TRY(run_thresh_rows(ix, k2, S, cut2, nullptr, 0));
+        ANNB_CUDA(cudaMemcpyAsync(ix->tcut1.p, ix->thresh.p, (size_t)ix->npad * 4, cudaMemcpyDeviceToDevice,
+                                  c->stream));
+        // 2. one visit per pair, records to both endpoints
+        const int R = (2 * S * (k1 + k2) + 31) / 32 * 32;
+        ANNB_TRY(ix->trec.ensure((size_t)n * R * 8));
+        ANNB_TRY(ix->tcnt.ensure((size_t)n * 4));
+        ANNB_CUDA(cudaMemsetAsync(ix->tcnt.p, 0, (size_t)n * 4, c->stream));
+        ThreshPairArgs P;
+        P.V = ix->view();
+        P.M = ix->model;
+        P.cut1 = ix->tcut1.as<float>();
+        P.cut2 = cut2;
+        P.rec = ix->trec.as<uint2>();
+        P.cnt = ix->tcnt.as<int32_t>();
+        P.R = R;
+        P.rank = ix->P.rank;
+        P.world = ix->P.world;
+        ANNB_TRY(launch_thresh_pairs(c, P));
+        ix->pairs_swept += n * (n - 1) / 2 / ix->P.world;
+        ix->sweeps += 1;
+        // 3. per-row selection (per-rank partial lists when the tiles are split)
+        if (ix->P.world == 1) {
+            ANNB_TRY(launch_thresh_select(c, P.rec, P.cnt, R, n, k1, k2, 1, ix->thresh.as<float>(), nullptr,
+                                          k2 > 0 ? ix->l2val.as<float>() : nullptr,
+                                          k2 > 0 ? ix->l2id.as<int32_t>() : nullptr));
+        } else {
+            // partial lists of all ranks side by side ([world][n][k] records, zero elsewhere, summed),
+            // then the same selection over the world lists of each row
+            const int W = ix->P.world, K = k1 + k2;
+            ANNB_TRY(ix->tgat.ensure((size_t)W * n * K * 8));
+            ANNB_TRY(ix->tgcnt.ensure((size_t)W * n * 4));
+            ANNB_TRY(ix->t0.ensure((size_t)n * 4));
+            ANNB_TRY(ix->t1.ensure((size_t)n * std::max(k2, 1) * 4));
+            ANNB_TRY(ix->t2.ensure((size_t)n * std::max(k2, 1) * 4));
+            ANNB_TRY(ix->l1part.ensure((size_t)n * k1 * 4));
+            ANNB_TRY(launch_thresh_select(c, P.rec, P.cnt, R, n, k1, k2, 1, ix->t0.as<float>(), ix->l1part.as<float>(),
+                                          ix->t1.as<float>(), ix->t2.as<int32_t>()));
+            ANNB_CUDA(cudaMemsetAsync(ix->tgat.p, 0, (size_t)W * n * K * 8, c->stream));
+            ANNB_CUDA(cudaMemsetAsync(ix->tgcnt.p, 0, (size_t)W * n * 4, c->stream));
+            ANNB_LAUNCH(pack_partial_lists_kernel, grid_for_n(c, n * K), 256, 0, c->stream, ix->t0.as<float>(),
+                        ix->t1.as<float>(), ix->t2.as<int32_t>(), ix->l1part.as<float>(), n, k1, k2,
+                        ix->tgat.as<uint2>() + (size_t)ix->P.rank * n * K,
+                        ix->tgcnt.as<int32_t>() + (size_t)ix->P.rank * n);
+            ANNB_CUDA(cudaStreamSynchronize(c->stream));
+            ANNB_TRY(ix->reduce(ix->tgat.p, (int64_t)W * n * K * 2, ANNB_RED_I32 | ANNB_RED_DEVICE));
+            ANNB_TRY(ix->reduce(ix->tgcnt.p, (int64_t)W * n, ANNB_RED_I32 | ANNB_RED_DEVICE));
+            ANNB_TRY(launch_thresh_select(c, ix->tgat.as<uint2>(), ix->tgcnt.as<int32_t>(), K, n, k1, k2, W,
+                                          ix->thresh.as<float>(), nullptr, k2 > 0 ? ix->l2val.as<float>() : nullptr,
+                                          k2 > 0 ? ix->l2id.as<int32_t>() : nullptr));
+        }
+        // 4. rows whose record list overflowed: recompute their row blocks with the row sweep
+        std::vector<int32_t> cnt_h(n);
+        ANNB_CUDA(cudaMemcpyAsync(cnt_h.data(), ix->tcnt.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+        ANNB_CUDA(cudaStreamSynchronize(c->stream));
+        std::vector<uint32_t> bad((size_t)ix->T, 0);
+        for (int64_t i = 0; i < n; ++i)
+            if (cnt_h[i] > R) bad[i / TILE] = 1;
+        ANNB_TRY(ix->reduce(bad.data(), (int64_t)bad.size(), ANNB_RED_I32));  // same list on every rank
+        std::vector<int32_t> rbs;
+        for (int t = 0; t < ix->T; ++t)
+            if (bad[t]) rbs.push_back(t);
+        if (g_trace)
+            fprintf(stderr, "[annb-trace]   two-stage thresh: R %d, %zu of %d row blocks overflowed\n", R, rbs.size(), ix->T);
+        if (!rbs.empty()) {
+            ANNB_TRY(ix->t3.ensure(rbs.size() * 4));
+            ANNB_CUDA(cudaMemcpyAsync(ix->t3.p, rbs.data(), rbs.size() * 4, cudaMemcpyHostToDevice, c->stream));
+            ANNB_TRY(run_thresh_rows(ix, k2, 1, nullptr, ix->t3.as<int32_t>(), (int)rbs.size()));
+        }
+    }
+    ANNB_CUDA(cudaEventRecord(c->ev1, c->stream));
+    ANNB_CUDA(cudaEventSynchronize(c->ev1));
     ix->have_thresh = true;
     return ANNB_OK;
 }

@@ -256,6 +256,20 @@ __device__ __forceinline__ bool flag_bit(const uint32_t *sB, int gi, int gj)
     return (sB[r * 4 + (c >> 5)] >> (c & 31)) & 1u;
 }
 
+// (ti, tj), ti <= tj, of the t-th upper-triangular tile (inverse of tile_index)
+__device__ __forceinline__ void tile_from_index(int64_t t, int T, int &ti, int &tj)
+{
+    // invert tile_index(): largest ti with ti*T - ti*(ti-1)/2 <= t
+    const double b = 2.0 * T + 1.0;
+    int r = (int)((b - sqrt(b * b - 8.0 * (double)t)) * 0.5);
+    if (r < 0) r = 0;
+    if (r > T - 1) r = T - 1;
+    while (r > 0 && tile_index(r, r, T) > t) --r;
+    while (r + 1 < T && tile_index(r + 1, r + 1, T) <= t) ++r;
+    ti = r;
+    tj = r + (int)(t - tile_index(r, r, T));
+}
+
 struct PairVal {
     float v;        // RefineApprox value (exact if computed, clipped prediction otherwise, -1 if forced)
     float dad;      // 2 * double anchor distance

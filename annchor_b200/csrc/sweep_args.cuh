@@ -14,6 +14,26 @@ struct ThreshArgs {
     int32_t *l2id;     // [n * k2]
     int rank, world;
     int qcap;          // set by the launcher: per-warp survivor queue capacity
+    int col_stride;    // visit the column tiles tc = col_phase, col_phase + col_stride, ... (1: all)
+    int col_phase;
+    float *cut2;       // [npad] out (k2 > 0): k2-th smallest not-computed value of the visited columns
+    const int32_t *rb_list;  // explicit row blocks to process (nullptr: all, split over the ranks)
+    int n_rb;
+};
+
+// upper-triangle pass of the two-stage threshold computation: every pair that can be among the
+// smallest values of either endpoint (value <= that endpoint's cut from the column-subset pre-pass)
+// is appended to the endpoint's record list
+struct ThreshPairArgs {
+    View V;
+    Model M;
+    const float *cut1;   // [npad] k1-th smallest RefineApprox over a column subset (upper bound of thresh)
+    const float *cut2;   // [npad] same for the not-computed list (nullptr: no second list)
+    uint2 *rec;          // [n][R] records (value bits, other endpoint | computed << 31)
+    int32_t *cnt;        // [n] records appended (may exceed R: the row is then recomputed the long way)
+    int R;
+    int rank, world;
+    int qcap;
 };
 
 struct ScoreArgs {
@@ -57,6 +77,9 @@ struct SampleArgs {
 };
 
 int launch_thresh_sweep(annb_ctx *c, ThreshArgs &A);
+int launch_thresh_pairs(annb_ctx *c, ThreshPairArgs &A);
+int launch_thresh_select(annb_ctx *c, const uint2 *rec, const int32_t *cnt, int R, int64_t n, int k1, int k2,
+                         int n_src, float *thresh, float *l1out, float *l2val, int32_t *l2id);
 int launch_score_sweep(annb_ctx *c, ScoreArgs &A);
 int launch_sample_sweep(annb_ctx *c, const SampleArgs &A);
 

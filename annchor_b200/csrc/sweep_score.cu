@@ -19,19 +19,6 @@ namespace annb {
 constexpr int EMIT_CAP = 256;  // per-warp emission staging (entries)
 
 
-__device__ __forceinline__ void tile_from_index(int64_t t, int T, int &ti, int &tj)
-{
-    // invert tile_index(): largest ti with ti*T - ti*(ti-1)/2 <= t
-    const double b = 2.0 * T + 1.0;
-    int r = (int)((b - sqrt(b * b - 8.0 * (double)t)) * 0.5);
-    if (r < 0) r = 0;
-    if (r > T - 1) r = T - 1;
-    while (r > 0 && tile_index(r, r, T) > t) --r;
-    while (r + 1 < T && tile_index(r + 1, r + 1, T) <= t) ++r;
-    ti = r;
-    tj = r + (int)(t - tile_index(r, r, T));
-}
-
 // flush a warp's staged emissions with ONE global atomic
 __device__ __forceinline__ void flush_emit(const ScoreArgs &A, uint64_t *ek, uint16_t *el, int &en, int lane)
 {

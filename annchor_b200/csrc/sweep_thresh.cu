@@ -11,6 +11,8 @@
 // synchronisation, no global atomics, and the result is deterministic).  A pair is handed to
 // phase 2 only when its lower bound beats the row's current k-th value, so after the first few
 // column tiles almost nothing survives phase 1.
+#include <algorithm>
+
 #include "sweep.cuh"
 #include "sweep_args.cuh"
 
@@ -86,7 +88,9 @@ __global__ void __launch_bounds__(256, 1) thresh_sweep_kernel(const __grid_const
 
     build_tile_model(M, tm);
     if (lane == 0) *qcnt = 0;
-    for (int rb = blockIdx.x * A.world + A.rank; rb < V.T; rb += gridDim.x * A.world) {
+    const int n_rb = A.rb_list ? A.n_rb : V.T;
+    for (int rq = blockIdx.x * A.world + A.rank; rq < n_rb; rq += gridDim.x * A.world) {
+        const int rb = A.rb_list ? A.rb_list[rq] : rq;
         // ---- init row state, stage the row tile ----
         for (int k = tid; k < TILE * A.k1; k += blockDim.x) L1[k] = INFINITY;
         if (L2ON)
@@ -100,19 +104,22 @@ __global__ void __launch_bounds__(256, 1) thresh_sweep_kernel(const __grid_const
             cut[tid] = INFINITY;
         }
         load_point_tile(V, rb, sDi, sMi);
-        load_point_tile(V, 0, sDj0, sMj0);
-        load_bitmap_tile(V, rb, 0, sB0);
+        if (A.col_phase < V.T) {
+            load_point_tile(V, A.col_phase, sDj0, sMj0);
+            load_bitmap_tile(V, rb, A.col_phase, sB0);
+        }
         cp_async_commit();
 
-        for (int tc = 0; tc < V.T; ++tc) {
-            const float *sDj = (tc & 1) ? sDj1 : sDj0;
-            const PointMeta *sMj = (tc & 1) ? sMj1 : sMj0;
-            const uint32_t *sBraw = (tc & 1) ? sB1 : sB0;
+        int par = 0;  // buffer parity
+        for (int tc = A.col_phase; tc < V.T; tc += A.col_stride, par ^= 1) {
+            const float *sDj = par ? sDj1 : sDj0;
+            const PointMeta *sMj = par ? sMj1 : sMj0;
+            const uint32_t *sBraw = par ? sB1 : sB0;
             cp_async_wait_all();
             __syncthreads();
-            if (tc + 1 < V.T) {  // prefetch the next column tile into the other buffer
-                load_point_tile(V, tc + 1, (tc & 1) ? sDj0 : sDj1, (tc & 1) ? sMj0 : sMj1);
-                load_bitmap_tile(V, rb, tc + 1, (tc & 1) ? sB0 : sB1);
+            if (tc + A.col_stride < V.T) {  // prefetch the next column tile into the other buffer
+                load_point_tile(V, tc + A.col_stride, par ? sDj0 : sDj1, par ? sMj0 : sMj1);
+                load_bitmap_tile(V, rb, tc + A.col_stride, par ? sB0 : sB1);
                 cp_async_commit();
             }
             // flag bits are stored once per pair, in the tile of (lo, hi): re-orient them so that
@@ -222,6 +229,7 @@ __global__ void __launch_bounds__(256, 1) thresh_sweep_kernel(const __grid_const
         // ---- write the row block's results ----
         __syncthreads();
         if (tid < TILE) A.thresh[rb * TILE + tid] = L1[tid * A.k1 + (A.k1 - 1)];
+        if (L2ON && A.cut2 && tid < TILE) A.cut2[rb * TILE + tid] = L2v[tid * A.k2 + (A.k2 - 1)];
         if (L2ON) {
             for (int k = tid; k < TILE * A.k2; k += blockDim.x) {
                 const int gi = rb * TILE + k / A.k2;
@@ -255,8 +263,10 @@ int launch_thresh_sweep(annb_ctx *c, ThreshArgs &A)
     if (qcap > QCAP) qcap = QCAP;
     A.qcap = qcap;
     const size_t smem = base + (size_t)8 * qcap * sizeof(Survivor);
-    const int rows_here = (A.V.T - A.rank + A.world - 1) / A.world;
+    const int n_rb = A.rb_list ? A.n_rb : A.V.T;
+    const int rows_here = (n_rb - A.rank + A.world - 1) / A.world;
     const int grid = rows_here < 1 ? 1 : rows_here;
+    if (A.col_stride < 1) A.col_stride = 1;
     if (A.k2 > 0) {
         ANNB_CUDA(cudaFuncSetAttribute(thresh_sweep_kernel<true>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -266,6 +276,263 @@ int launch_thresh_sweep(annb_ctx *c, ThreshArgs &A)
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ANNB_LAUNCH(thresh_sweep_kernel<false>, grid, 256, smem, c->stream, A);
     }
+    return ANNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Two-stage thresholds.  The row sweep above evaluates every pair twice (once per endpoint).  For
+// metrics, a pre-pass of it over every S-th column tile gives, per point, the k-th smallest value of
+// a SUBSET of its pairs -- an upper bound of its threshold.  The pass below then visits each pair
+// ONCE (upper-triangular tiles, like the scoring sweep) and appends (value, other endpoint) to the
+// record list of either endpoint whose bound it does not exceed; thresh_select_kernel finishes per
+// row.  Rows whose record list overflowed are recomputed by the row sweep (launch with rb_list).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 1) thresh_pairs_kernel(const __grid_constant__ ThreshPairArgs A)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const View &V = A.V;
+    const Model &M = A.M;
+    const int na = V.na;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ty = tid >> 4, tx = tid & 15;
+    float *sD0i = reinterpret_cast<float *>(smem);
+    float *sD0j = sD0i + na * SROW;
+    float *sD1i = sD0j + na * SROW;
+    float *sD1j = sD1i + na * SROW;
+    PointMeta *sM0i = reinterpret_cast<PointMeta *>(sD1j + na * SROW);
+    PointMeta *sM0j = sM0i + TILE;
+    PointMeta *sM1i = sM0j + TILE;
+    PointMeta *sM1j = sM1i + TILE;
+    uint32_t *sB0 = reinterpret_cast<uint32_t *>(sM1j + TILE);
+    uint32_t *sB1 = sB0 + BITMAP_WORDS;
+    Survivor *queue = reinterpret_cast<Survivor *>(sB1 + BITMAP_WORDS) + warp * A.qcap;
+    float *c1I = reinterpret_cast<float *>(reinterpret_cast<Survivor *>(sB1 + BITMAP_WORDS) + 8 * A.qcap);
+    float *c1J = c1I + 2 * TILE;  // [2][128] each: cut1 / cut2 of the row and column tiles (double-buffered)
+    float *c2I = c1J + 2 * TILE;
+    float *c2J = c2I + 2 * TILE;
+    TileModel *tm = reinterpret_cast<TileModel *>(c2J + 2 * TILE);
+    int *qcnt = reinterpret_cast<int *>(tm + 1) + warp;
+    const bool l2on = A.cut2 != nullptr;
+    build_tile_model(M, tm);
+    if (lane == 0) *qcnt = 0;
+
+    const int64_t NT = (int64_t)V.T * (V.T + 1) / 2;
+    const int64_t nq = (NT - A.rank + A.world - 1) / A.world;
+    const int64_t per = (nq + gridDim.x - 1) / gridDim.x;
+    const int64_t m0 = (int64_t)blockIdx.x * per, m1 = min(nq, m0 + per);
+    auto stage_cuts = [&](int ti, int tj, int b) {
+        if (tid < TILE) {
+            const int64_t gi = (int64_t)ti * TILE + tid, gj = (int64_t)tj * TILE + tid;
+            c1I[b * TILE + tid] = A.cut1[gi];
+            c1J[b * TILE + tid] = A.cut1[gj];
+            c2I[b * TILE + tid] = l2on ? A.cut2[gi] : -INFINITY;
+            c2J[b * TILE + tid] = l2on ? A.cut2[gj] : -INFINITY;
+        }
+    };
+    if (m0 < m1) {
+        int ti, tj;
+        tile_from_index(m0 * A.world + A.rank, V.T, ti, tj);
+        load_point_tile(V, ti, sD0i, sM0i);
+        load_point_tile(V, tj, sD0j, sM0j);
+        load_bitmap_tile(V, ti, tj, sB0);
+        stage_cuts(ti, tj, 0);
+        cp_async_commit();
+    }
+    for (int64_t m = m0; m < m1; ++m) {
+        const int buf = (int)((m - m0) & 1);
+        int ti, tj;
+        tile_from_index(m * A.world + A.rank, V.T, ti, tj);
+        cp_async_wait_all();
+        __syncthreads();
+        if (m + 1 < m1) {
+            int ni, nj;
+            tile_from_index((m + 1) * A.world + A.rank, V.T, ni, nj);
+            load_point_tile(V, ni, buf ? sD0i : sD1i, buf ? sM0i : sM1i);
+            load_point_tile(V, nj, buf ? sD0j : sD1j, buf ? sM0j : sM1j);
+            load_bitmap_tile(V, ni, nj, buf ? sB0 : sB1);
+            stage_cuts(ni, nj, buf ^ 1);
+            cp_async_commit();
+        }
+        const float *sDi = buf ? sD1i : sD0i, *sDj = buf ? sD1j : sD0j;
+        const PointMeta *sMi = buf ? sM1i : sM0i, *sMj = buf ? sM1j : sM0j;
+        const uint32_t *bm = buf ? sB1 : sB0;
+        const float *k1I = c1I + buf * TILE, *k1J = c1J + buf * TILE;
+        const float *k2I = c2I + buf * TILE, *k2J = c2J + buf * TILE;
+        float cj[8];
+        int cAj[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const int lj = micro_off(tx, c);
+            cj[c] = fmaxf(k1J[lj], k2J[lj]);
+            cAj[c] = sMj[lj].cA * SROW;
+        }
+        float lb[4][8], ub[4][8];
+#pragma unroll 1
+        for (int pass = 0; pass < 10; ++pass) {  // 2 x (4 row steps + 1 drain-only step)
+            const int h = pass >= 5 ? 1 : 0, step = pass - 5 * h;
+            const int row0 = h * 64 + ty * 4;
+            if (step == 0) {
+                bounds_half(sDi, sDj, na, row0, tx, lb, ub);
+                if (ti == tj) mask_diagonal<true>(row0, tx, lb, ub);
+            }
+            auto row_step = [&](const float (&lbr)[8], const float (&ubr)[8], int r) {
+                const int li = row0 + r;
+                const float ci = fmaxf(k1I[li], k2I[li]);
+                const float *dj_row = sDj + sMi[li].cA * SROW;
+                uint32_t w0, w1;
+                flag_words(bm, li, tx, w0, w1);
+                uint32_t km = (w0 & 0xfu) | ((w1 & 0xfu) << 4);  // flagged pairs always go to phase 2
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float s2 = sDi[cAj[c] + li] + dj_row[micro_off(tx, c)];
+                    int bin;
+                    const float y = predict_clip2(tm, M, lbr[c], ubr[c], s2, bin);
+                    km |= (y <= fmaxf(ci, cj[c])) ? (1u << c) : 0u;
+                }
+                stage_row(queue, qcnt, lbr, ubr, km, li, tx);
+            };
+            switch (step) {
+                case 0: row_step(lb[0], ub[0], 0); break;
+                case 1: row_step(lb[1], ub[1], 1); break;
+                case 2: row_step(lb[2], ub[2], 2); break;
+                case 3: row_step(lb[3], ub[3], 3); break;
+                default: break;
+            }
+            __syncwarp();
+            const int qn = *reinterpret_cast<volatile int *>(qcnt);
+            if (pass < 9 && qn <= A.qcap - QROW) continue;
+            for (int e0 = 0; e0 < qn; e0 += 32) {
+                const int e = e0 + lane;
+                if (e < qn) {
+                    const Survivor s = queue[e];
+                    const int li2 = s.ids & 0xff, lj = s.ids >> 8;
+                    const int gi = ti * TILE + li2, gj = tj * TILE + lj;
+                    if (gj < V.n && s.lb < INFINITY) {
+                        const PointMeta pi = sMi[li2], pj = sMj[lj];
+                        if (is_candidate(pi, pj)) {
+                            const PairVal pv = pair_value(V, tm, M, s.lb, s.ub, li2, lj, gi, gj, pi, pj, sDi, sDj,
+                                                          flag_bit(bm, gi, gj));
+                            const float v = pv.v;
+                            const uint32_t cflag = pv.computed ? 0x80000000u : 0u;
+                            if (v <= k1I[li2] || (!pv.computed && v <= k2I[li2])) {
+                                const int pos = atomicAdd(&A.cnt[gi], 1);
+                                if (pos < A.R) A.rec[(int64_t)gi * A.R + pos] = make_uint2(__float_as_uint(v), (uint32_t)gj | cflag);
+                            }
+                            if (v <= k1J[lj] || (!pv.computed && v <= k2J[lj])) {
+                                const int pos = atomicAdd(&A.cnt[gj], 1);
+                                if (pos < A.R) A.rec[(int64_t)gj * A.R + pos] = make_uint2(__float_as_uint(v), (uint32_t)gi | cflag);
+                            }
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) *qcnt = 0;
+            __syncwarp();
+        }
+    }
+}
+
+int launch_thresh_pairs(annb_ctx *c, ThreshPairArgs &A)
+{
+    const size_t lim = 227 * 1024;
+    const size_t base = (size_t)4 * A.V.na * SROW * 4 + 4 * TILE * sizeof(PointMeta) + 2 * BITMAP_WORDS * 4 +
+                        8 * TILE * 4 + sizeof(TileModel) + 8 * 4 + 64;
+    ANNB_REQUIRE(base + (size_t)8 * (QROW + 32) * sizeof(Survivor) <= lim, ANNB_ERANGE,
+                 "threshold pair sweep needs %zu bytes of shared memory (n_anchors=%d)",
+                 base + (size_t)8 * (QROW + 32) * sizeof(Survivor), A.V.na);
+    int qcap = (int)((lim - base) / (8 * sizeof(Survivor))) / 32 * 32;
+    if (qcap > QCAP) qcap = QCAP;
+    A.qcap = qcap;
+    const size_t smem = base + (size_t)8 * qcap * sizeof(Survivor);
+    ANNB_CUDA(cudaFuncSetAttribute(thresh_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t NT = (int64_t)A.V.T * (A.V.T + 1) / 2;
+    const int64_t nq = (NT - A.rank + A.world - 1) / A.world;
+    int grid = c->num_sms;
+    if (nq < grid) grid = nq < 1 ? 1 : (int)nq;
+    ANNB_LAUNCH(thresh_pairs_kernel, grid, 256, smem, c->stream, A);
+    return ANNB_OK;
+}
+
+// Per row: the k1 smallest values and the k2 smallest not-computed (value, id) pairs of its records
+// (n_src record lists of R slots per row: n_src = 1 after the pair sweep; world when merging the
+// per-rank partial lists).  One warp per row, lists in shared memory, order-independent result.
+__global__ void __launch_bounds__(256)
+thresh_select_kernel(const uint2 *__restrict__ rec, const int32_t *__restrict__ cnt, int R, int64_t n, int k1,
+                     int k2, int n_src, float *__restrict__ thresh, float *__restrict__ l1out,
+                     float *__restrict__ l2val, int32_t *__restrict__ l2id)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *L1 = reinterpret_cast<float *>(smem) + warp * (k1 + 2 * k2 + 2);
+    float *L2v = L1 + k1;
+    int32_t *L2i = reinterpret_cast<int32_t *>(L2v + k2);
+    float *thr = reinterpret_cast<float *>(L2i + k2);  // [0] k1-th value, [1] k2-th value
+    for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < n; row += (int64_t)gridDim.x * 8) {
+        for (int k = lane; k < k1; k += 32) L1[k] = INFINITY;
+        for (int k = lane; k < k2; k += 32) {
+            L2v[k] = INFINITY;
+            L2i[k] = INT32_MAX;
+        }
+        if (lane == 0) {
+            thr[0] = INFINITY;
+            thr[1] = k2 > 0 ? INFINITY : -INFINITY;
+        }
+        __syncwarp();
+        for (int src = 0; src < n_src; ++src) {
+            const int64_t rrow = (int64_t)src * n + row;
+            const int m = min(cnt[rrow], R);
+            const uint2 *rr = rec + rrow * R;
+            for (int e0 = 0; e0 < m; e0 += 32) {
+                const int e = e0 + lane;
+                float v = INFINITY;
+                int32_t id = 0;
+                bool comp = true, l2only = false;
+                if (e < m) {
+                    const uint2 x = rr[e];
+                    v = __uint_as_float(x.x);
+                    id = (int32_t)(x.y & 0x3fffffffu);
+                    comp = (x.y >> 31) != 0;           // computed pair: not a guarantee_nmin candidate
+                    l2only = (x.y & 0x40000000u) != 0; // merge input that is already in a value list
+                }
+                unsigned m1 = __ballot_sync(0xffffffffu, e < m && !l2only && v <= thr[0]);
+                while (m1) {
+                    const int s = __ffs(m1) - 1;
+                    m1 &= m1 - 1;
+                    const float xv = __shfl_sync(0xffffffffu, v, s);
+                    if (xv <= thr[0]) SortedRow::insert(L1, nullptr, k1, xv, 0, lane, &thr[0]);
+                }
+                if (k2 > 0) {
+                    unsigned m2 = __ballot_sync(0xffffffffu, e < m && !comp && v < INFINITY && v <= thr[1]);
+                    while (m2) {
+                        const int s = __ffs(m2) - 1;
+                        m2 &= m2 - 1;
+                        const float xv = __shfl_sync(0xffffffffu, v, s);
+                        const int xi = __shfl_sync(0xffffffffu, id, s);
+                        if (xv <= thr[1]) SortedRow::insert(L2v, L2i, k2, xv, xi, lane, &thr[1]);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) thresh[row] = L1[k1 - 1];
+        if (l1out)
+            for (int k = lane; k < k1; k += 32) l1out[row * k1 + k] = L1[k];
+        for (int k = lane; k < k2; k += 32) {
+            l2val[row * k2 + k] = L2v[k];
+            l2id[row * k2 + k] = L2i[k] == INT32_MAX ? -1 : L2i[k];
+        }
+        __syncwarp();
+    }
+}
+
+int launch_thresh_select(annb_ctx *c, const uint2 *rec, const int32_t *cnt, int R, int64_t n, int k1, int k2,
+                         int n_src, float *thresh, float *l1out, float *l2val, int32_t *l2id)
+{
+    const size_t smem = (size_t)8 * (k1 + 2 * k2 + 2) * 4;
+    const int grid = (int)std::min<int64_t>((n + 7) / 8, (int64_t)c->num_sms * 8);
+    ANNB_LAUNCH(thresh_select_kernel, grid, 256, smem, c->stream, rec, cnt, R, n, k1, k2, n_src, thresh, l1out, l2val,
+                l2id);
     return ANNB_OK;
 }
 

@@ -252,3 +252,37 @@ def test_p_work_clamps_and_errors(gpu_ctx):
         Annchor(X, lambda x, y: 0.0)
     with pytest.raises(AssertionError):
         Annchor(X, "manhattan")
+
+
+def test_two_stage_thresholds_equal_row_sweep(gpu_ctx, monkeypatch):
+    """Large metric problems compute thresh / the guarantee_nmin lists in two stages (column-subset
+    bounds, one visit per pair, per-row selection; sweep_thresh.cu).  The result must equal the row
+    sweep's bit for bit: thresholds directly, and the whole fit() (which also exercises the
+    guarantee_nmin lists of iteration 0) through the final graph."""
+    from annchor_b200.annchor import Annchor
+    X = bench_blobs(20000, 128, 100, 42, np.float32)
+    kw = dict(n_anchors=30, n_neighbors=15, n_samples=5000, p_work=0.01)
+
+    def staged():
+        a = Annchor(X, "euclidean", ctx=gpu_ctx, **kw)
+        a.get_anchors()
+        a.get_locality()
+        a.get_sample()
+        a.fit_predict_regression()
+        a.fit_predict_errors()
+        return a
+
+    a = staged()
+    monkeypatch.delenv("ANNB_THRESH_ROWS", raising=False)
+    th_two = a._index.row_thresh()
+    monkeypatch.setenv("ANNB_THRESH_ROWS", "1")
+    th_rows = a._index.row_thresh()
+    assert np.array_equal(th_two, th_rows)
+    assert np.isfinite(th_rows).all()
+    full_rows = Annchor(X, "euclidean", ctx=gpu_ctx, **kw).fit()
+    monkeypatch.delenv("ANNB_THRESH_ROWS")
+    full_two = Annchor(X, "euclidean", ctx=gpu_ctx, **kw).fit()
+    assert full_two.n_forced == full_rows.n_forced
+    assert full_two.evals == full_rows.evals
+    assert np.array_equal(full_two.neighbor_graph[0], full_rows.neighbor_graph[0])
+    assert np.array_equal(full_two.neighbor_graph[1], full_rows.neighbor_graph[1])
