@@ -1830,9 +1830,9 @@ static int run_score(annb_index *ix, int floor_level, uint64_t floor_mix_thr, in
     float ms = 0;
     ANNB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     const int64_t pairs = ix->n * (ix->n - 1) / 2 / ix->P.world / stride;
-    if (stride == 1) {
-        ix->last_sweep_ms = ms;
-        ix->last_sweep_pairs = pairs;
+    if (stride == 1) {  // accumulated over the full scoring sweeps of this index (bench.py: roofline)
+        ix->last_sweep_ms += ms;
+        ix->last_sweep_pairs += pairs;
     }
     ix->pairs_swept += pairs;
     ix->sweeps += 1;

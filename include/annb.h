@@ -205,7 +205,8 @@ int annb_index_neighbor_graph(annb_index *ix, int64_t *idx, double *dist);
 /* counters: [0] pairs swept, [1] known pairs, [2] tightened pairs, [3] sweep launches,
  * [4] candidate pairs, [5] hash capacity, [6] anchor pairs, [7] not-computed candidates */
 int annb_index_stats(annb_index *ix, int64_t *out, int64_t n);
-/* device-time (ms) of the last sweep kernel and the pairs it covered */
+/* device time (ms, CUDA events on the context stream) and pairs covered, summed over the full
+ * scoring sweeps (score_sweep_kernel, stride 1) this index has run */
 int annb_index_last_sweep(annb_index *ix, float *ms, int64_t *pairs);
 
 /* ---- multi-GPU (no counterpart in the single-host reference) ----------------------
