@@ -527,15 +527,24 @@ __device__ __forceinline__ void group_key(const int64_t *__restrict__ kptr, int 
     other = a_key ? b : a;
 }
 
+// group sizes, and per key row the list entries its group will stream (scheduling weight)
 __global__ void count_by_lo_kernel(const int32_t *__restrict__ I, const int32_t *__restrict__ J, int64_t m,
-                                   const int64_t *__restrict__ kptr, int32_t *__restrict__ cnt)
+                                   const int64_t *__restrict__ kptr, int32_t *__restrict__ cnt,
+                                   unsigned long long *__restrict__ work, unsigned long long *__restrict__ total)
 {
+    unsigned long long mine = 0;
     for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < m;
          p += (int64_t)gridDim.x * blockDim.x) {
         int key, other;
         group_key(kptr, I[p], J[p], key, other);
         atomicAdd(&cnt[key], 1);
+        const unsigned long long d = (unsigned long long)(kptr[other + 1] - kptr[other]);
+        atomicAdd(&work[key], d);
+        mine += d;
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(total, mine);
 }
 
 __global__ void scatter_by_lo_kernel(const int32_t *__restrict__ I, const int32_t *__restrict__ J, int64_t m,
@@ -1561,7 +1570,8 @@ static int run_thresh(annb_index *ix, int k2)
     }
     ANNB_CUDA(cudaEventRecord(c->ev0, c->stream));
     const bool force_rows = getenv("ANNB_THRESH_ROWS") != nullptr;  // test knob: row sweep only
-    const int S = 8;  // pre-pass visits every S-th column tile
+    static const int S_env = getenv("ANNB_THRESH_STRIDE") ? atoi(getenv("ANNB_THRESH_STRIDE")) : 0;
+    const int S = S_env > 0 ? S_env : 8;  // pre-pass visits every S-th column tile
     const bool two_stage = ix->P.is_metric && ix->T >= 16 * S && n < (1 << 30) && !force_rows;
     if (!two_stage) {
         ANNB_TRY(run_thresh_rows(ix, k2, 1, nullptr, nullptr, 0));
@@ -1577,7 +1587,10 @@ static int run_thresh(annb_index *ix, int k2)
         ANNB_CUDA(cudaMemcpyAsync(ix->tcut1.p, ix->thresh.p, (size_t)ix->npad * 4, cudaMemcpyDeviceToDevice,
                                   c->stream));
         // 2. one visit per pair, records to both endpoints
-        const int R = (2 * S * (k1 + k2) + 31) / 32 * 32;
+        // record slots per point: ~S*(k1+k2) expected (the k-th smallest of 1/S of the columns is about
+        // the S*k-th smallest overall), x2 (x4 without the second list) for the spread
+        static const int R_env = getenv("ANNB_THRESH_RECORDS") ? atoi(getenv("ANNB_THRESH_RECORDS")) : 0;
+        const int R = R_env > 0 ? R_env : ((k2 > 0 ? 2 : 4) * S * (k1 + k2) + 31) / 32 * 32;
         ANNB_TRY(ix->trec.ensure((size_t)n * R * 8));
         ANNB_TRY(ix->tcnt.ensure((size_t)n * 4));
         ANNB_CUDA(cudaMemsetAsync(ix->tcnt.p, 0, (size_t)n * 4, c->stream));
@@ -2188,8 +2201,15 @@ ANNB_API int annb_index_update_bounds(annb_index *ix, int64_t *n_updated)
     ANNB_TRY(ix->gJ.ensure((size_t)m * 4));
     ANNB_TRY(ix->gsrc.ensure((size_t)m * 4));
     ANNB_CUDA(cudaMemsetAsync(ix->kdeg.p, 0, (size_t)(n + 1) * 4, c->stream));
+    ANNB_TRY(ix->twork.ensure((size_t)n * 8));
+    ANNB_TRY(ix->theavy.ensure((size_t)n * 4));
+    ANNB_CUDA(cudaMemsetAsync(ix->twork.p, 0, (size_t)n * 8, c->stream));
+    ANNB_CUDA(cudaMemsetAsync(ix->counters.p, 0, 64, c->stream));
     ANNB_LAUNCH(count_by_lo_kernel, grid_for_n(c, m), 256, 0, c->stream, ix->nxt_i.as<int32_t>(),
-                ix->nxt_j.as<int32_t>(), m, ix->kptr.as<int64_t>(), ix->kdeg.as<int32_t>());
+                ix->nxt_j.as<int32_t>(), m, ix->kptr.as<int64_t>(), ix->kdeg.as<int32_t>(),
+                ix->twork.as<unsigned long long>(), ix->counters.as<unsigned long long>() + 7);
+    unsigned long long wsum[3] = {0, 0, 0};
+    ANNB_CUDA(cudaMemcpyAsync(wsum, ix->counters.as<unsigned long long>() + 7, 8, cudaMemcpyDeviceToHost, c->stream));
     ANNB_LAUNCH(exclusive_scan_kernel, 1, 1024, 0, c->stream, ix->kdeg.as<int32_t>(),
                 ix->gptr.as<int64_t>(), n);
     ANNB_CUDA(cudaMemsetAsync(ix->kdeg.p, 0, (size_t)(n + 1) * 4, c->stream));
@@ -2254,15 +2274,7 @@ ANNB_API int annb_index_update_bounds(annb_index *ix, int64_t *n_updated)
         ANNB_LAUNCH(cA_scatter_kernel, grid_for_n(c, n), 256, 0, c->stream, ix->meta.as<PointMeta>(), n,
                     ix->counters.as<int32_t>(), ix->row_order.as<int32_t>());
     }
-    // per-row streaming work -> heavy rows first, then closest-anchor order, fetched dynamically
-    ANNB_TRY(ix->twork.ensure((size_t)n * 8));
-    ANNB_TRY(ix->theavy.ensure((size_t)n * 4));
-    ANNB_CUDA(cudaMemsetAsync(ix->counters.p, 0, 64, c->stream));
-    ANNB_LAUNCH(tighten_work_kernel, grid_for_n(c, n), 256, 0, c->stream, ix->kptr.as<int64_t>(),
-                ix->gptr.as<int64_t>(), ix->gJ.as<int32_t>(), n, ix->counters.as<unsigned long long>(),
-                ix->twork.as<unsigned long long>());
-    unsigned long long wsum[3] = {0, 0, 0};
-    ANNB_CUDA(cudaMemcpyAsync(wsum, ix->counters.p, 24, cudaMemcpyDeviceToHost, c->stream));
+    // per-row streaming work (from the grouping pass) -> heavy rows first, then closest-anchor order
     ANNB_CUDA(cudaStreamSynchronize(c->stream));
     const int tg_grid = c->num_sms * 3;
     // a row is "heavy" when it is more than 1/16 of a CTA's fair share of the streamed entries

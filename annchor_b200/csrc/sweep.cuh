@@ -72,6 +72,23 @@ __device__ __forceinline__ void load_bitmap_tile(const View &V, int ti, int tj, 
     if (tid >= 128) cp_async16(sB + (tid - 128) * 4, src + (tid - 128) * 4);
 }
 
+// Pull the hash slots of a tile's flagged pairs into L2 while the tile's phase 1 runs: the canonical
+// bitmap tile (rows = lower endpoint) is in shared memory, every thread walks the set bits of two
+// words.  Phase 2's look-ups for known / tightened pairs then hit L2 instead of DRAM.
+__device__ __forceinline__ void prefetch_flagged(const View &V, const uint32_t *sB, int tlo, int thi)
+{
+    for (int w = threadIdx.x; w < BITMAP_WORDS; w += blockDim.x) {
+        uint32_t bits = sB[w];
+        const uint32_t lo = (uint32_t)(tlo * TILE + (w >> 2)), hi0 = (uint32_t)(thi * TILE + (w & 3) * 32);
+        while (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const uint64_t h = mix64(pair_key(lo, hi0 + b)) & V.hmask;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(V.htab + h));
+        }
+    }
+}
+
 __device__ __forceinline__ int micro_off(int t4, int k)  // local index of the k-th of 8 rows/cols
 {
     return (k < 4) ? (t4 * 4 + k) : (64 + t4 * 4 + (k - 4));

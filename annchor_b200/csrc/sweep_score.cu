@@ -137,6 +137,7 @@ __global__ void __launch_bounds__(256, 1) score_sweep_kernel(const __grid_consta
         const float *sDi = buf ? sD1i : sD0i, *sDj = buf ? sD1j : sD0j;
         const PointMeta *sMi = buf ? sM1i : sM0i, *sMj = buf ? sM1j : sM0j;
         const uint32_t *bm = buf ? sB1 : sB0;
+        prefetch_flagged(V, bm, ti, tj);
         const float *tI = thI + buf * TILE, *tJ = thJ + buf * TILE;
         // ---- phase 1: bounds + clipped prediction; keep (pred < cut-off) | flagged ----
         float cj[8];

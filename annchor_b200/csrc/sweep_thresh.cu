@@ -356,6 +356,7 @@ __global__ void __launch_bounds__(256, 1) thresh_pairs_kernel(const __grid_const
         const float *sDi = buf ? sD1i : sD0i, *sDj = buf ? sD1j : sD0j;
         const PointMeta *sMi = buf ? sM1i : sM0i, *sMj = buf ? sM1j : sM0j;
         const uint32_t *bm = buf ? sB1 : sB0;
+        prefetch_flagged(V, bm, ti, tj);
         const float *k1I = c1I + buf * TILE, *k1J = c1J + buf * TILE;
         const float *k2I = c2I + buf * TILE, *k2J = c2J + buf * TILE;
         float cj[8];
