@@ -1102,11 +1102,13 @@ static int hash_alloc(annb_index *ix, uint64_t cap)
     return ANNB_OK;
 }
 
-// make room for `extra` more entries (load factor <= 0.5)
+// make room for `extra` more entries: load factor <= 0.75 (look-ups are almost always hits -- the
+// flag bitmap filters the misses -- so the longer probe chains of a fuller table cost little, and a
+// power-of-two table at <= 0.5 would need 69 GB instead of 34 GB at N=1M, p_work=1e-3)
 static int hash_reserve(annb_index *ix, int64_t extra)
 {
     annb_ctx *c = ix->ctx;
-    const uint64_t need = (uint64_t)(ix->hcount_ub + extra) * 2 + 1024;
+    const uint64_t need = (uint64_t)(ix->hcount_ub + extra) * 4 / 3 + 1024;
     if (need <= ix->hcap) return ANNB_OK;
     uint64_t cap = ix->hcap ? ix->hcap : 1024;
     while (cap < need) cap <<= 1;

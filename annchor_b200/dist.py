@@ -136,19 +136,29 @@ class Comm:
         return out
 
 
-def exchange(comm, local_columns, import_fn):
+def exchange(comm, local_columns, import_fn, chunk=1 << 24):
     """All-gather this rank's result columns and hand every OTHER rank's rows to import_fn(cols).
-    Returns the number of rows imported."""
-    gathered = comm.all_gather_var(local_columns)
-    comm.sync()  # the gathered columns are read next by kernels on the index's own stream
+    Works through the rows in chunks so that the staging buffers stay small (at N=1M a refine round
+    moves ~10^8 rows per rank).  Returns the number of rows imported."""
+    import torch
+    n = int(local_columns[0].shape[0]) if local_columns else 0
+    counts = torch.zeros(comm.world, dtype=torch.int64, device=local_columns[0].device)
+    counts[comm.rank] = n
+    comm.dist.all_reduce(counts, op=comm.dist.ReduceOp.SUM, group=comm.group)
+    n_max = int(counts.max().item())
     imported = 0
-    for r in range(comm.world):
-        if r == comm.rank:
-            continue
-        cols = [g[r] for g in gathered]
-        if cols and cols[0].shape[0]:
-            import_fn(cols)
-            imported += int(cols[0].shape[0])
+    for lo in range(0, n_max, chunk):
+        part = [c[min(lo, n):min(lo + chunk, n)] for c in local_columns]
+        gathered = comm.all_gather_var(part)
+        comm.sync()  # the gathered columns are read next by kernels on the index's own stream
+        for r in range(comm.world):
+            if r == comm.rank:
+                continue
+            cols = [g[r] for g in gathered]
+            if cols and cols[0].shape[0]:
+                import_fn(cols)
+                imported += int(cols[0].shape[0])
+        del gathered
     return imported
 
 
