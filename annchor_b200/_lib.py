@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libannb.so")
+SO_PATH = os.environ.get("ANNB_LIBRARY") or os.path.join(_HERE, "libannb.so")  # ANNB_LIBRARY: A/B builds
 
 EUCLIDEAN, COSINE, LEVENSHTEIN, WASSERSTEIN1D = 0, 1, 2, 3
 F32, F64, U8 = 0, 1, 2

@@ -28,7 +28,12 @@ def needs_build():
     return any(os.path.getmtime(p) > t for p in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, extra_flags=(), out=None):
+    """extra_flags / out: build a variant library (e.g. -DANNB_VARIANT=...) next to the default one;
+    select it at run time with ANNB_LIBRARY=<path>."""
+    global SO
+    if out is not None:
+        return _build_variant(list(extra_flags), out, verbose)
     if not force and not needs_build():
         return SO
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -57,6 +62,27 @@ def build(force=False, verbose=False):
     subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart",
                            "static", "-o", SO] + objs)
     return SO
+
+
+def _build_variant(extra, out, verbose):
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    bdir = os.path.join(HERE, "build", os.path.basename(out).replace(".", "_"))
+    os.makedirs(bdir, exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if f not in ("-shared",)] + extra
+    procs, objs = [], []
+    for src in sources():
+        obj = os.path.join(bdir, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        procs.append((src, subprocess.Popen([nvcc] + flags + ["-c", src, "-o", obj], stdout=subprocess.PIPE,
+                                            stderr=subprocess.STDOUT)))
+    for src, p in procs:
+        o = p.communicate()[0].decode()
+        if p.returncode != 0:
+            sys.stderr.write(o)
+            raise RuntimeError("nvcc failed on %s" % src)
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static",
+                           "-o", out] + objs)
+    return out
 
 
 if __name__ == "__main__":

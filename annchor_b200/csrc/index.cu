@@ -276,20 +276,6 @@ __global__ void pair_features_kernel(View V, const int32_t *__restrict__ I,
 }
 
 // ---- selection over the emitted list -----------------------------------------------------------
-// digit histogram of the mixed pair keys at one level (deterministic tie-break at the cut)
-__global__ void tie_hist_kernel(const uint64_t *__restrict__ keys, const uint16_t *__restrict__ lvl,
-                                int64_t E, int level, uint64_t prefix, int shift /* bits below digit */,
-                                uint32_t *__restrict__ hist /* 65536 */)
-{
-    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < E;
-         p += (int64_t)gridDim.x * blockDim.x) {
-        if (lvl[p] != level) continue;
-        const uint64_t mk = mix64(keys[p]);
-        if (shift < 48 && (mk >> (shift + 16)) != prefix) continue;
-        atomicAdd(&hist[(mk >> shift) & 0xffff], 1u);
-    }
-}
-
 // block-wide exclusive scan of a packed pair of 16-bit counts (lo | hi << 16); returns this
 // thread's exclusive prefix and the block total (256 threads, each count <= 8 per half)
 __device__ __forceinline__ uint32_t block_scan_packed(uint32_t v, uint32_t *s_warp /* [9] */, uint32_t &total)
@@ -448,69 +434,6 @@ __global__ void known_fill_kernel(const HashSlot *__restrict__ htab, uint64_t ca
     }
 }
 
-// sort every CSR row by id: bitonic network, one block per row, in shared memory when the
-// row fits (<= 4096 entries) else directly in global memory
-__global__ void __launch_bounds__(256)
-sort_rows_kernel(const int64_t *__restrict__ ptr, int64_t n, int32_t *__restrict__ ids,
-                 float *__restrict__ ds)
-{
-    __shared__ int32_t s_id[4096];
-    __shared__ float s_d[4096];
-    for (int64_t row = blockIdx.x; row < n; row += gridDim.x) {
-        const int64_t beg = ptr[row];
-        const int m = (int)(ptr[row + 1] - beg);
-        if (m <= 1) continue;
-        int P2 = 1;
-        while (P2 < m) P2 <<= 1;
-        const bool in_smem = P2 <= 4096;
-        __syncthreads();
-        if (in_smem) {
-            for (int k = threadIdx.x; k < P2; k += blockDim.x) {
-                s_id[k] = k < m ? ids[beg + k] : INT32_MAX;
-                s_d[k] = k < m ? ds[beg + k] : 0.0f;
-            }
-        }
-        __syncthreads();
-        for (int size = 2; size <= P2; size <<= 1)
-            for (int stride = size >> 1; stride > 0; stride >>= 1) {
-                for (int k = threadIdx.x; k < P2 / 2; k += blockDim.x) {
-                    const int lo = 2 * k - (k & (stride - 1));
-                    const int hi = lo + stride;
-                    const bool up = (lo & size) == 0;
-                    if (in_smem) {
-                        const int32_t a = s_id[lo], b = s_id[hi];
-                        if ((a > b) == up) {
-                            s_id[lo] = b;
-                            s_id[hi] = a;
-                            const float t = s_d[lo];
-                            s_d[lo] = s_d[hi];
-                            s_d[hi] = t;
-                        }
-                    } else {
-                        const int32_t a = lo < m ? ids[beg + lo] : INT32_MAX;
-                        const int32_t b = hi < m ? ids[beg + hi] : INT32_MAX;
-                        if ((a > b) == up && lo < m) {
-                            // hi >= m can only hold padding, which never needs to move left of real data
-                            if (hi < m) {
-                                ids[beg + lo] = b;
-                                ids[beg + hi] = a;
-                                const float t = ds[beg + lo];
-                                ds[beg + lo] = ds[beg + hi];
-                                ds[beg + hi] = t;
-                            }
-                        }
-                    }
-                }
-                __syncthreads();
-            }
-        if (in_smem)
-            for (int k = threadIdx.x; k < m; k += blockDim.x) {
-                ids[beg + k] = s_id[k];
-                ds[beg + k] = s_d[k];
-            }
-    }
-}
-
 // ---- update_bounds (utils.py:304-352) for the look-ahead pairs -------------------------------
 // Every point k with both d(i,k) and d(j,k) known acts as an extra anchor for the pair (i,j):
 //   lb = max_k |d_ik - d_jk|,  ub = min_k (d_ik + d_jk)   over k in N(i) & N(j).
@@ -618,6 +541,12 @@ __global__ void tighten_heavy_kernel(const unsigned long long *__restrict__ work
 // K2b.  Dynamic row scheduling (one atomic per row), bucketed shared-memory hash (4 ids per bucket,
 // one 128-bit probe, no divergent chains at load <= 0.25), partner lists streamed with the next
 // 128 entries in flight while the current ones are probed.
+#ifdef ANNB_VARIANT_TGU8
+constexpr int TGU = 8;  // 32-entry loads of a partner list in flight per warp
+#else
+constexpr int TGU = 4;
+#endif
+
 __global__ void __launch_bounds__(512)
 tighten_grouped_kernel(View V, const int64_t *__restrict__ kptr, const int32_t *__restrict__ kids,
                        const float *__restrict__ kds, const int64_t *__restrict__ gptr,
@@ -699,25 +628,25 @@ tighten_grouped_kernel(View V, const int64_t *__restrict__ kptr, const int32_t *
                 const int64_t bj = kptr[j];
                 const int mj = (int)(kptr[j + 1] - bj);
                 float lb = 0.0f, ub = INFINITY;
-                int32_t idv[4], idn[4];
-                float yv[4], yn[4];
+                int32_t idv[TGU], idn[TGU];
+                float yv[TGU], yn[TGU];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < TGU; ++u) {
                     const int k = u * 32 + lane;
                     idv[u] = k < mj ? __ldg(kids + bj + k) : -2;
                     yv[u] = k < mj ? __ldg(kds + bj + k) : 0.0f;
                 }
-                for (int k0 = 0; k0 < mj; k0 += 128) {
-                    if (k0 + 128 < mj) {
+                for (int k0 = 0; k0 < mj; k0 += 32 * TGU) {
+                    if (k0 + 32 * TGU < mj) {
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int k = k0 + 128 + u * 32 + lane;
+                        for (int u = 0; u < TGU; ++u) {
+                            const int k = k0 + 32 * TGU + u * 32 + lane;
                             idn[u] = k < mj ? __ldg(kids + bj + k) : -2;
                             yn[u] = k < mj ? __ldg(kds + bj + k) : 0.0f;
                         }
                     }
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
+                    for (int u = 0; u < TGU; ++u) {
                         // branch-free probe of the home bucket: one 128-bit load (3 ids + overflow flag),
                         // one load of the candidate value; padding lanes carry id = -2 and match nothing
                         const int32_t id = idv[u];
@@ -739,7 +668,7 @@ tighten_grouped_kernel(View V, const int64_t *__restrict__ kptr, const int32_t *
                         ub = fminf(ub, hit ? x + yv[u] : INFINITY);
                     }
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
+                    for (int u = 0; u < TGU; ++u) {
                         idv[u] = idn[u];
                         yv[u] = yn[u];
                     }

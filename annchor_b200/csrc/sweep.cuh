@@ -110,7 +110,11 @@ __device__ __forceinline__ void bounds_half(const float *__restrict__ sDi, const
             ub[r][c] = INFINITY;
         }
     int a = 0;
+#ifdef ANNB_VARIANT_UNROLL2
+#pragma unroll 2
+#else
 #pragma unroll 1
+#endif
     for (; a + 2 <= na; a += 2) {
         const float *pi = sDi + a * SROW + row0, *pj = sDj + a * SROW + tx * 4;
         const float4 i0 = *reinterpret_cast<const float4 *>(pi);

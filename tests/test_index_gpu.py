@@ -254,17 +254,22 @@ def test_p_work_clamps_and_errors(gpu_ctx):
         Annchor(X, "manhattan")
 
 
-def test_two_stage_thresholds_equal_row_sweep(gpu_ctx, monkeypatch):
+@pytest.mark.parametrize("kind", ["euclid", "strings"])
+def test_two_stage_thresholds_equal_row_sweep(gpu_ctx, monkeypatch, kind):
     """Large metric problems compute thresh / the guarantee_nmin lists in two stages (column-subset
     bounds, one visit per pair, per-row selection; sweep_thresh.cu).  The result must equal the row
     sweep's bit for bit: thresholds directly, and the whole fit() (which also exercises the
     guarantee_nmin lists of iteration 0) through the final graph."""
     from annchor_b200.annchor import Annchor
-    X = bench_blobs(20000, 128, 100, 42, np.float32)
+    if kind == "euclid":
+        X, metric = bench_blobs(20000, 128, 100, 42, np.float32), "euclidean"
+    else:  # integer metric: massive ties at every cut
+        from test_configs_gpu import synthetic_strings
+        X, metric = synthetic_strings(20000), "levenshtein"
     kw = dict(n_anchors=30, n_neighbors=15, n_samples=5000, p_work=0.01)
 
     def staged():
-        a = Annchor(X, "euclidean", ctx=gpu_ctx, **kw)
+        a = Annchor(X, metric, ctx=gpu_ctx, **kw)
         a.get_anchors()
         a.get_locality()
         a.get_sample()
@@ -279,9 +284,9 @@ def test_two_stage_thresholds_equal_row_sweep(gpu_ctx, monkeypatch):
     th_rows = a._index.row_thresh()
     assert np.array_equal(th_two, th_rows)
     assert np.isfinite(th_rows).all()
-    full_rows = Annchor(X, "euclidean", ctx=gpu_ctx, **kw).fit()
+    full_rows = Annchor(X, metric, ctx=gpu_ctx, **kw).fit()
     monkeypatch.delenv("ANNB_THRESH_ROWS")
-    full_two = Annchor(X, "euclidean", ctx=gpu_ctx, **kw).fit()
+    full_two = Annchor(X, metric, ctx=gpu_ctx, **kw).fit()
     assert full_two.n_forced == full_rows.n_forced
     assert full_two.evals == full_rows.evals
     assert np.array_equal(full_two.neighbor_graph[0], full_rows.neighbor_graph[0])
