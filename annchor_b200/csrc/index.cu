@@ -114,9 +114,13 @@ locality_count_kernel(const PointMeta *__restrict__ meta, int64_t n, int loc_thr
         for (int k = 0; k < lim; ++k) {
             const int c = __popcll(mi.amask & s_mask[k]);
             if (pass == 1) {
-                const int cc = c < loc_thresh ? c : loc_thresh;
+                if (loc_thresh <= 1) {
+                    cnt[1] += (c >= 1);  // default loc_thresh = 1: one counter; cnt[0] follows from n
+                } else {
+                    const int cc = c < loc_thresh ? c : loc_thresh;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) cnt[q] += (cc == q);
+                    for (int q = 0; q < 8; ++q) cnt[q] += (cc == q);
+                }
             } else {
                 const int t = mi.loc_t < s_t[k] ? mi.loc_t : s_t[k];
                 cnt[0] += (c >= t) && (j0 + k != i);
@@ -125,6 +129,11 @@ locality_count_kernel(const PointMeta *__restrict__ meta, int64_t n, int loc_thr
     }
     if (!live) return;
     if (pass == 1) {
+        if (loc_thresh <= 1) cnt[0] = (int)n - cnt[1];  // (loc_thresh = 0: everything is in bin 0 = cnt[0] + cnt[1])
+        if (loc_thresh == 0) {
+            cnt[0] = (int)n;
+            cnt[1] = 0;
+        }
 #pragma unroll
         for (int q = 0; q < 8; ++q) out[i * 8 + q] = cnt[q];
     } else {
