@@ -56,3 +56,17 @@ def test_product_path_has_no_oracle_import():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), fn
+
+
+def test_host_only_entry_point_numba_rng(lib_path):
+    """annb_numba_rng_* is pure host code (numba's in-@njit MT19937 + Fisher-Yates, used by the
+    exact-mode sampler, annchor/utils.py:555-557,572): callable without a GPU, and it must agree with
+    the oracle's restatement (which tests/test_oracle.py pins against draws of the real numba)."""
+    import numpy as np
+    from annchor_b200.plugins import NumbaRNG
+    from oracle.pipeline import NumbaRNG as OracleRNG
+    for seed in (0, 42, 43, 2**31 + 5):
+        a, b = NumbaRNG(seed), OracleRNG(seed)
+        for n, size in ((10, 3), (1000, 714), (7, 7), (1, 1)):
+            x = np.arange(n, dtype=np.int64) * 3 + 1
+            np.testing.assert_array_equal(a.choice_no_replace(x, size), b.choice_no_replace(x, size))
