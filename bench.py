@@ -295,7 +295,7 @@ def run_ours(args, w):
         "recall_at_k": rec, "evals": int(last_evals), "stage_seconds": last_stage,
         "index_stats": last_stats,
     }
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:  # reported on rank 0 at N=1 only
         line["cpu_baseline"] = cpu_baseline(w)
     print(json.dumps(line))
 
@@ -319,6 +319,13 @@ def main():
         run_reference(args, w)
     else:
         run_ours(args, w)
+        try:
+            import torch.distributed as dist
+            if dist.is_initialized():
+                dist.barrier()
+                dist.destroy_process_group()
+        except Exception:
+            pass
 
 
 if __name__ == "__main__":
