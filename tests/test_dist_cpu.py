@@ -78,6 +78,15 @@ def _worker(rank, world, port, out_dir):
         got = D.exchange(comm, [li, lj, ld], lambda cols: ix.add(*cols))
         assert got == 11 - len(pairs)
         assert ix.store == {(p, p + 1): p * 0.25 for p in range(11)}
+        # chunked staging (what bounds the buffers at N=1M): same union, ragged last chunk, and a
+        # rank that runs out of rows before the other keeps taking part in the collectives
+        ix2 = FakeIndex()
+        ix2.add(li, lj, ld)
+        calls = []
+        got2 = D.exchange(comm, [li, lj, ld], lambda cols: (calls.append(int(cols[0].shape[0])), ix2.add(*cols)),
+                          chunk=2)
+        assert got2 == got and ix2.store == ix.store
+        assert max(calls) <= 2 and sum(calls) == got
         # ---- tile partition: disjoint cover
         T = 37
         mine = set(D.tiles_of_rank(T, rank, world))
