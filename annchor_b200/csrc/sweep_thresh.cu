@@ -196,6 +196,7 @@ __global__ void __launch_bounds__(256, 1) thresh_sweep_kernel(const __grid_const
                         }
                     }
                     unsigned m1 = __ballot_sync(0xffffffffu, w1b);
+                    __syncwarp();  // every lane has read thr1 / thr2 before an insert rewrites them
                     while (m1) {
                         const int src = __ffs(m1) - 1;
                         m1 &= m1 - 1;
@@ -497,6 +498,7 @@ thresh_select_kernel(const uint2 *__restrict__ rec, const int32_t *__restrict__ 
                     l2only = (x.y & 0x40000000u) != 0; // merge input that is already in a value list
                 }
                 unsigned m1 = __ballot_sync(0xffffffffu, e < m && !l2only && v <= thr[0]);
+                __syncwarp();  // every lane has read thr[0] before an insert rewrites it
                 while (m1) {
                     const int s = __ffs(m1) - 1;
                     m1 &= m1 - 1;
@@ -505,6 +507,7 @@ thresh_select_kernel(const uint2 *__restrict__ rec, const int32_t *__restrict__ 
                 }
                 if (k2 > 0) {
                     unsigned m2 = __ballot_sync(0xffffffffu, e < m && !comp && v < INFINITY && v <= thr[1]);
+                    __syncwarp();
                     while (m2) {
                         const int s = __ffs(m2) - 1;
                         m2 &= m2 - 1;
