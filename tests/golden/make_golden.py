@@ -225,7 +225,23 @@ def gen_cosine():
     save("cosine", X=X, params=np.array([8, 10, 500, 0.2, 42, 2]), **out)
 
 
-GENS = {"kat": gen_kat, "euclid_small": gen_euclid_small, "euclid_f32": gen_euclid_f32,
+def gen_niters4():
+    """The reference's own strings test (annchor/tests/test_annchor.py:71-102): n_anchors=23, k=15,
+    p_work=0.12, niters=4 on the bundled strings -- three update_anchor_points rounds, later
+    iterations re-fit on what is still not computed.  (The Euclidean blob generators make the
+    reference raise "Some sampler bins contain too few samples" in iteration 2 or 3.)"""
+    from annchor import Annchor
+    from annchor.datasets import load_strings
+    X = load_strings()["X"]
+    t = time.time()
+    ann = Annchor(X, "levenshtein", n_anchors=23, n_neighbors=15, n_samples=5000, p_work=0.12, niters=4)
+    out = staged_fit(ann, full=False)
+    print("strings niters=4 fit %.1fs evals %d" % (time.time() - t, out["evals"]))
+    out.pop("D")  # same strings as strings.npz; anchors differ (23 of them): keep A only
+    save("niters4", params=np.array([23, 15, 5000, 0.12, 42, 4]), **out)
+
+
+GENS = {"niters4": gen_niters4, "kat": gen_kat, "euclid_small": gen_euclid_small, "euclid_f32": gen_euclid_f32,
         "blobs1000": gen_blobs1000, "strings": gen_strings, "w1": gen_w1, "cosine": gen_cosine}
 
 if __name__ == "__main__":
