@@ -64,6 +64,9 @@ _SIGS = {
     "annb_index_sample_pool": [_P, _U64, _I64, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(C.c_int)],
     "annb_index_get_pool": [_P, _P, _P],
     "annb_index_pair_features": [_P, _P, _I64, _P],
+    "annb_index_pair_state": [_P, _P, _I64, _P, _P, _P],
+    "annb_index_get_thresh": [_P, _P],
+    "annb_index_set_lookahead": [_P, _P, _I64],
     "annb_index_add_known": [_P, _P, _P, _I64],
     "annb_index_eval_pairs": [_P, _P, _I64, _P],
     "annb_index_set_model": [_P, _P, _P, _P, _I64, _P, _P],

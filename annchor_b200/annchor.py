@@ -95,6 +95,25 @@ class Index:
         check(self._L.annb_index_pair_features(self.handle, ptr(ij), ij.shape[0], ptr(feat)))
         return feat
 
+    def pair_state(self, ij):
+        """-> (kind int32[n], a float64[n], b float64[n]): the store entry of each pair
+        (0 none, 1 known: a = distance, 2 tightened: (a, b) = (lb, ub), 3 forced)."""
+        ij = as_c(ij, np.int64).reshape(-1, 2)
+        n = ij.shape[0]
+        kind, a, b = np.zeros(n, dtype=np.int32), np.zeros(n), np.zeros(n)
+        check(self._L.annb_index_pair_state(self.handle, ptr(ij), n, ptr(kind), ptr(a), ptr(b)))
+        return kind, a, b
+
+    def get_thresh(self):
+        th = np.empty(self.n, dtype=np.float64)
+        check(self._L.annb_index_get_thresh(self.handle, ptr(th)))
+        return th
+
+    def set_lookahead(self, ij):
+        ij = as_c(ij, np.int64).reshape(-1, 2)
+        check(self._L.annb_index_set_lookahead(self.handle, ptr(ij), ij.shape[0]))
+        self._sel = (0, ij.shape[0])
+
     def add_known(self, ij, d):
         ij, d = as_c(ij, np.int64).reshape(-1, 2), as_c(d, np.float64)
         check(self._L.annb_index_add_known(self.handle, ptr(ij), ptr(d), ij.shape[0]))
@@ -185,17 +204,28 @@ class Annchor:
     """Quickly computes the approximate k-NN graph for slow metrics -- on a B200.
 
     Parameters are those of the reference class (annchor/annchor.py:27-88).  ``func`` must be one
-    of the bundled metric names ('euclidean', 'cosine', 'levenshtein', 'wasserstein' with a 1-D
-    ``cost_matrix``): arbitrary Python callables cannot run on the device and there is no CPU
-    fallback.  ``backend`` and ``get_exact_ijs`` are accepted for signature compatibility;
-    the metric is always evaluated by the CUDA kernels.
+    of the bundled metric names ('euclidean', 'cosine', 'levenshtein', 'wasserstein'): arbitrary
+    Python callables cannot run on the device and there is no CPU fallback, so they raise.
+    ``backend`` is accepted for signature compatibility.  ``get_exact_ijs`` must be None or an
+    ``annchor_b200.GpuExactIJs`` (the metric is always evaluated by the CUDA kernels; a host
+    evaluator would be a CPU fallback and raises instead of being silently ignored).
+
+    Plug-ins: anchor pickers use the reference protocol unchanged; samplers may implement either
+    ``sample_index(ann)`` (streaming, any N) or the reference's ``sample(features, ...)``
+    (annchor/samplers.py:75-110), which is served from a materialised view of the not-computed
+    candidate pairs and therefore limited to ``plugins.MATERIALISED_LIMIT`` such pairs;
+    regression / error predictor must expose their fitted tables (see annchor_b200.plugins).
+
+    Device limits (checked here, before any work is done): n_anchors <= 64,
+    n_neighbors <= 42 (guarantee_nmin keeps 3*n_neighbors//2 + 1 <= 64 entries per row),
+    loc_thresh <= 7, n_partitions <= 8.
     """
 
     def __init__(self, X, func, func_kwargs=None, n_anchors=20, n_neighbors=15, n_samples=5000,
                  p_work=0.1, anchor_picker=None, sampler=None, regression=None, error_predictor=None,
                  random_seed=42, locality=5, loc_thresh=1, loc_min=None, verbose=False, is_metric=True,
                  get_exact_ijs=None, backend="loky", niters=2, lookahead=5, device=0, ctx=None,
-                 comm=None, _dataset=None):
+                 comm=None, _dataset=None, _trace=None):
         if not isinstance(func, str):
             raise NotImplementedError(
                 "annchor_b200 evaluates metrics on the GPU; pass one of 'euclidean', 'cosine', "
@@ -208,6 +238,20 @@ class Annchor:
                 "Error: wassetstein metric requires cost_function kwarg"
             cost = func_kwargs["cost_matrix"]
         assert backend in ["loky", "multiprocessing"]
+        if get_exact_ijs is not None and not isinstance(get_exact_ijs, GpuExactIJs):
+            raise NotImplementedError(
+                "get_exact_ijs=%r: annchor_b200 evaluates the metric with its CUDA kernels; a host-side "
+                "evaluator (annchor/annchor.py:77-82) would be a CPU fallback, which this package does not "
+                "provide.  Pass None or an annchor_b200.GpuExactIJs." % (get_exact_ijs,))
+        if n_anchors > 64:
+            raise ValueError("n_anchors=%d: the device keeps the nearest-anchor set in a 64-bit mask "
+                             "(n_anchors <= 64)" % n_anchors)
+        if 3 * n_neighbors // 2 + 1 > 64 or n_neighbors < 2:
+            raise ValueError("n_neighbors=%d: the device row lists hold 64 entries and guarantee_nmin "
+                             "(annchor/utils.py:606-621) needs 3*n_neighbors//2 + 1 of them "
+                             "(2 <= n_neighbors <= 42)" % n_neighbors)
+        if loc_thresh > 7:
+            raise ValueError("loc_thresh=%d: the device counts shared anchors up to 7" % loc_thresh)
         self.X = X
         self.nx = len(X)
         self.N = (self.nx * (self.nx - 1)) // 2
@@ -236,9 +280,12 @@ class Annchor:
         self.regression = regression or SimpleStratifiedLinearRegression()
         self.error_predictor = error_predictor or SimpleStratifiedErrorRegression()
         if not hasattr(self.sampler, "sample_index"):
-            raise NotImplementedError(
-                "samplers must implement sample_index(ann) (see annchor_b200.plugins): the reference "
-                "protocol sample(features, ...) needs the materialised Theta(N^2) feature array")
+            if not hasattr(self.sampler, "sample"):
+                raise NotImplementedError("samplers must implement sample_index(ann) or the reference "
+                                          "protocol sample(features, feature_names, n_samples, "
+                                          "not_computed_mask, random_seed)")
+            # reference-protocol sampler (annchor/samplers.py:75-110): materialised view
+            self.sampler = plugins.MaterialisedSamplerAdapter(self.sampler)
         self.random_seed = random_seed
         self.verbose = verbose
         self.locality = locality
@@ -251,6 +298,7 @@ class Annchor:
         self.backend = backend
         self.feature_names = list(FEATURE_NAMES)
         self.ctx = ctx or default_context(device)
+        self._cost = cost
         # _dataset: an already-uploaded annchor_b200.Dataset of X (skips the host-to-device copy)
         self._dataset = _dataset if _dataset is not None else Dataset(self.ctx, X, func, cost_matrix=cost)
         self._plug = GpuExactIJs(func, self.ctx, cost)
@@ -275,6 +323,10 @@ class Annchor:
             self._xchg = IndexExchange(self._index, comm)
         self._D = None
         self.stage_times = {}
+        # _trace: a dict that receives per-stage results (sample, thresholds, selected / look-ahead
+        # sets, ...) -- used by the stage-parity tests; costs device-to-host copies, off by default
+        self._trace = _trace
+        self._it = 0
 
     # -- stage 1 -----------------------------------------------------------------------------
     def get_anchors(self):
@@ -303,17 +355,23 @@ class Annchor:
         self.sample_features = np.hstack([feats, np.zeros((feats.shape[0], 1))])
         self.sample_y = self._index.eval_pairs(ijs)  # evaluates the metric and marks the pairs computed
         self.evals += self.sample_y.shape[0]
+        if self._trace is not None:
+            self._trace["sample_ijs%d" % self._it] = ijs.copy()
+            self._trace["sample_bins%d" % self._it] = np.array(bins, copy=True)
+            self._trace["sample_features%d" % self._it] = self.sample_features.copy()
 
     def fit_predict_regression(self):
         self.regression.fit(self.sample_features, self.feature_names, self.sample_y,
                             sample_bins=self.sample_bins)
         self.sample_predict = self.regression.predict(self.sample_features, self.feature_names)
+        if self._trace is not None:
+            self._trace["coef%d" % self._it] = regression_device_spec(self.regression, self.feature_names)[1]
 
     def fit_predict_errors(self):
         self.error_predictor.fit(self.sample_features, self.feature_names,
                                  self.sample_y - self.sample_predict, sample_bins=self.sample_bins)
         bins, coef, icpt = regression_device_spec(self.regression, self.feature_names)
-        errs, eptr = error_device_spec(self.error_predictor)
+        errs, eptr = error_device_spec(self.error_predictor, n_bins=bins.shape[0] - 1)
         self._index.set_model(bins, coef, icpt, errs, eptr)
 
     # -- select / refine ---------------------------------------------------------------------
@@ -327,6 +385,13 @@ class Annchor:
         n_refine = 0 if n_refine < 0 else n_refine
         self.n_refine = n_refine
         self._index.select(n_refine, self.lookahead)
+        if self._trace is not None:
+            sel, nxt = self._index.get_selected()
+            self._trace["thresh%d" % it] = self._index.get_thresh()
+            self._trace["selected%d" % it] = sel
+            self._trace["next%d" % it] = nxt
+            if it == 0:
+                self._trace["n_forced"] = self.n_forced
         n_eval = self._index.refine_selected()
         if self._xchg is not None:  # every rank evaluated its own share: make all stores identical
             self._xchg.refined()
@@ -338,6 +403,8 @@ class Annchor:
         if self._xchg is not None:
             self._xchg.tightened()
             self.n_tightened = self.comm.all_reduce_sum(self.n_tightened)
+        if self._trace is not None:
+            self._trace["n_tightened%d" % self._it] = self.n_tightened
 
     def get_ann(self):
         self.neighbor_graph = self._index.neighbor_graph()
@@ -360,6 +427,7 @@ class Annchor:
         stage("get_locality", self.get_locality)
         niters = self.niters
         for it in range(niters):
+            self._it = it
             try:
                 stage("get_sample", self.get_sample)
             except NothingToSample as err:

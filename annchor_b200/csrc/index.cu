@@ -284,6 +284,21 @@ __global__ void pair_features_kernel(View V, const int32_t *__restrict__ I,
     }
 }
 
+// store entry of explicit pairs: kind (0 none, 1 known, 2 tightened, 3 forced) and its two values
+__global__ void pair_state_kernel(View V, const int32_t *__restrict__ I, const int32_t *__restrict__ J,
+                                  int64_t m, int32_t *__restrict__ kind, float *__restrict__ ab /* (m,2) */)
+{
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < m;
+         p += (int64_t)gridDim.x * blockDim.x) {
+        const int i = I[p], j = J[p];
+        const uint32_t lo = i < j ? i : j, hi = i < j ? j : i;
+        float a = 0.0f, b = 0.0f;
+        kind[p] = i == j ? 0 : (int32_t)hash_lookup(V, pair_key(lo, hi), a, b);
+        ab[2 * p] = a;
+        ab[2 * p + 1] = b;
+    }
+}
+
 // ---- selection over the emitted list -----------------------------------------------------------
 // block-wide exclusive scan of a packed pair of 16-bit counts (lo | hi << 16); returns this
 // thread's exclusive prefix and the block total (256 threads, each count <= 8 per half)
@@ -1389,6 +1404,30 @@ ANNB_API int annb_index_pair_features(annb_index *ix, const int64_t *ij, int64_t
     return ANNB_OK;
 }
 
+ANNB_API int annb_index_pair_state(annb_index *ix, const int64_t *ij, int64_t m, int32_t *kind, double *a,
+                                   double *b)
+{
+    TraceScope _ts("annb_index_pair_state");
+    ANNB_REQUIRE(ix && (m == 0 || (ij && kind)), ANNB_EINVAL, "NULL argument");
+    if (m == 0) return ANNB_OK;
+    annb_ctx *c = ix->ctx;
+    ANNB_CUDA(cudaSetDevice(c->device));
+    ANNB_TRY(upload_pairs(ix, ij, nullptr, m));
+    ANNB_TRY(ix->t4.ensure((size_t)m * 8));
+    ANNB_TRY(ix->t5.ensure((size_t)m * 4));
+    ANNB_LAUNCH(pair_state_kernel, grid_for_n(c, m), 256, 0, c->stream, ix->view(), ix->t1.as<int32_t>(),
+                ix->t2.as<int32_t>(), m, ix->t5.as<int32_t>(), ix->t4.as<float>());
+    std::vector<float> f((size_t)m * 2);
+    ANNB_CUDA(cudaMemcpyAsync(f.data(), ix->t4.p, f.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+    ANNB_CUDA(cudaMemcpyAsync(kind, ix->t5.p, (size_t)m * 4, cudaMemcpyDeviceToHost, c->stream));
+    ANNB_CUDA(cudaStreamSynchronize(c->stream));
+    for (int64_t k = 0; k < m; ++k) {
+        if (a) a[k] = f[2 * k];
+        if (b) b[k] = f[2 * k + 1];
+    }
+    return ANNB_OK;
+}
+
 ANNB_API int annb_index_set_model(annb_index *ix, const double *bins, const double *coef,
                                   const double *icpt, int64_t nb, const double *errs,
                                   const int64_t *eptr)
@@ -2040,6 +2079,39 @@ ANNB_API int annb_index_select(annb_index *ix, int64_t n_refine, int64_t lookahe
     return ANNB_OK;
 }
 
+ANNB_API int annb_index_get_thresh(annb_index *ix, double *thresh)
+{
+    ANNB_REQUIRE(ix && thresh, ANNB_EINVAL, "NULL argument");
+    ANNB_REQUIRE(ix->have_thresh, ANNB_ESTATE, "thresholds have not been computed yet");
+    annb_ctx *c = ix->ctx;
+    ANNB_CUDA(cudaSetDevice(c->device));
+    std::vector<float> h(ix->n);
+    ANNB_CUDA(cudaMemcpyAsync(h.data(), ix->thresh.p, (size_t)ix->n * 4, cudaMemcpyDeviceToHost, c->stream));
+    ANNB_CUDA(cudaStreamSynchronize(c->stream));
+    for (int64_t i = 0; i < ix->n; ++i) thresh[i] = h[i];
+    return ANNB_OK;
+}
+
+// load a caller-chosen look-ahead set (what annb_index_select leaves behind as `next`), so that
+// annb_index_update_bounds can be driven and checked on explicit pairs
+ANNB_API int annb_index_set_lookahead(annb_index *ix, const int64_t *ij, int64_t m)
+{
+    TraceScope _ts("annb_index_set_lookahead");
+    ANNB_REQUIRE(ix && (m == 0 || ij), ANNB_EINVAL, "NULL argument");
+    annb_ctx *c = ix->ctx;
+    ANNB_CUDA(cudaSetDevice(c->device));
+    ix->n_next = 0;
+    if (m == 0) return ANNB_OK;
+    ANNB_TRY(upload_pairs(ix, ij, nullptr, m));
+    ANNB_TRY(ix->nxt_i.ensure((size_t)m * 4));
+    ANNB_TRY(ix->nxt_j.ensure((size_t)m * 4));
+    ANNB_CUDA(cudaMemcpyAsync(ix->nxt_i.p, ix->t1.p, (size_t)m * 4, cudaMemcpyDeviceToDevice, c->stream));
+    ANNB_CUDA(cudaMemcpyAsync(ix->nxt_j.p, ix->t2.p, (size_t)m * 4, cudaMemcpyDeviceToDevice, c->stream));
+    ANNB_CUDA(cudaStreamSynchronize(c->stream));
+    ix->n_next = m;
+    return ANNB_OK;
+}
+
 ANNB_API int annb_index_get_selected(annb_index *ix, int64_t *ij_sel, int64_t *ij_next)
 {
     TraceScope _ts("annb_index_get_selected");
@@ -2266,7 +2338,49 @@ ANNB_API int annb_index_neighbor_graph(annb_index *ix, int64_t *idx, double *dis
                 ix->counters.as<int32_t>());
     ANNB_CUDA(cudaMemcpyAsync(idx, ix->t0.p, (size_t)n * nn * 8, cudaMemcpyDeviceToHost, c->stream));
     ANNB_CUDA(cudaMemcpyAsync(dist, ix->t1.p, (size_t)n * nn * 8, cudaMemcpyDeviceToHost, c->stream));
+    int32_t n_deficient = 0;
+    ANNB_CUDA(cudaMemcpyAsync(&n_deficient, ix->counters.p, 4, cudaMemcpyDeviceToHost, c->stream));
     ANNB_CUDA(cudaStreamSynchronize(c->stream));
+    if (n_deficient == 0) return ANNB_OK;
+    // Rows with fewer than nn-1 computed pairs: the reference's get_nn ranks the not-computed
+    // candidates behind the computed ones by their RefineApprox (d[ncm] += max(d), utils.py:415-428)
+    // and emits the prediction.  Same here: the row sweep's second list gives, for the affected row
+    // blocks, the nn-1 smallest not-computed predictions with their ids.
+    ANNB_REQUIRE(ix->have_model, ANNB_ESTATE,
+                 "%d neighbour slots have no computed pair and no regression model is set to rank predictions",
+                 (int)n_deficient);
+    const int k2 = nn - 1;
+    std::vector<int32_t> rbs;
+    {
+        std::vector<char> bad((size_t)ix->T, 0);
+        for (int64_t r = 0; r < n; ++r)
+            if (idx[r * nn + nn - 1] < 0) bad[r / TILE] = 1;
+        for (int t = 0; t < ix->T; ++t)
+            if (bad[t]) rbs.push_back(t);
+    }
+    ANNB_TRY(ix->l2val.ensure((size_t)n * k2 * 4));
+    ANNB_TRY(ix->l2id.ensure((size_t)n * k2 * 4));
+    ANNB_TRY(ix->t3.ensure(rbs.size() * 4));
+    ANNB_CUDA(cudaMemcpyAsync(ix->t3.p, rbs.data(), rbs.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    ANNB_TRY(run_thresh_rows(ix, k2, 1, nullptr, ix->t3.as<int32_t>(), (int)rbs.size()));
+    ix->have_thresh = false;  // the sweep overwrote the thresholds of those row blocks
+    std::vector<float> lv((size_t)n * k2);
+    std::vector<int32_t> li((size_t)n * k2);
+    ANNB_CUDA(cudaMemcpyAsync(lv.data(), ix->l2val.p, lv.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+    ANNB_CUDA(cudaMemcpyAsync(li.data(), ix->l2id.p, li.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+    ANNB_CUDA(cudaStreamSynchronize(c->stream));
+    for (int64_t r = 0; r < n; ++r) {
+        if (idx[r * nn + nn - 1] >= 0) continue;
+        int col = 1;
+        while (col < nn && idx[r * nn + col] >= 0) ++col;
+        for (int q = 0; col < nn && q < k2; ++q) {
+            const int32_t id = li[(size_t)r * k2 + q];
+            if (id < 0) break;  // fewer candidates than neighbours asked for
+            idx[r * nn + col] = id;
+            dist[r * nn + col] = (double)lv[(size_t)r * k2 + q];
+            ++col;
+        }
+    }
     return ANNB_OK;
 }
 

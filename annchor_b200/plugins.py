@@ -34,6 +34,33 @@ class MaxMinAnchorPicker:
         return A, None, ann.n_anchors * ann.nx
 
 
+class ExternalAnchorPicker:
+    """annchor/pickers.py:55-83: the anchors are items that need not belong to X.  Returns an empty
+    ``A`` like the reference, so no pair is pre-marked as computed.  The distances X -> anchors are
+    evaluated on the device over a temporary data set holding X followed by the anchor items."""
+
+    def __init__(self, A):
+        self.A = A
+        self.is_anchor_safe = False
+
+    def get_anchors(self, ann):
+        from .core import Dataset
+        nx, na = ann.nx, ann.n_anchors
+        items = list(self.A)[:na]
+        if len(items) != na:
+            raise ValueError("ExternalAnchorPicker needs n_anchors=%d items, got %d" % (na, len(items)))
+        if isinstance(ann.X, np.ndarray) and ann.X.dtype.kind not in "US":
+            both = np.concatenate([np.asarray(ann.X), np.asarray(items, dtype=ann.X.dtype).reshape(na, -1)])
+        else:
+            both = list(ann.X) + items
+        tmp = Dataset(ann.ctx, both, ann.f, cost_matrix=ann._cost)
+        try:
+            D = tmp.anchor_dists(np.arange(nx, nx + na, dtype=np.int64))[:nx]
+        finally:
+            tmp.close()
+        return np.array([], dtype=np.int64), np.ascontiguousarray(D), na * nx
+
+
 class SelectedAnchorPicker:
     """annchor/pickers.py:86-107: anchors given as indices into X."""
 
@@ -183,8 +210,58 @@ class SimpleStratifiedSampler:
         if n_samples != sel.shape[0]:
             print("Warning: Some bins contained fewer samples than requested")
         sample_ijs = np.ascontiguousarray(ijs[sel])
-        feats = host_features(ann.D, sample_ijs) if exact else ix.pair_features(sample_ijs)
+        if exact:
+            # float64 anchor bounds, overlaid with the bounds update_anchor_points has tightened:
+            # the reference trains on features[sample_ixs], which carry them (annchor.py:338,503-510)
+            feats = host_features(ann.D, sample_ijs)
+            kind, a, b = ix.pair_state(sample_ijs)
+            t = kind == 2
+            feats[t, 0] = np.maximum(feats[t, 0], a[t])
+            feats[t, 1] = np.minimum(feats[t, 1], b[t])
+        else:
+            feats = ix.pair_features(sample_ijs)
         return sample_ijs, feats, bins
+
+
+MATERIALISED_LIMIT = 20_000_000  # not-computed candidate pairs a reference-protocol sampler may see
+
+
+class MaterialisedSamplerAdapter:
+    """Serves a reference-protocol sampler -- ``sample(features, feature_names, n_samples,
+    not_computed_mask, random_seed) -> (sample_ixs, n_actual, sample_bins)`` (annchor/samplers.py:75-110;
+    the reference's own SimpleStratifiedSampler / ClusterSampler instances qualify) -- from a
+    materialised view of the not-computed candidate pairs: rows in the reference's IJs order
+    (sorted by (i, j)), columns [lb, ub, dad, is_anchor=0] in the sweeps' float32 arithmetic
+    including tightened bounds.  Limited to MATERIALISED_LIMIT pairs (the reference itself needs
+    ~200 B of host memory per candidate pair)."""
+
+    def __init__(self, sampler):
+        self.sampler = sampler
+
+    def sample_index(self, ann):
+        ix = ann._index
+        n_nc = ix.stats()["n_not_computed"]
+        if n_nc > MATERIALISED_LIMIT:
+            raise NotImplementedError(
+                "%d not-computed candidate pairs: a sampler with the reference protocol sample(features, ...) "
+                "needs them materialised (limit %d).  Use a sample_index(ann) sampler "
+                "(annchor_b200.plugins.SimpleStratifiedSampler) at this size." % (n_nc, MATERIALISED_LIMIT))
+        n_pool, n_nc, exact = ix.sample_pool(int(ann.random_seed), max(n_nc + 1024, 1024))
+        if n_pool == 0:
+            raise NothingToSample()
+        ijs, _ = ix.get_pool()
+        ijs = ijs[np.argsort(ijs[:, 0] * np.int64(ann.nx) + ijs[:, 1], kind="stable")]
+        feats = np.zeros((n_pool, 4))
+        feats[:, :3] = ix.pair_features(ijs)
+        try:
+            sample_ixs, _n, bins = self.sampler.sample(feats, list(FEATURE_NAMES), ann.n_samples,
+                                                       np.ones(n_pool, dtype=bool), ann.random_seed)
+        except Exception as e:  # the reference raises its own NothingToSample class
+            if type(e).__name__ == "NothingToSample":
+                raise NothingToSample() from e
+            raise
+        sample_ixs = np.asarray(sample_ixs, dtype=np.int64)
+        return np.ascontiguousarray(ijs[sample_ixs]), feats[sample_ixs, :3], np.asarray(bins, dtype=np.float64)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -308,11 +385,15 @@ class SimpleStratifiedErrorRegression:
         return labels
 
 
-def error_device_spec(ep):
+def error_device_spec(ep, n_bins=None):
     """(errs_flat, eptr) of a fitted error predictor (ours or annchor/error_predictors.py:47-54)."""
     if not hasattr(ep, "errs"):
         raise NotImplementedError("error predictors must expose per-bin sorted error tables `.errs`")
     nb = len(ep.errs)
+    if n_bins is not None and nb != n_bins:
+        raise ValueError("the error predictor has %d bins, the regression %d: the device scores with one "
+                         "partition for both (annchor/annchor.py:150-161 builds both from the sampler's bins)"
+                         % (nb, n_bins))
     tabs = [np.asarray(ep.errs[b], dtype=np.float64) for b in range(nb)]
     eptr = np.zeros(nb + 1, dtype=np.int64)
     np.cumsum([len(t) for t in tabs], out=eptr[1:])

@@ -174,6 +174,11 @@ int annb_index_sample_pool(annb_index *ix, uint64_t seed, int64_t max_pool, int6
 int annb_index_get_pool(annb_index *ix, int64_t *ij, double *dad);
 /* features [lb, ub, dad] of explicit pairs in the sweeps' float32 arithmetic: feat (n, 3) */
 int annb_index_pair_features(annb_index *ix, const int64_t *ij, int64_t n, double *feat);
+/* the store's entry for explicit pairs: kind[p] = 0 none, 1 exactly known (a = distance),
+ * 2 tightened by update_anchor_points ((a, b) = (lb, ub), annchor/annchor.py:503-510),
+ * 3 forced by guarantee_nmin (annchor/utils.py:619).  a / b may be NULL. */
+int annb_index_pair_state(annb_index *ix, const int64_t *ij, int64_t n, int32_t *kind, double *a,
+                          double *b);
 /* mark pairs as exactly computed with distance d (sample_y / refine results,
  * annchor/annchor.py:342,380,472-473) */
 int annb_index_add_known(annb_index *ix, const int64_t *ij, const double *d, int64_t n);
@@ -185,6 +190,8 @@ int annb_index_set_model(annb_index *ix, const double *bins, const double *coef,
 /* thresh (annchor/annchor.py:399-404) over RefineApprox = exact where known else clipped
  * prediction; thresh float64[n] out (may be NULL; kept on device for select) */
 int annb_index_row_thresh(annb_index *ix, double *thresh);
+/* the thresholds of the last annb_index_row_thresh / annb_index_guarantee_nmin, float64[n] */
+int annb_index_get_thresh(annb_index *ix, double *thresh);
 /* guarantee_nmin (annchor/utils.py:606-621) with nmin = 3*nn//2; returns # forced pairs */
 int annb_index_guarantee_nmin(annb_index *ix, int64_t nmin, int64_t *n_forced);
 /* select_refine_candidate_pairs scoring + choice (annchor/annchor.py:416-465): picks the
@@ -195,6 +202,10 @@ int annb_index_select(annb_index *ix, int64_t n_refine, int64_t lookahead, int64
                       int64_t *n_next);
 /* copy the selected / look-ahead pairs to the host ((n,2) int64) */
 int annb_index_get_selected(annb_index *ix, int64_t *ij_sel, int64_t *ij_next);
+/* replace the look-ahead set (`nextback`, annchor/annchor.py:457,462) by caller-chosen pairs:
+ * lets annb_index_update_bounds be driven -- and checked against the reference's
+ * update_anchor_points -- on an explicit pair list */
+int annb_index_set_lookahead(annb_index *ix, const int64_t *ij, int64_t n);
 /* evaluate the metric on the selected pairs and mark them known (annchor/annchor.py:467-473) */
 int annb_index_refine_selected(annb_index *ix, int64_t *n_evals);
 /* update_anchor_points (annchor/annchor.py:475-512) on the look-ahead pairs */

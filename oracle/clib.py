@@ -38,6 +38,9 @@ def lib():
         L.orc_row_kth.argtypes = [_P, _P, _P, _I, _I, _P]
         L.orc_probs.argtypes = [_P, _P, _I, _P, _P, _P]
         L.orc_get_nn.argtypes = [_I, _I, _P, _P, _P, _P, _P, _P, _P]
+        L.orc_f32_features.argtypes = [_P, _I, _P, _I, _P, _P, _P, _P]
+        L.orc_f32_predict.argtypes = [_P, _P, _P, _I, _P, _P, _P, _P, _P]
+        L.orc_f32_update_bounds.argtypes = [_P, _I, _P, _P, _P, _P, _P]
         L.orc_mt_state_size.restype = C.c_size_t
         L.orc_mt_seed.argtypes = [_P, C.c_uint32]
         L.orc_numba_shuffle.argtypes = [_P, _P, _I]

@@ -426,3 +426,80 @@ API void orc_numba_shuffle(mt_t *s, int64_t *x, int64_t n)
         x[j] = t;
     }
 }
+
+/* ------------------------------------------------------------------ */
+/* Device-arithmetic mode (oracle/devmode.py).  The CUDA sweeps compute  */
+/* the same quantities as annchor/utils.py:274-301,355-380 and           */
+/* annchor/regressors.py:71-103 + annchor/annchor.py:359-363, but in      */
+/* float32 from a float32 copy of D and with a fused multiply-add chain.  */
+/* These restate that arithmetic operation for operation (IEEE float32,  */
+/* fmaf correctly rounded) so stage outputs can be compared for equality. */
+/* ------------------------------------------------------------------ */
+
+/* lb = max_a |D[i,a] - D[j,a]|, ub = min_a (D[i,a] + D[j,a]), s2 = D[i,cA[j]] + D[j,cA[i]] (= 2 dad) */
+API void orc_f32_features(const int64_t *ij, int64_t n, const float *D, int64_t na,
+                          const int32_t *cA, float *lb, float *ub, float *s2)
+{
+#pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < n; ++k) {
+        const int64_t i = ij[2 * k], j = ij[2 * k + 1];
+        const float *di = D + i * na, *dj = D + j * na;
+        float lo = 0.0f, hi = INFINITY;
+        for (int64_t a = 0; a < na; ++a) {
+            const float df = fabsf(di[a] - dj[a]), sm = di[a] + dj[a];
+            if (df > lo) lo = df;
+            if (sm < hi) hi = sm;
+        }
+        lb[k] = lo;
+        ub[k] = hi;
+        s2[k] = di[cA[j]] + dj[cA[i]];
+    }
+}
+
+/* bin = #{interior doubled edges strictly below s2} ((lo, hi], regressors.py:85-87);
+ * label = #{interior doubled edges <= s2} (closed, later bins win, error_predictors.py:63-66);
+ * pred = clip(fma(lb, c0, fma(ub, c1, fma(s2, c2/2, icpt))), lb, ub).
+ * e2[8]: e2[k] = 2*edge[k] for k = 1..nb-1, +inf otherwise; cf (8,4) = (c0, c1, c2/2, icpt). */
+API void orc_f32_predict(const float *lb, const float *ub, const float *s2, int64_t n,
+                         const float *e2, const float *cf, float *pred, int8_t *bin,
+                         int8_t *label)
+{
+#pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < n; ++k) {
+        int b = 0, l = 0;
+        for (int q = 1; q < 8; ++q) {
+            b += s2[k] > e2[q];
+            l += s2[k] >= e2[q];
+        }
+        const float *c = cf + 4 * b;
+        const float y = fmaf(lb[k], c[0], fmaf(ub[k], c[1], fmaf(s2[k], c[2], c[3])));
+        pred[k] = fminf(fmaxf(y, lb[k]), ub[k]);
+        if (bin) bin[k] = (int8_t)b;
+        if (label) label[k] = (int8_t)l;
+    }
+}
+
+/* update_bounds (annchor/utils.py:304-352) in float32 over CSR lists sorted by id */
+API void orc_f32_update_bounds(const int64_t *ij, int64_t n, const int64_t *ptr,
+                               const int64_t *ids, const float *ds, float *lbo, float *ubo)
+{
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int64_t k = 0; k < n; ++k) {
+        int64_t i = ij[2 * k], j = ij[2 * k + 1];
+        int64_t p = ptr[i], pe = ptr[i + 1], q = ptr[j], qe = ptr[j + 1];
+        float ub = INFINITY, lb = 0.0f;
+        while (p < pe && q < qe) {
+            if (ids[p] < ids[q]) ++p;
+            else if (ids[p] > ids[q]) ++q;
+            else {
+                const float a = ds[p] + ds[q], b = fabsf(ds[p] - ds[q]);
+                if (a < ub) ub = a;
+                if (b > lb) lb = b;
+                ++p;
+                ++q;
+            }
+        }
+        lbo[k] = lb;
+        ubo[k] = ub;
+    }
+}
