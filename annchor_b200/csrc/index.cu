@@ -157,7 +157,6 @@ __global__ void fill_u64_kernel(uint64_t *p, int64_t n, uint64_t v)
 
 // insert / overwrite entries of the known-pair hash map and raise their flag bits
 __global__ void hash_insert_kernel(HashSlot *__restrict__ htab, uint64_t hmask,
-                                   uint32_t *__restrict__ bitmap, int T,
                                    const int32_t *__restrict__ I, const int32_t *__restrict__ J,
                                    const float *__restrict__ a, const float *__restrict__ b,
                                    uint32_t kind, int64_t m)
@@ -187,9 +186,36 @@ __global__ void hash_insert_kernel(HashSlot *__restrict__ htab, uint64_t hmask,
             }
             h = (h + 1) & hmask;
         }
+    }
+}
+
+// ---- per-tile lists of the store's entries (what the sweeps read; see sweep.cuh) ----------------
+__global__ void tl_count_kernel(const HashSlot *__restrict__ htab, uint64_t cap, int T, int32_t *__restrict__ cnt)
+{
+    for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s < cap;
+         s += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t k = htab[s].key;
+        if (k == HKEY_EMPTY || kind_of(k) == KIND_NONE) continue;
+        const uint64_t key = k & HKEY_MASK;
+        const uint32_t lo = (uint32_t)(key >> 32), hi = (uint32_t)(key & 0xffffffffu);
+        atomicAdd(&cnt[tile_index((int)(lo >> 7), (int)(hi >> 7), T)], 1);
+    }
+}
+__global__ void tl_fill_kernel(const HashSlot *__restrict__ htab, uint64_t cap, int T,
+                               const long long *__restrict__ ptr, int32_t *__restrict__ cursor,
+                               uint32_t *__restrict__ code, float *__restrict__ a, float *__restrict__ b)
+{
+    for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s < cap;
+         s += (uint64_t)gridDim.x * blockDim.x) {
+        const HashSlot e = htab[s];
+        if (e.key == HKEY_EMPTY || kind_of(e.key) == KIND_NONE) continue;
+        const uint64_t key = e.key & HKEY_MASK;
+        const uint32_t lo = (uint32_t)(key >> 32), hi = (uint32_t)(key & 0xffffffffu);
         const int64_t t = tile_index((int)(lo >> 7), (int)(hi >> 7), T);
-        const int r = lo & 127, c = hi & 127;
-        atomicOr(&bitmap[t * BITMAP_WORDS + r * 4 + (c >> 5)], 1u << (c & 31));
+        const long long p = ptr[t] + atomicAdd(&cursor[t], 1);
+        code[p] = ((lo & 127u) << 9) | ((hi & 127u) << 2) | kind_of(e.key);
+        a[p] = e.a;
+        b[p] = e.b;
     }
 }
 
@@ -961,7 +987,11 @@ struct annb_index {
     DevBuf A_dev, D64, D32, Dpm, meta, scratch;
     int dpitch = 32;
     // known-pair store
-    DevBuf htab, bitmap;
+    DevBuf htab;
+    // per-tile entry lists derived from the hash map (rebuilt lazily before a sweep)
+    DevBuf tl_ptr, tl_cnt, tl_code, tl_a, tl_b;
+    bool tl_dirty = false;
+    int64_t tl_entries = 0;
     uint64_t hcap = 0;
     int64_t hcount_ub = 0;  // upper bound on occupied slots
     // model
@@ -1033,7 +1063,10 @@ struct annb_index {
         V.meta = meta.as<PointMeta>();
         V.htab = htab.as<HashSlot>();
         V.hmask = hcap - 1;
-        V.bitmap = bitmap.as<uint32_t>();
+        V.tl_ptr = tl_ptr.as<long long>();
+        V.tl_code = tl_code.as<uint32_t>();
+        V.tl_a = tl_a.as<float>();
+        V.tl_b = tl_b.as<float>();
         return V;
     }
     int64_t n_not_computed() const { return n_candidates - n_anchor_pairs - n_known; }
@@ -1085,8 +1118,37 @@ static int hash_insert(annb_index *ix, const int32_t *I, const int32_t *J, const
     annb_ctx *c = ix->ctx;
     ANNB_TRY(hash_reserve(ix, m));
     ANNB_LAUNCH(hash_insert_kernel, grid_for_n(c, m), 256, 0, c->stream, ix->htab.as<HashSlot>(),
-                ix->hcap - 1, ix->bitmap.as<uint32_t>(), ix->T, I, J, a, b, kind, m);
+                ix->hcap - 1, I, J, a, b, kind, m);
     ix->hcount_ub += m;
+    ix->tl_dirty = true;
+    return ANNB_OK;
+}
+
+// bring the per-tile entry lists up to date with the hash map (count, scan, fill: two streaming
+// passes over the table)
+static int tile_lists_rebuild(annb_index *ix)
+{
+    if (!ix->tl_dirty) return ANNB_OK;
+    TraceScope _ts("  tile_lists_rebuild");
+    annb_ctx *c = ix->ctx;
+    const int64_t NT = ix->NT;
+    ANNB_TRY(ix->tl_cnt.ensure((size_t)(NT + 1) * 4));
+    ANNB_CUDA(cudaMemsetAsync(ix->tl_cnt.p, 0, (size_t)(NT + 1) * 4, c->stream));
+    ANNB_LAUNCH(tl_count_kernel, grid_for_n(c, (int64_t)ix->hcap), 256, 0, c->stream, ix->htab.as<HashSlot>(),
+                ix->hcap, ix->T, ix->tl_cnt.as<int32_t>());
+    ANNB_TRY(launch_scan_i32_i64(c, ix->tl_cnt.as<int32_t>(), ix->tl_ptr.as<int64_t>(), NT, ix->scan_tmp));
+    int64_t total = 0;
+    ANNB_CUDA(cudaMemcpyAsync(&total, ix->tl_ptr.as<int64_t>() + NT, 8, cudaMemcpyDeviceToHost, c->stream));
+    ANNB_CUDA(cudaStreamSynchronize(c->stream));
+    ix->tl_entries = total;
+    ANNB_TRY(ix->tl_code.ensure((size_t)(total + 64) * 4));
+    ANNB_TRY(ix->tl_a.ensure((size_t)(total + 64) * 4));
+    ANNB_TRY(ix->tl_b.ensure((size_t)(total + 64) * 4));
+    ANNB_CUDA(cudaMemsetAsync(ix->tl_cnt.p, 0, (size_t)(NT + 1) * 4, c->stream));
+    ANNB_LAUNCH(tl_fill_kernel, grid_for_n(c, (int64_t)ix->hcap), 256, 0, c->stream, ix->htab.as<HashSlot>(),
+                ix->hcap, ix->T, ix->tl_ptr.as<long long>(), ix->tl_cnt.as<int32_t>(), ix->tl_code.as<uint32_t>(),
+                ix->tl_a.as<float>(), ix->tl_b.as<float>());
+    ix->tl_dirty = false;
     return ANNB_OK;
 }
 
@@ -1137,7 +1199,10 @@ ANNB_API int annb_index_create(annb_ctx *c, const annb_dataset *ds, int metric,
         ix->dpitch = (ix->na + 31) / 32 * 32;
         if ((rc = ix->Dpm.ensure((size_t)ix->npad * ix->dpitch * 4))) break;
         if ((rc = ix->meta.ensure((size_t)ix->npad * sizeof(PointMeta)))) break;
-        if ((rc = ix->bitmap.ensure((size_t)ix->NT * BITMAP_WORDS * 4))) break;
+        if ((rc = ix->tl_ptr.ensure((size_t)(ix->NT + 1) * 8))) break;
+        if ((rc = ix->tl_code.ensure(256))) break;
+        if ((rc = ix->tl_a.ensure(256))) break;
+        if ((rc = ix->tl_b.ensure(256))) break;
         if ((rc = ix->thresh.ensure((size_t)ix->npad * 4))) break;
         if ((rc = ix->counters.ensure(256))) break;
         if ((rc = ix->tiehist.ensure(65536 * 4))) break;
@@ -1146,7 +1211,7 @@ ANNB_API int annb_index_create(annb_ctx *c, const annb_dataset *ds, int metric,
         annb_index_destroy(ix);
         return rc;
     }
-    ANNB_CUDA(cudaMemsetAsync(ix->bitmap.p, 0, (size_t)ix->NT * BITMAP_WORDS * 4, c->stream));
+    ANNB_CUDA(cudaMemsetAsync(ix->tl_ptr.p, 0, (size_t)(ix->NT + 1) * 8, c->stream));  // every tile list empty
     ANNB_TRY(hash_alloc(ix, 1 << 16));
     *out = ix;
     return ANNB_OK;
@@ -1169,7 +1234,7 @@ ANNB_API int annb_index_destroy(annb_index *ix)
     if (!ix) return ANNB_OK;
     cudaSetDevice(ix->ctx->device);
     cudaStreamSynchronize(ix->ctx->stream);
-    DevBuf *all[] = {&ix->A_dev, &ix->D64, &ix->D32, &ix->Dpm, &ix->meta, &ix->scratch, &ix->htab, &ix->bitmap,
+    DevBuf *all[] = {&ix->A_dev, &ix->D64, &ix->D32, &ix->Dpm, &ix->meta, &ix->scratch, &ix->htab, &ix->tl_ptr, &ix->tl_cnt, &ix->tl_code, &ix->tl_a, &ix->tl_b,
                      &ix->errs_dev, &ix->rank_dev, &ix->thresh, &ix->l2val, &ix->l2id, &ix->hist,
                      &ix->counters, &ix->emit_key, &ix->emit_lvl, &ix->sel_i, &ix->sel_j, &ix->nxt_i,
                      &ix->nxt_j, &ix->tiehist, &ix->tiekeys, &ix->pool_key, &ix->pool_dad, &ix->t0,
@@ -1493,6 +1558,7 @@ ANNB_API int annb_index_set_model(annb_index *ix, const double *bins, const doub
 static int run_thresh_rows(annb_index *ix, int k2, int col_stride, float *cut2, const int32_t *rb_list, int n_rb)
 {
     annb_ctx *c = ix->ctx;
+    ANNB_TRY(tile_lists_rebuild(ix));
     ThreshArgs A;
     A.V = ix->view();
     A.M = ix->model;
@@ -1573,6 +1639,7 @@ static int run_thresh(annb_index *ix, int k2)
         ANNB_TRY(ix->trec.ensure((size_t)n * R * 8));
         ANNB_TRY(ix->tcnt.ensure((size_t)n * 4));
         ANNB_CUDA(cudaMemsetAsync(ix->tcnt.p, 0, (size_t)n * 4, c->stream));
+        ANNB_TRY(tile_lists_rebuild(ix));
         ThreshPairArgs P;
         P.V = ix->view();
         P.M = ix->model;
@@ -1769,6 +1836,7 @@ static int run_score(annb_index *ix, int floor_level, uint64_t floor_mix_thr, in
                      int64_t emit_cap, std::vector<uint64_t> &hist, unsigned long long cnt[5])
 {
     annb_ctx *c = ix->ctx;
+    ANNB_TRY(tile_lists_rebuild(ix));
     ScoreArgs A;
     A.V = ix->view();
     A.M = ix->model;
@@ -2157,6 +2225,7 @@ ANNB_API int annb_index_refine_selected(annb_index *ix, int64_t *n_evals)
         ANNB_LAUNCH(hash_retire_forced_kernel, grid_for_n(c, (int64_t)ix->hcap), 256, 0, c->stream,
                     ix->htab.as<HashSlot>(), ix->hcap);
         ix->has_forced = false;
+        ix->tl_dirty = true;
     }
     ix->n_sel = 0;
     return ANNB_OK;
@@ -2425,6 +2494,7 @@ ANNB_API int annb_index_sample_pool(annb_index *ix, uint64_t seed, int64_t max_p
     ix->n_pool = 0;
     *n_pool = 0;
     if (n_nc <= 0) return ANNB_OK;
+    ANNB_TRY(tile_lists_rebuild(ix));
     SampleArgs A;
     A.V = ix->view();
     A.seed = (uint32_t)(mix64(seed) >> 32);

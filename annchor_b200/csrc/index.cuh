@@ -4,7 +4,7 @@
 // errors, masks (annchor/annchor.py:258-303,345-393) -- Theta(N^2) host memory.  Here the only
 // per-pair state is what was actually measured or tightened:
 //   * a hash map  pair -> {exact distance | tightened (lb, ub) | forced}, 16 B per slot   (HBM)
-//   * a bit per pair "has an entry", blocked per 128x128 tile (2 KB per tile)               (HBM)
+//   * the same entries listed per 128x128 tile (12 B each), which is what the sweeps read  (HBM)
 // Everything else (bounds, dad, prediction, label, probability) is re-derived inside the tile
 // sweeps from the anchor-distance matrix D (n_anchors x N float32, anchor-major) staged in
 // shared memory.
@@ -16,7 +16,7 @@ namespace annb {
 constexpr int TILE = 128;        // points per tile side
 constexpr int SROW = 132;        // shared-memory row stride in floats (128 + 4: keeps 16 B alignment,
                                  // spreads the dad look-ups D[i][cA[j]] over banks)
-constexpr int BITMAP_WORDS = TILE * TILE / 32;  // 512 words = 2 KB per tile
+constexpr int BITMAP_WORDS = TILE * TILE / 32;  // 512 words = 2 KB: a tile's flag bitmap (shared memory only)
 constexpr int MAX_BINS = 8;
 constexpr int MAX_LIST = 64;     // longest per-row sorted list the thresh sweep keeps
 
@@ -65,7 +65,10 @@ struct View {
     const PointMeta *meta;     // npad
     const HashSlot *htab;
     uint64_t hmask;            // capacity - 1
-    const uint32_t *bitmap;    // upper-triangular tiles x BITMAP_WORDS
+    // per-tile lists of the store's entries (rebuilt from the hash map after every insert batch)
+    const long long *tl_ptr;   // [NT + 1] upper-triangular tiles, row-major (tile_index)
+    const uint32_t *tl_code;   // r << 9 | c << 2 | kind
+    const float *tl_a, *tl_b;  // KNOWN: a = distance; TIGHT: (a, b) = (lb, ub)
 };
 
 __host__ __device__ __forceinline__ int64_t tile_index(int ti, int tj, int T)

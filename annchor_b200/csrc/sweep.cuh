@@ -64,29 +64,139 @@ __device__ __forceinline__ void load_point_tile(const View &V, int t, float *sD,
     }
     if (tid < TILE) cp_async16(sM + tid, V.meta + (int64_t)t * TILE + tid);
 }
-__device__ __forceinline__ void load_bitmap_tile(const View &V, int ti, int tj, uint32_t *sB)
+__device__ __forceinline__ void cp_async4(void *smem, const void *gmem)
 {
-    const int lo = ti < tj ? ti : tj, hi = ti < tj ? tj : ti;
-    const uint32_t *src = V.bitmap + tile_index(lo, hi, V.T) * BITMAP_WORDS;
-    const int tid = threadIdx.x;
-    if (tid >= 128) cp_async16(sB + (tid - 128) * 4, src + (tid - 128) * 4);
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
+{
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem) : "memory");
 }
 
-// Pull the hash slots of a tile's flagged pairs into L2 while the tile's phase 1 runs: the canonical
-// bitmap tile (rows = lower endpoint) is in shared memory, every thread walks the set bits of two
-// words.  Phase 2's look-ups for known / tightened pairs then hit L2 instead of DRAM.
-__device__ __forceinline__ void prefetch_flagged(const View &V, const uint32_t *sB, int tlo, int thi)
+// ---- per-tile store entries -------------------------------------------------------------------
+// Every pair with a store entry (exactly known / tightened / forced) is listed once, in the list of
+// the upper-triangular tile that holds it: code = r << 9 | c << 2 | kind (r, c = local index of the
+// lower / higher endpoint) plus the two values in parallel arrays.  A sweep stages the codes of its
+// tile next to the anchor-distance rows, scatters them into a 128 x 128 flag bitmap in shared memory
+// and indexes them by bit rank (rowbase + popcount), so phase 2 finds a flagged pair's entry without
+// any search: no Theta(N^2) bitmap in HBM, no random hash probes in the sweeps.
+constexpr int TL_CAP = 1024;  // entries staged per tile; larger tiles take their flags from the global list
+                              // and their values from the hash map (small N with a large p_work)
+
+struct TileDesc {  // [base, end) of a tile's entries in the global lists
+    long long base, end;
+};
+
+struct TileStore {
+    uint32_t *bm;         // [BITMAP_WORDS] flags, canonical orientation (row = lower endpoint)
+    uint16_t *rowbase;    // [TILE] set bits in the rows above
+    uint16_t *perm;       // [TL_CAP] bit rank -> entry
+    const uint32_t *codes;  // staged codes of this tile
+    long long base;
+    int cnt;
+    bool staged;          // cnt <= TL_CAP
+    bool clean;           // bm is all zero
+};
+
+// asynchronously fetch the descriptor of upper-triangular tile t (two 8-byte copies)
+__device__ __forceinline__ void load_tile_desc(const View &V, int64_t t, TileDesc *d)
 {
-    for (int w = threadIdx.x; w < BITMAP_WORDS; w += blockDim.x) {
-        uint32_t bits = sB[w];
-        const uint32_t lo = (uint32_t)(tlo * TILE + (w >> 2)), hi0 = (uint32_t)(thi * TILE + (w & 3) * 32);
-        while (bits) {
-            const int b = __ffs(bits) - 1;
-            bits &= bits - 1;
-            const uint64_t h = mix64(pair_key(lo, hi0 + b)) & V.hmask;
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(V.htab + h));
-        }
+    if (threadIdx.x == 0) {
+        cp_async8(&d->base, V.tl_ptr + t);
+        cp_async8(&d->end, V.tl_ptr + t + 1);
     }
+}
+// asynchronously stage the codes of a tile whose descriptor is already in shared memory
+__device__ __forceinline__ void load_tile_codes(const View &V, const TileDesc &d, uint32_t *codes)
+{
+    const long long cnt = d.end - d.base;
+    if (cnt > TL_CAP) return;
+    for (int e = threadIdx.x; e < (int)cnt; e += blockDim.x) cp_async4(codes + e, V.tl_code + d.base + e);
+}
+
+// `bf` is the flag bitmap phase 1 reads.  Upper-triangle sweeps pass bf == ts.bm (mode 0).  A row sweep
+// keeps a separate row-oriented copy: mode 1 = transposed (row tile below the column tile), 2 = both
+// orientations (diagonal tile), 3 = same orientation (row tile above the column tile).
+__device__ __forceinline__ void build_tile_store(const View &V, TileStore &ts, const TileDesc &d,
+                                                 const uint32_t *codes, uint32_t *bf, int mode)
+{
+    const int tid = threadIdx.x;
+    const int cnt = (int)(d.end - d.base);
+    ts.base = d.base;
+    ts.cnt = cnt;
+    ts.codes = codes;
+    ts.staged = cnt <= TL_CAP;
+    if (cnt == 0 && ts.clean) return;  // nothing flagged here and the bitmaps are already zero
+    const bool sep = bf != ts.bm;
+    for (int k = tid; k < BITMAP_WORDS; k += blockDim.x) {
+        ts.bm[k] = 0;
+        if (sep) bf[k] = 0;
+    }
+    __syncthreads();
+    ts.clean = cnt == 0;
+    if (cnt == 0) return;
+    for (int e = tid; e < cnt; e += blockDim.x) {
+        const uint32_t code = ts.staged ? codes[e] : __ldg(V.tl_code + d.base + e);
+        const int r = code >> 9, c = (code >> 2) & 127;
+        atomicOr(&ts.bm[r * 4 + (c >> 5)], 1u << (c & 31));
+        if (mode == 1 || mode == 2) atomicOr(&bf[c * 4 + (r >> 5)], 1u << (r & 31));
+        if (mode == 2 || mode == 3) atomicOr(&bf[r * 4 + (c >> 5)], 1u << (c & 31));
+    }
+    __syncthreads();
+    if (!ts.staged) return;
+    // rowbase = exclusive prefix of the per-row popcounts (threads 0..127, one row each)
+    __shared__ int s_wsum[4];
+    int mine = 0, incl = 0;
+    if (tid < TILE) {
+        const uint4 w = *reinterpret_cast<const uint4 *>(ts.bm + tid * 4);
+        mine = __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
+        incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((tid & 31) >= o) incl += y;
+        }
+        if ((tid & 31) == 31) s_wsum[tid >> 5] = incl;
+    }
+    __syncthreads();
+    if (tid < TILE) {
+        int off = 0;
+        for (int q = 0; q < (tid >> 5); ++q) off += s_wsum[q];
+        ts.rowbase[tid] = (uint16_t)(off + incl - mine);
+    }
+    __syncthreads();
+    for (int e = tid; e < cnt; e += blockDim.x) {
+        const uint32_t code = codes[e];
+        const int r = code >> 9, c = (code >> 2) & 127, w = c >> 5;
+        const uint32_t *row = ts.bm + r * 4;
+        int rho = ts.rowbase[r] + __popc(row[w] & ((1u << (c & 31)) - 1u));
+        rho += (w > 0 ? __popc(row[0]) : 0) + (w > 1 ? __popc(row[1]) : 0) + (w > 2 ? __popc(row[2]) : 0);
+        ts.perm[rho] = (uint16_t)e;
+    }
+    __syncthreads();
+    // pull the values of this tile's entries into L2 while phase 1 runs (one line per 32 entries)
+    for (int e = tid * 32; e < cnt; e += blockDim.x * 32) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(V.tl_a + d.base + e));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(V.tl_b + d.base + e));
+    }
+}
+
+// store entry of a FLAGGED pair: (r, c) = local index of its lower / higher endpoint
+__device__ __forceinline__ uint32_t store_lookup(const View &V, const TileStore &ts, int r, int c, uint32_t glo,
+                                                 uint32_t ghi, float &a, float &b)
+{
+    if (!ts.staged) return hash_lookup(V, pair_key(glo, ghi), a, b);
+    const uint32_t *row = ts.bm + r * 4;
+    const int w = c >> 5;
+    int rho = ts.rowbase[r] + __popc(row[w] & ((1u << (c & 31)) - 1u));
+    rho += (w > 0 ? __popc(row[0]) : 0) + (w > 1 ? __popc(row[1]) : 0) + (w > 2 ? __popc(row[2]) : 0);
+    const int e = ts.perm[rho];
+    const uint32_t kind = ts.codes[e] & 3u;
+    a = __ldg(V.tl_a + ts.base + e);
+    b = kind == KIND_TIGHT ? __ldg(V.tl_b + ts.base + e) : 0.0f;
+    return kind;
 }
 
 __device__ __forceinline__ int micro_off(int t4, int k)  // local index of the k-th of 8 rows/cols
@@ -227,21 +337,6 @@ __device__ __forceinline__ void flag_words(const uint32_t *sB, int row, int tx, 
     w1 = sB[row * 4 + 2 + (tx >> 3)] >> ((tx & 7) * 4);
 }
 
-// transpose a 128 x 128 bit tile (rows x 4 words) inside shared memory: dst[c][r] = src[r][c]
-__device__ __forceinline__ void transpose_bitmap(const uint32_t *src, uint32_t *dst)
-{
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    for (int combo = warp; combo < 16; combo += nwarps) {
-        const int w = combo >> 2, q = combo & 3;  // source rows 32w..32w+31, source column word q
-        const uint32_t x = src[(w * 32 + lane) * 4 + q];
-#pragma unroll 4
-        for (int k = 0; k < 32; ++k) {
-            const uint32_t m = __ballot_sync(0xffffffffu, (x >> k) & 1u);
-            if (lane == 0) dst[(q * 32 + k) * 4 + w] = m;
-        }
-    }
-}
-
 // append one micro-tile row's survivors (bit c of km = column c survives) to the warp queue: one
 // shared-memory atomic per thread that has any, then predicated 128-bit stores
 __device__ __forceinline__ void stage_row(Survivor *q, int *qcnt, const float (&lb)[8], const float (&ub)[8],
@@ -269,11 +364,9 @@ __device__ __forceinline__ bool is_candidate(const PointMeta &a, const PointMeta
     return __popcll(a.amask & b.amask) >= t;
 }
 
-// flag bit of the canonical pair (lo < hi) inside its tile's bitmap
-__device__ __forceinline__ bool flag_bit(const uint32_t *sB, int gi, int gj)
+// flag bit of local (row, col) in a tile bitmap
+__device__ __forceinline__ bool flag_bit(const uint32_t *sB, int r, int c)
 {
-    const int lo = gi < gj ? gi : gj, hi = gi < gj ? gj : gi;
-    const int r = lo & (TILE - 1), c = hi & (TILE - 1);
     return (sB[r * 4 + (c >> 5)] >> (c & 31)) & 1u;
 }
 
@@ -297,11 +390,12 @@ struct PairVal {
     bool computed;  // anchor pair or exactly evaluated (not_computed_mask == False)
 };
 
-// RefineApprox of one candidate pair as annchor.py:345-380 leaves it.
-__device__ __forceinline__ PairVal pair_value(const View &V, const TileModel *tm, const Model &M, float lb, float ub,
-                                              int li, int lj, int gi, int gj, const PointMeta &pi,
-                                              const PointMeta &pj, const float *sDi, const float *sDj,
-                                              bool flagged)
+// RefineApprox of one candidate pair as annchor.py:345-380 leaves it.  (cr, cc) = local index of the
+// pair's lower / higher endpoint inside the canonical (upper-triangular) tile, used when flagged.
+__device__ __forceinline__ PairVal pair_value(const View &V, const TileStore &ts, const TileModel *tm, const Model &M,
+                                              float lb, float ub, int li, int lj, int gi, int gj, int cr, int cc,
+                                              const PointMeta &pi, const PointMeta &pj, const float *sDi,
+                                              const float *sDj, bool flagged)
 {
     PairVal out;
     const float s = sDi[pj.cA * SROW + li] + sDj[pi.cA * SROW + lj];  // 2 * dad (utils.py:378-380)
@@ -311,7 +405,7 @@ __device__ __forceinline__ PairVal pair_value(const View &V, const TileModel *tm
     if (flagged) {
         float a = 0.0f, b = 0.0f;
         const uint32_t lo = gi < gj ? gi : gj, hi = gi < gj ? gj : gi;
-        const uint32_t kind = hash_lookup(V, pair_key(lo, hi), a, b);
+        const uint32_t kind = store_lookup(V, ts, cr, cc, lo, hi, a, b);
         if (kind == KIND_KNOWN) {
             out.v = a;
             out.computed = true;

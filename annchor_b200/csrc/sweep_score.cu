@@ -55,9 +55,12 @@ __global__ void __launch_bounds__(256, 1) score_sweep_kernel(const __grid_consta
     PointMeta *sM0j = sM0i + TILE;
     PointMeta *sM1i = sM0j + TILE;
     PointMeta *sM1j = sM1i + TILE;
-    uint32_t *sB0 = reinterpret_cast<uint32_t *>(sM1j + TILE);
-    uint32_t *sB1 = sB0 + BITMAP_WORDS;
-    unsigned char *sp = reinterpret_cast<unsigned char *>(sB1 + BITMAP_WORDS);
+    uint32_t *sBm = reinterpret_cast<uint32_t *>(sM1j + TILE);  // flag bitmap of the current tile
+    uint32_t *sCode = sBm + BITMAP_WORDS;                       // [2][TL_CAP] staged store codes
+    uint16_t *sPerm = reinterpret_cast<uint16_t *>(sCode + 2 * TL_CAP);
+    uint16_t *sRowBase = sPerm + TL_CAP;
+    TileDesc *sDesc = reinterpret_cast<TileDesc *>(sRowBase + TILE);  // [4] descriptors in flight
+    unsigned char *sp = reinterpret_cast<unsigned char *>(sDesc + 4);
     Survivor *queue = reinterpret_cast<Survivor *>(sp) + warp * A.qcap;
     sp += (size_t)8 * A.qcap * sizeof(Survivor);
     uint64_t *ek = reinterpret_cast<uint64_t *>(sp) + warp * EMIT_CAP;  // per-warp emission staging
@@ -104,12 +107,25 @@ __global__ void __launch_bounds__(256, 1) score_sweep_kernel(const __grid_consta
         const int64_t q = A.q_begin + m * A.q_stride;
         tile_from_index(q * A.world + A.rank, V.T, ti, tj);
     };
+    auto tile_no = [&](int64_t m) { return (A.q_begin + m * A.q_stride) * A.world + A.rank; };
+    TileStore ts;
+    ts.bm = sBm;
+    ts.rowbase = sRowBase;
+    ts.perm = sPerm;
+    ts.clean = false;
     if (m0 < m1) {
+        // descriptors of the first two tiles directly, everything later through cp.async one tile ahead
+        if (tid < 2 && m0 + tid < m1) {
+            const int64_t t = tile_no(m0 + tid);
+            sDesc[tid].base = V.tl_ptr[t];
+            sDesc[tid].end = V.tl_ptr[t + 1];
+        }
+        __syncthreads();
         int ti, tj;
         tile_of(m0, ti, tj);
         load_point_tile(V, ti, sD0i, sM0i);
         load_point_tile(V, tj, sD0j, sM0j);
-        load_bitmap_tile(V, ti, tj, sB0);
+        load_tile_codes(V, sDesc[0], sCode);
         if (tid < TILE) {
             thI[tid] = A.thresh[(int64_t)ti * TILE + tid];
             thJ[tid] = A.thresh[(int64_t)tj * TILE + tid];
@@ -127,7 +143,8 @@ __global__ void __launch_bounds__(256, 1) score_sweep_kernel(const __grid_consta
             tile_of(m + 1, ni, nj);
             load_point_tile(V, ni, buf ? sD0i : sD1i, buf ? sM0i : sM1i);
             load_point_tile(V, nj, buf ? sD0j : sD1j, buf ? sM0j : sM1j);
-            load_bitmap_tile(V, ni, nj, buf ? sB0 : sB1);
+            load_tile_codes(V, sDesc[(m + 1 - m0) & 3], sCode + (buf ^ 1) * TL_CAP);
+            if (m + 2 < m1) load_tile_desc(V, tile_no(m + 2), &sDesc[(m + 2 - m0) & 3]);
             if (tid < TILE) {
                 thI[(buf ^ 1) * TILE + tid] = A.thresh[(int64_t)ni * TILE + tid];
                 thJ[(buf ^ 1) * TILE + tid] = A.thresh[(int64_t)nj * TILE + tid];
@@ -136,8 +153,8 @@ __global__ void __launch_bounds__(256, 1) score_sweep_kernel(const __grid_consta
         }
         const float *sDi = buf ? sD1i : sD0i, *sDj = buf ? sD1j : sD0j;
         const PointMeta *sMi = buf ? sM1i : sM0i, *sMj = buf ? sM1j : sM0j;
-        const uint32_t *bm = buf ? sB1 : sB0;
-        prefetch_flagged(V, bm, ti, tj);
+        build_tile_store(V, ts, sDesc[(m - m0) & 3], sCode + buf * TL_CAP, sBm, 0);
+        const uint32_t *bm = sBm;
         const float *tI = thI + buf * TILE, *tJ = thJ + buf * TILE;
         // ---- phase 1: bounds + clipped prediction; keep (pred < cut-off) | flagged ----
         float cj[8];
@@ -175,7 +192,7 @@ __global__ void __launch_bounds__(256, 1) score_sweep_kernel(const __grid_consta
                         const float y = predict_clip2(tm, M, lbr[c], ubr[c], s2, bin);
                         const float4 mx = tm->mx[bin];
                         const float mg = (s2 == tm->en[bin]) ? mx.y : mx.x;
-                        km |= (y + mg < fmaxf(ci, cj[c])) ? (1u << c) : 0u;
+                        km |= (fmaxf(ci, cj[c]) - y > mg) ? (1u << c) : 0u;  // the very expression phase 2 tests
                     }
                 } else {
                     // many more pairs tie AT the floor level than the cut can take: of those, only the
@@ -196,8 +213,8 @@ __global__ void __launch_bounds__(256, 1) score_sweep_kernel(const __grid_consta
                         h ^= h >> 12;
                         h *= 0x297A2D39u;
                         h ^= h >> 15;
-                        const bool above = y + (eq ? mx.w : mx.z) < cut;
-                        const bool atfl = (y + (eq ? mx.y : mx.x) < cut) && h <= thr_hi;
+                        const bool above = cut - y > (eq ? mx.w : mx.z);  // same arithmetic as phase 2: p = cut - v
+                        const bool atfl = (cut - y > (eq ? mx.y : mx.x)) && h <= thr_hi;
                         km |= (above | atfl) ? (1u << c) : 0u;
                     }
                 }
@@ -227,10 +244,10 @@ __global__ void __launch_bounds__(256, 1) score_sweep_kernel(const __grid_consta
                     if (gj < V.n && s.lb < INFINITY) {  // gi < gj by construction (diagonal masked to +inf)
                         const PointMeta pi = sMi[li2], pj = sMj[lj];
                         if (is_candidate(pi, pj)) {
-                            const bool fl = flag_bit(bm, gi, gj);
+                            const bool fl = flag_bit(bm, li2, lj);
                             n_flagged += fl ? 1 : 0;
-                            const PairVal pv = pair_value(V, tm, M, s.lb, s.ub, li2, lj, gi, gj, pi, pj, sDi,
-                                                          sDj, fl);
+                            const PairVal pv = pair_value(V, ts, tm, M, s.lb, s.ub, li2, lj, gi, gj, li2, lj, pi, pj,
+                                                          sDi, sDj, fl);
                             if (!pv.computed) {
                                 ++n_nc;
                                 const float p = fmaxf(tI[li2], tJ[lj]) - pv.v;
@@ -299,7 +316,8 @@ int launch_score_sweep(annb_ctx *c, ScoreArgs &A)
 {
     const size_t lim = 227 * 1024;
     const size_t base = (size_t)4 * A.V.na * SROW * 4 + 4 * TILE * sizeof(PointMeta) +
-                        2 * BITMAP_WORDS * 4 + (size_t)8 * EMIT_CAP * 10 + 4 * TILE * 4 + sizeof(TileModel) +
+                        BITMAP_WORDS * 4 + 2 * TL_CAP * 4 + TL_CAP * 2 + TILE * 2 + 4 * sizeof(TileDesc) +
+                        (size_t)8 * EMIT_CAP * 10 + 4 * TILE * 4 + sizeof(TileModel) +
                         8 * 4 + (size_t)A.nlevels * 4 + 64;
     const size_t tables = ((size_t)A.n_errs * 4 + (size_t)(A.n_errs + A.M.nb) * 2 + 15) & ~(size_t)15;
     const size_t qmin = (size_t)8 * (QROW + 32) * sizeof(Survivor);
@@ -340,7 +358,16 @@ __global__ void __launch_bounds__(256, 2) sample_sweep_kernel(const SampleArgs A
     PointMeta *sMi = reinterpret_cast<PointMeta *>(sDj + na * SROW);
     PointMeta *sMj = sMi + TILE;
     uint32_t *bm = reinterpret_cast<uint32_t *>(sMj + TILE);
-    uint32_t *queue = bm + BITMAP_WORDS + warp * QCAP;  // li | lj << 8
+    uint32_t *sCode = bm + BITMAP_WORDS;  // [TL_CAP]
+    uint16_t *sPerm = reinterpret_cast<uint16_t *>(sCode + TL_CAP);
+    uint16_t *sRowBase = sPerm + TL_CAP;
+    TileDesc *sDesc = reinterpret_cast<TileDesc *>(sRowBase + TILE);
+    uint32_t *queue = reinterpret_cast<uint32_t *>(sDesc + 1) + warp * QCAP;  // li | lj << 8
+    TileStore ts;
+    ts.bm = bm;
+    ts.rowbase = sRowBase;
+    ts.perm = sPerm;
+    ts.clean = false;
     const int64_t NT = (int64_t)V.T * (V.T + 1) / 2;
     const int64_t nq = (NT - A.rank + A.world - 1) / A.world;
     const int64_t per = (nq + gridDim.x - 1) / gridDim.x;
@@ -355,12 +382,19 @@ __global__ void __launch_bounds__(256, 2) sample_sweep_kernel(const SampleArgs A
         int ti, tj;
         tile_from_index(m * A.world + A.rank, V.T, ti, tj);
         __syncthreads();
+        if (tid == 0) {
+            const int64_t t = m * A.world + A.rank;
+            sDesc->base = V.tl_ptr[t];
+            sDesc->end = V.tl_ptr[t + 1];
+        }
+        __syncthreads();
         load_point_tile(V, ti, sDi, sMi);
         load_point_tile(V, tj, sDj, sMj);
-        load_bitmap_tile(V, ti, tj, bm);
+        load_tile_codes(V, *sDesc, sCode);
         cp_async_commit();
         cp_async_wait_all();
         __syncthreads();
+        build_tile_store(V, ts, *sDesc, sCode, bm, 0);
         const bool diag = ti == tj;
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
@@ -389,9 +423,9 @@ __global__ void __launch_bounds__(256, 2) sample_sweep_kernel(const SampleArgs A
                     const PointMeta pi = sMi[li2], pj = sMj[lj];
                     if (pi.slot < 0 && pj.slot < 0 && is_candidate(pi, pj)) {  // anchor pairs are computed
                         bool known = false;
-                        if (flag_bit(bm, gi2, gj)) {
+                        if (flag_bit(bm, li2, lj)) {
                             float a, b;
-                            known = hash_lookup(V, pair_key((uint32_t)gi2, (uint32_t)gj), a, b) == KIND_KNOWN;
+                            known = store_lookup(V, ts, li2, lj, (uint32_t)gi2, (uint32_t)gj, a, b) == KIND_KNOWN;
                         }
                         if (!known) {
                             emit = true;
@@ -420,7 +454,8 @@ __global__ void __launch_bounds__(256, 2) sample_sweep_kernel(const SampleArgs A
 int launch_sample_sweep(annb_ctx *c, const SampleArgs &A)
 {
     const size_t smem = (size_t)2 * A.V.na * SROW * 4 + 2 * TILE * sizeof(PointMeta) +
-                        BITMAP_WORDS * 4 + (size_t)8 * QCAP * 4 + 64;
+                        BITMAP_WORDS * 4 + TL_CAP * 4 + TL_CAP * 2 + TILE * 2 + sizeof(TileDesc) +
+                        (size_t)8 * QCAP * 4 + 64;
     ANNB_CUDA(cudaFuncSetAttribute(sample_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)smem));
     const int64_t NT = (int64_t)A.V.T * (A.V.T + 1) / 2;

@@ -72,10 +72,13 @@ __global__ void __launch_bounds__(256, 1) thresh_sweep_kernel(const __grid_const
     PointMeta *sMi = reinterpret_cast<PointMeta *>(sDj1 + na * SROW);
     PointMeta *sMj0 = sMi + TILE;
     PointMeta *sMj1 = sMj0 + TILE;
-    uint32_t *sB0 = reinterpret_cast<uint32_t *>(sMj1 + TILE);
-    uint32_t *sB1 = sB0 + BITMAP_WORDS;
-    uint32_t *sBT = sB1 + BITMAP_WORDS;  // flags re-oriented to (row = this CTA's point, col = column point)
-    TileModel *tm = reinterpret_cast<TileModel *>(sBT + BITMAP_WORDS);
+    uint32_t *sBm = reinterpret_cast<uint32_t *>(sMj1 + TILE);  // flags, canonical orientation (lower endpoint = row)
+    uint32_t *sBF = sBm + BITMAP_WORDS;  // flags oriented (row = this CTA's point, col = column point)
+    uint32_t *sCode = sBF + BITMAP_WORDS;  // [2][TL_CAP] staged store codes
+    uint16_t *sPerm = reinterpret_cast<uint16_t *>(sCode + 2 * TL_CAP);
+    uint16_t *sRowBase = sPerm + TL_CAP;
+    TileDesc *sDesc = reinterpret_cast<TileDesc *>(sRowBase + TILE);  // [4]
+    TileModel *tm = reinterpret_cast<TileModel *>(sDesc + 4);
     Survivor *queue = reinterpret_cast<Survivor *>(tm + 1) + warp * A.qcap;
     float *thr1 = reinterpret_cast<float *>(reinterpret_cast<Survivor *>(tm + 1) + 8 * A.qcap);
     float *thr2 = thr1 + TILE;
@@ -88,6 +91,11 @@ __global__ void __launch_bounds__(256, 1) thresh_sweep_kernel(const __grid_const
 
     build_tile_model(M, tm);
     if (lane == 0) *qcnt = 0;
+    TileStore ts;
+    ts.bm = sBm;
+    ts.rowbase = sRowBase;
+    ts.perm = sPerm;
+    ts.clean = false;
     const int n_rb = A.rb_list ? A.n_rb : V.T;
     for (int rq = blockIdx.x * A.world + A.rank; rq < n_rb; rq += gridDim.x * A.world) {
         const int rb = A.rb_list ? A.rb_list[rq] : rq;
@@ -103,37 +111,40 @@ __global__ void __launch_bounds__(256, 1) thresh_sweep_kernel(const __grid_const
             thr2[tid] = L2ON ? INFINITY : -INFINITY;
             cut[tid] = INFINITY;
         }
+        // canonical (upper-triangular) tile that holds the pairs of (row block rb, column tile tc)
+        auto canon = [&](int tc) { return tile_index(rb < tc ? rb : tc, rb < tc ? tc : rb, V.T); };
+        __syncthreads();  // the previous row block is done with the descriptors
+        if (tid < 2 && A.col_phase + tid * A.col_stride < V.T) {
+            const int64_t t = canon(A.col_phase + tid * A.col_stride);
+            sDesc[tid].base = V.tl_ptr[t];
+            sDesc[tid].end = V.tl_ptr[t + 1];
+        }
+        __syncthreads();
         load_point_tile(V, rb, sDi, sMi);
         if (A.col_phase < V.T) {
             load_point_tile(V, A.col_phase, sDj0, sMj0);
-            load_bitmap_tile(V, rb, A.col_phase, sB0);
+            load_tile_codes(V, sDesc[0], sCode);
         }
         cp_async_commit();
+        ts.clean = false;
 
         int par = 0;  // buffer parity
-        for (int tc = A.col_phase; tc < V.T; tc += A.col_stride, par ^= 1) {
+        int step_no = 0;
+        for (int tc = A.col_phase; tc < V.T; tc += A.col_stride, par ^= 1, ++step_no) {
             const float *sDj = par ? sDj1 : sDj0;
             const PointMeta *sMj = par ? sMj1 : sMj0;
-            const uint32_t *sBraw = par ? sB1 : sB0;
             cp_async_wait_all();
             __syncthreads();
             if (tc + A.col_stride < V.T) {  // prefetch the next column tile into the other buffer
                 load_point_tile(V, tc + A.col_stride, par ? sDj0 : sDj1, par ? sMj0 : sMj1);
-                load_bitmap_tile(V, rb, tc + A.col_stride, par ? sB0 : sB1);
+                load_tile_codes(V, sDesc[(step_no + 1) & 3], sCode + (par ^ 1) * TL_CAP);
+                if (tc + 2 * A.col_stride < V.T)
+                    load_tile_desc(V, canon(tc + 2 * A.col_stride), &sDesc[(step_no + 2) & 3]);
                 cp_async_commit();
             }
-            // flag bits are stored once per pair, in the tile of (lo, hi): re-orient them so that
-            // bit (row, col) of sBF is the flag of (this CTA's row point, column point)
-            const uint32_t *sBF = sBraw;
-            if (tc <= rb) {
-                transpose_bitmap(sBraw, sBT);
-                __syncthreads();
-                if (tc == rb) {
-                    for (int k = tid; k < BITMAP_WORDS; k += blockDim.x) sBT[k] |= sBraw[k];
-                    __syncthreads();
-                }
-                sBF = sBT;
-            }
+            // entries are stored once per pair, in the tile of (lo, hi): the flags phase 1 reads are
+            // re-oriented so that bit (row, col) of sBF is the flag of (this CTA's row point, column point)
+            build_tile_store(V, ts, sDesc[step_no & 3], sCode + par * TL_CAP, sBF, tc < rb ? 1 : (tc == rb ? 2 : 3));
             // ---- phase 1: bounds + clipped prediction, two passes of 4 x 8 pairs per thread ----
             int cAj[8];
 #pragma unroll
@@ -187,9 +198,10 @@ __global__ void __launch_bounds__(256, 1) thresh_sweep_kernel(const __grid_const
                         gj = tc * TILE + lj;
                         const PointMeta pi = sMi[row], pj = sMj[lj];
                         if (gi < V.n && gj < V.n && gi != gj && is_candidate(pi, pj)) {
-                            const bool fl = (sBF[row * 4 + (lj >> 5)] >> (lj & 31)) & 1u;
-                            const PairVal pv = pair_value(V, tm, M, sv.lb, sv.ub, row, lj, gi, gj, pi, pj, sDi,
-                                                          sDj, fl);
+                            const bool fl = flag_bit(sBF, row, lj);
+                            const bool rlo = gi < gj;  // canonical local coordinates: lower endpoint first
+                            const PairVal pv = pair_value(V, ts, tm, M, sv.lb, sv.ub, row, lj, gi, gj, rlo ? row : lj,
+                                                          rlo ? lj : row, pi, pj, sDi, sDj, fl);
                             v = pv.v;
                             w1b = v < thr1[row];
                             w2b = L2ON && !pv.computed && v < thr2[row];
@@ -246,8 +258,8 @@ __global__ void __launch_bounds__(256, 1) thresh_sweep_kernel(const __grid_const
 
 static size_t thresh_smem_base(int na, int k1, int k2)
 {
-    return (size_t)3 * na * SROW * 4 + 3 * TILE * sizeof(PointMeta) + 3 * BITMAP_WORDS * 4 +
-           sizeof(TileModel) + 3 * TILE * 4 + 8 * 4 + (size_t)TILE * k1 * 4 + (size_t)TILE * k2 * 8 + 64;
+    return (size_t)3 * na * SROW * 4 + 3 * TILE * sizeof(PointMeta) + 2 * BITMAP_WORDS * 4 + 2 * TL_CAP * 4 +
+           TL_CAP * 2 + TILE * 2 + 4 * sizeof(TileDesc) + sizeof(TileModel) + 3 * TILE * 4 + 8 * 4 + (size_t)TILE * k1 * 4 + (size_t)TILE * k2 * 8 + 64;
 }
 
 int launch_thresh_sweep(annb_ctx *c, ThreshArgs &A)
@@ -304,10 +316,13 @@ __global__ void __launch_bounds__(256, 1) thresh_pairs_kernel(const __grid_const
     PointMeta *sM0j = sM0i + TILE;
     PointMeta *sM1i = sM0j + TILE;
     PointMeta *sM1j = sM1i + TILE;
-    uint32_t *sB0 = reinterpret_cast<uint32_t *>(sM1j + TILE);
-    uint32_t *sB1 = sB0 + BITMAP_WORDS;
-    Survivor *queue = reinterpret_cast<Survivor *>(sB1 + BITMAP_WORDS) + warp * A.qcap;
-    float *c1I = reinterpret_cast<float *>(reinterpret_cast<Survivor *>(sB1 + BITMAP_WORDS) + 8 * A.qcap);
+    uint32_t *sBm = reinterpret_cast<uint32_t *>(sM1j + TILE);
+    uint32_t *sCode = sBm + BITMAP_WORDS;  // [2][TL_CAP]
+    uint16_t *sPerm = reinterpret_cast<uint16_t *>(sCode + 2 * TL_CAP);
+    uint16_t *sRowBase = sPerm + TL_CAP;
+    TileDesc *sDesc = reinterpret_cast<TileDesc *>(sRowBase + TILE);  // [4]
+    Survivor *queue = reinterpret_cast<Survivor *>(sDesc + 4) + warp * A.qcap;
+    float *c1I = reinterpret_cast<float *>(reinterpret_cast<Survivor *>(sDesc + 4) + 8 * A.qcap);
     float *c1J = c1I + 2 * TILE;  // [2][128] each: cut1 / cut2 of the row and column tiles (double-buffered)
     float *c2I = c1J + 2 * TILE;
     float *c2J = c2I + 2 * TILE;
@@ -330,12 +345,23 @@ __global__ void __launch_bounds__(256, 1) thresh_pairs_kernel(const __grid_const
             c2J[b * TILE + tid] = l2on ? A.cut2[gj] : -INFINITY;
         }
     };
+    TileStore ts;
+    ts.bm = sBm;
+    ts.rowbase = sRowBase;
+    ts.perm = sPerm;
+    ts.clean = false;
     if (m0 < m1) {
+        if (tid < 2 && m0 + tid < m1) {
+            const int64_t t = (m0 + tid) * A.world + A.rank;
+            sDesc[tid].base = V.tl_ptr[t];
+            sDesc[tid].end = V.tl_ptr[t + 1];
+        }
+        __syncthreads();
         int ti, tj;
         tile_from_index(m0 * A.world + A.rank, V.T, ti, tj);
         load_point_tile(V, ti, sD0i, sM0i);
         load_point_tile(V, tj, sD0j, sM0j);
-        load_bitmap_tile(V, ti, tj, sB0);
+        load_tile_codes(V, sDesc[0], sCode);
         stage_cuts(ti, tj, 0);
         cp_async_commit();
     }
@@ -350,14 +376,15 @@ __global__ void __launch_bounds__(256, 1) thresh_pairs_kernel(const __grid_const
             tile_from_index((m + 1) * A.world + A.rank, V.T, ni, nj);
             load_point_tile(V, ni, buf ? sD0i : sD1i, buf ? sM0i : sM1i);
             load_point_tile(V, nj, buf ? sD0j : sD1j, buf ? sM0j : sM1j);
-            load_bitmap_tile(V, ni, nj, buf ? sB0 : sB1);
+            load_tile_codes(V, sDesc[(m + 1 - m0) & 3], sCode + (buf ^ 1) * TL_CAP);
+            if (m + 2 < m1) load_tile_desc(V, (m + 2) * A.world + A.rank, &sDesc[(m + 2 - m0) & 3]);
             stage_cuts(ni, nj, buf ^ 1);
             cp_async_commit();
         }
         const float *sDi = buf ? sD1i : sD0i, *sDj = buf ? sD1j : sD0j;
         const PointMeta *sMi = buf ? sM1i : sM0i, *sMj = buf ? sM1j : sM0j;
-        const uint32_t *bm = buf ? sB1 : sB0;
-        prefetch_flagged(V, bm, ti, tj);
+        build_tile_store(V, ts, sDesc[(m - m0) & 3], sCode + buf * TL_CAP, sBm, 0);
+        const uint32_t *bm = sBm;
         const float *k1I = c1I + buf * TILE, *k1J = c1J + buf * TILE;
         const float *k2I = c2I + buf * TILE, *k2J = c2J + buf * TILE;
         float cj[8];
@@ -412,8 +439,8 @@ __global__ void __launch_bounds__(256, 1) thresh_pairs_kernel(const __grid_const
                     if (gj < V.n && s.lb < INFINITY) {
                         const PointMeta pi = sMi[li2], pj = sMj[lj];
                         if (is_candidate(pi, pj)) {
-                            const PairVal pv = pair_value(V, tm, M, s.lb, s.ub, li2, lj, gi, gj, pi, pj, sDi, sDj,
-                                                          flag_bit(bm, gi, gj));
+                            const PairVal pv = pair_value(V, ts, tm, M, s.lb, s.ub, li2, lj, gi, gj, li2, lj, pi, pj, sDi,
+                                                          sDj, flag_bit(bm, li2, lj));
                             const float v = pv.v;
                             const uint32_t cflag = pv.computed ? 0x80000000u : 0u;
                             if (v <= k1I[li2] || (!pv.computed && v <= k2I[li2])) {
@@ -438,8 +465,9 @@ __global__ void __launch_bounds__(256, 1) thresh_pairs_kernel(const __grid_const
 int launch_thresh_pairs(annb_ctx *c, ThreshPairArgs &A)
 {
     const size_t lim = 227 * 1024;
-    const size_t base = (size_t)4 * A.V.na * SROW * 4 + 4 * TILE * sizeof(PointMeta) + 2 * BITMAP_WORDS * 4 +
-                        8 * TILE * 4 + sizeof(TileModel) + 8 * 4 + 64;
+    const size_t base = (size_t)4 * A.V.na * SROW * 4 + 4 * TILE * sizeof(PointMeta) + BITMAP_WORDS * 4 +
+                        2 * TL_CAP * 4 + TL_CAP * 2 + TILE * 2 + 4 * sizeof(TileDesc) + 8 * TILE * 4 +
+                        sizeof(TileModel) + 8 * 4 + 64;
     ANNB_REQUIRE(base + (size_t)8 * (QROW + 32) * sizeof(Survivor) <= lim, ANNB_ERANGE,
                  "threshold pair sweep needs %zu bytes of shared memory (n_anchors=%d)",
                  base + (size_t)8 * (QROW + 32) * sizeof(Survivor), A.V.na);

@@ -55,6 +55,15 @@ def _pairset(ij, n):
     return np.sort(k)
 
 
+def _same_pairs(dev_ij, orc_ij, n, tag):
+    a, b = _pairset(dev_ij, n), _pairset(orc_ij, n)
+    if not np.array_equal(a, b):
+        only_d, only_o = np.setdiff1d(a, b), np.setdiff1d(b, a)
+        raise AssertionError("%s: %d pairs only on the device %s, %d only in the oracle %s (of %d)"
+                             % (tag, only_d.size, [(int(k // n), int(k % n)) for k in only_d[:5]], only_o.size,
+                                [(int(k // n), int(k % n)) for k in only_o[:5]], a.size))
+
+
 def _run_both(gpu_ctx, X, metric, kw, cost):
     from annchor_b200.annchor import Annchor
     from oracle.devmode import OracleAnnchorF32
@@ -81,8 +90,8 @@ def test_fit_equals_device_arithmetic_oracle(gpu_ctx, case):
         np.testing.assert_allclose(td["coef%d" % it], to["coef%d" % it], rtol=1e-9, atol=1e-12, err_msg=tag)
         assert np.array_equal(td["thresh%d" % it], to["thresh%d" % it]), \
             (tag, np.nonzero(td["thresh%d" % it] != to["thresh%d" % it])[0][:10])
-        assert np.array_equal(_pairset(td["selected%d" % it], n), _pairset(to["selected%d" % it], n)), tag
-        assert np.array_equal(_pairset(td["next%d" % it], n), _pairset(to["next%d" % it], n)), tag
+        _same_pairs(td["selected%d" % it], to["selected%d" % it], n, tag + " selected")
+        _same_pairs(td["next%d" % it], to["next%d" % it], n, tag + " look-ahead")
         if it < niters - 1:
             assert td["n_tightened%d" % it] == to["n_tightened%d" % it], tag
     assert td["n_forced"] == to["n_forced"]

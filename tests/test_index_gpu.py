@@ -87,6 +87,7 @@ def test_anchors_locality_thresh_select(gpu_ctx, case):
     # selected / look-ahead SETS, n_forced and the thresholds of both iterations are compared for
     # equality with the device-arithmetic oracle in tests/test_exact_parity_gpu.py, and
     # test_select_is_top_by_probability below checks the cut against the float64 probabilities
+    nc_before = o.IJs[ncm]  # (the oracle's selection below clears the mask of what it picks)
     o.select_refine_candidate_pairs(0.5, 0)
     ix.guarantee_nmin(3 * nn // 2)
     n_sel, n_next = ix.select(o.n_refine, o.lookahead)
@@ -95,7 +96,7 @@ def test_anchors_locality_thresh_select(gpu_ctx, case):
     key = lambda ij: set((ij[:, 0] * len(X) + ij[:, 1]).tolist())
     s_dev = key(sel)
     assert len(s_dev) == n_sel and np.all(sel[:, 0] < sel[:, 1])
-    assert s_dev <= key(o.IJs[ncm]), "selected pairs must be not-computed candidates"
+    assert s_dev <= key(nc_before), "selected pairs must be not-computed candidates"
     assert not (key(nxt) & s_dev)
     if o.n_refine * o.lookahead < o.prob.shape[0]:
         assert nxt.shape[0] == o.n_refine * (o.lookahead - 1)
