@@ -425,43 +425,91 @@ __global__ void known_degree_kernel(const HashSlot *__restrict__ htab, uint64_t 
     }
 }
 
-// single-block exclusive scan (n up to a few million; one-off per iteration)
-__global__ void __launch_bounds__(1024) exclusive_scan_kernel(const int32_t *__restrict__ in,
-                                                              int64_t *__restrict__ out, int64_t n)
+// exclusive scan int32 -> int64 (out[n] = total) in three passes: per-block sums, scan of the sums by
+// one block, per-block scan with offsets.  n ranges from N (CSR row pointers) to N^2 / 32768 (tile lists).
+constexpr int SCAN_CHUNK = 1024 * 8;
+
+__device__ __forceinline__ int64_t block_exclusive_scan_1024(int64_t v, int64_t *s_warp /* [33] */, int64_t &total)
 {
-    __shared__ int64_t s_warp[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int64_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int64_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    __syncthreads();
+    if (lane == 31) s_warp[w] = x;
+    __syncthreads();
+    if (w == 0) {
+        int64_t t = s_warp[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int64_t y = __shfl_up_sync(0xffffffffu, t, o);
+            if (lane >= o) t += y;
+        }
+        s_warp[lane] = t;
+    }
+    __syncthreads();
+    total = s_warp[31];
+    return x - v + (w > 0 ? s_warp[w - 1] : 0);
+}
+
+__global__ void __launch_bounds__(1024) scan_block_sums_kernel(const int32_t *__restrict__ in, int64_t n,
+                                                               int64_t *__restrict__ sums)
+{
+    __shared__ int64_t s_warp[33];
+    const int64_t base = (int64_t)blockIdx.x * SCAN_CHUNK + (int64_t)threadIdx.x * 8;
+    int64_t v = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (base + k < n) v += in[base + k];
+    int64_t total;
+    block_exclusive_scan_1024(v, s_warp, total);
+    if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) scan_sums_kernel(int64_t *__restrict__ sums, int64_t nb)
+{
+    __shared__ int64_t s_warp[33];
     __shared__ int64_t s_carry;
     if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int64_t base = 0; base < n; base += 1024) {
+    for (int64_t base = 0; base < nb; base += 1024) {
         const int64_t idx = base + threadIdx.x;
-        int64_t v = idx < n ? in[idx] : 0;
-        int64_t x = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int64_t y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= o) x += y;
-        }
-        if (lane == 31) s_warp[w] = x;
+        const int64_t v = idx < nb ? sums[idx] : 0;
+        int64_t total;
+        const int64_t ex = block_exclusive_scan_1024(v, s_warp, total);
+        const int64_t carry = s_carry;
+        if (idx < nb) sums[idx] = carry + ex;
         __syncthreads();
-        if (w == 0) {
-            int64_t t = s_warp[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int64_t y = __shfl_up_sync(0xffffffffu, t, o);
-                if (lane >= o) t += y;
-            }
-            s_warp[lane] = t;
-        }
-        __syncthreads();
-        const int64_t incl = x + (w > 0 ? s_warp[w - 1] : 0) + s_carry;
-        if (idx < n) out[idx] = incl - v;
-        __syncthreads();
-        if (threadIdx.x == 1023) s_carry = incl;
+        if (threadIdx.x == 0) s_carry = carry + total;
         __syncthreads();
     }
-    if (threadIdx.x == 0) out[n] = s_carry;
+    if (threadIdx.x == 0) sums[nb] = s_carry;
+}
+
+__global__ void __launch_bounds__(1024) scan_apply_kernel(const int32_t *__restrict__ in, int64_t n,
+                                                          const int64_t *__restrict__ sums, int64_t nb,
+                                                          int64_t *__restrict__ out)
+{
+    __shared__ int64_t s_warp[33];
+    const int64_t base = (int64_t)blockIdx.x * SCAN_CHUNK + (int64_t)threadIdx.x * 8;
+    int32_t x[8];
+    int64_t v = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        x[k] = base + k < n ? in[base + k] : 0;
+        v += x[k];
+    }
+    int64_t total;
+    int64_t run = sums[blockIdx.x] + block_exclusive_scan_1024(v, s_warp, total);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if (base + k < n) out[base + k] = run;
+        run += x[k];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = sums[nb];
 }
 
 __global__ void known_fill_kernel(const HashSlot *__restrict__ htab, uint64_t cap,
@@ -989,7 +1037,7 @@ struct annb_index {
     // known-pair store
     DevBuf htab;
     // per-tile entry lists derived from the hash map (rebuilt lazily before a sweep)
-    DevBuf tl_ptr, tl_cnt, tl_code, tl_a, tl_b;
+    DevBuf tl_ptr, tl_cnt, tl_code, tl_a, tl_b, scan_tmp;
     bool tl_dirty = false;
     int64_t tl_entries = 0;
     uint64_t hcap = 0;
@@ -1124,6 +1172,20 @@ static int hash_insert(annb_index *ix, const int32_t *I, const int32_t *J, const
     return ANNB_OK;
 }
 
+static int launch_scan_i32_i64(annb_ctx *c, const int32_t *in, int64_t *out, int64_t n, DevBuf &tmp)
+{
+    const int64_t nb = (n + SCAN_CHUNK - 1) / SCAN_CHUNK;
+    ANNB_TRY(tmp.ensure((size_t)(nb + 1) * 8));
+    if (n == 0) {
+        ANNB_CUDA(cudaMemsetAsync(out, 0, 8, c->stream));
+        return ANNB_OK;
+    }
+    ANNB_LAUNCH(scan_block_sums_kernel, (int)nb, 1024, 0, c->stream, in, n, tmp.as<int64_t>());
+    ANNB_LAUNCH(scan_sums_kernel, 1, 1024, 0, c->stream, tmp.as<int64_t>(), nb);
+    ANNB_LAUNCH(scan_apply_kernel, (int)nb, 1024, 0, c->stream, in, n, tmp.as<int64_t>(), nb, out);
+    return ANNB_OK;
+}
+
 // bring the per-tile entry lists up to date with the hash map (count, scan, fill: two streaming
 // passes over the table)
 static int tile_lists_rebuild(annb_index *ix)
@@ -1234,7 +1296,7 @@ ANNB_API int annb_index_destroy(annb_index *ix)
     if (!ix) return ANNB_OK;
     cudaSetDevice(ix->ctx->device);
     cudaStreamSynchronize(ix->ctx->stream);
-    DevBuf *all[] = {&ix->A_dev, &ix->D64, &ix->D32, &ix->Dpm, &ix->meta, &ix->scratch, &ix->htab, &ix->tl_ptr, &ix->tl_cnt, &ix->tl_code, &ix->tl_a, &ix->tl_b,
+    DevBuf *all[] = {&ix->A_dev, &ix->D64, &ix->D32, &ix->Dpm, &ix->meta, &ix->scratch, &ix->htab, &ix->tl_ptr, &ix->tl_cnt, &ix->tl_code, &ix->tl_a, &ix->tl_b, &ix->scan_tmp,
                      &ix->errs_dev, &ix->rank_dev, &ix->thresh, &ix->l2val, &ix->l2id, &ix->hist,
                      &ix->counters, &ix->emit_key, &ix->emit_lvl, &ix->sel_i, &ix->sel_j, &ix->nxt_i,
                      &ix->nxt_j, &ix->tiehist, &ix->tiekeys, &ix->pool_key, &ix->pool_dad, &ix->t0,
@@ -2240,8 +2302,7 @@ static int build_known_csr(annb_index *ix)
     ANNB_CUDA(cudaMemsetAsync(ix->kdeg.p, 0, (size_t)(n + 1) * 4, c->stream));
     ANNB_LAUNCH(known_degree_kernel, grid_for_n(c, (int64_t)ix->hcap), 256, 0, c->stream,
                 ix->htab.as<HashSlot>(), ix->hcap, ix->kdeg.as<int32_t>());
-    ANNB_LAUNCH(exclusive_scan_kernel, 1, 1024, 0, c->stream, ix->kdeg.as<int32_t>(),
-                ix->kptr.as<int64_t>(), n);
+    ANNB_TRY(launch_scan_i32_i64(c, ix->kdeg.as<int32_t>(), ix->kptr.as<int64_t>(), n, ix->scan_tmp));
     int64_t total = 0;
     ANNB_CUDA(cudaMemcpyAsync(&total, ix->kptr.as<int64_t>() + n, 8, cudaMemcpyDeviceToHost, c->stream));
     ANNB_CUDA(cudaStreamSynchronize(c->stream));
@@ -2291,8 +2352,7 @@ ANNB_API int annb_index_update_bounds(annb_index *ix, int64_t *n_updated)
                 ix->twork.as<unsigned long long>(), ix->counters.as<unsigned long long>() + 7);
     unsigned long long wsum[3] = {0, 0, 0};
     ANNB_CUDA(cudaMemcpyAsync(wsum, ix->counters.as<unsigned long long>() + 7, 8, cudaMemcpyDeviceToHost, c->stream));
-    ANNB_LAUNCH(exclusive_scan_kernel, 1, 1024, 0, c->stream, ix->kdeg.as<int32_t>(),
-                ix->gptr.as<int64_t>(), n);
+    ANNB_TRY(launch_scan_i32_i64(c, ix->kdeg.as<int32_t>(), ix->gptr.as<int64_t>(), n, ix->scan_tmp));
     ANNB_CUDA(cudaMemsetAsync(ix->kdeg.p, 0, (size_t)(n + 1) * 4, c->stream));
     ANNB_LAUNCH(scatter_by_lo_kernel, grid_for_n(c, m), 256, 0, c->stream, ix->nxt_i.as<int32_t>(),
                 ix->nxt_j.as<int32_t>(), m, ix->kptr.as<int64_t>(), ix->gptr.as<int64_t>(),

@@ -89,15 +89,28 @@ struct TileDesc {  // [base, end) of a tile's entries in the global lists
     long long base, end;
 };
 
+// Shared-memory block of the current tile's store state: bm[BITMAP_WORDS] (flags, canonical
+// orientation: row = lower endpoint) | rowbase[TILE] u16 (set bits in the rows above) | perm[TL_CAP] u16
+// (bit rank -> entry) | clean flag.  The handle keeps only three pointers in registers.
+constexpr int TS_BYTES = BITMAP_WORDS * 4 + TILE * 2 + TL_CAP * 2 + 16;
+
 struct TileStore {
-    uint32_t *bm;         // [BITMAP_WORDS] flags, canonical orientation (row = lower endpoint)
-    uint16_t *rowbase;    // [TILE] set bits in the rows above
-    uint16_t *perm;       // [TL_CAP] bit rank -> entry
+    uint32_t *bm;           // start of the block
     const uint32_t *codes;  // staged codes of this tile
-    long long base;
-    int cnt;
-    bool staged;          // cnt <= TL_CAP
-    bool clean;           // bm is all zero
+    const TileDesc *d;      // its descriptor (shared memory)
+    __device__ __forceinline__ uint16_t *rowbase() const { return reinterpret_cast<uint16_t *>(bm + BITMAP_WORDS); }
+    __device__ __forceinline__ uint16_t *perm() const { return rowbase() + TILE; }
+    __device__ __forceinline__ volatile uint32_t *clean() const
+    {
+        return reinterpret_cast<volatile uint32_t *>(perm() + TL_CAP);
+    }
+    __device__ __forceinline__ void init(void *block)
+    {
+        bm = reinterpret_cast<uint32_t *>(block);
+        codes = nullptr;
+        d = nullptr;
+        if (threadIdx.x == 0) *clean() = 0;  // (made visible by the first barrier of the tile loop)
+    }
 };
 
 // asynchronously fetch the descriptor of upper-triangular tile t (two 8-byte copies)
@@ -109,45 +122,47 @@ __device__ __forceinline__ void load_tile_desc(const View &V, int64_t t, TileDes
     }
 }
 // asynchronously stage the codes of a tile whose descriptor is already in shared memory
-__device__ __forceinline__ void load_tile_codes(const View &V, const TileDesc &d, uint32_t *codes)
+__device__ __forceinline__ void load_tile_codes(const View &V, const TileDesc *d, uint32_t *codes)
 {
-    const long long cnt = d.end - d.base;
+    const long long base = d->base, cnt = d->end - base;
     if (cnt > TL_CAP) return;
-    for (int e = threadIdx.x; e < (int)cnt; e += blockDim.x) cp_async4(codes + e, V.tl_code + d.base + e);
+    for (int e = threadIdx.x; e < (int)cnt; e += blockDim.x) cp_async4(codes + e, V.tl_code + base + e);
 }
 
 // `bf` is the flag bitmap phase 1 reads.  Upper-triangle sweeps pass bf == ts.bm (mode 0).  A row sweep
 // keeps a separate row-oriented copy: mode 1 = transposed (row tile below the column tile), 2 = both
 // orientations (diagonal tile), 3 = same orientation (row tile above the column tile).
-__device__ __forceinline__ void build_tile_store(const View &V, TileStore &ts, const TileDesc &d,
+__device__ __forceinline__ void build_tile_store(const View &V, TileStore &ts, const TileDesc *dp,
                                                  const uint32_t *codes, uint32_t *bf, int mode)
 {
     const int tid = threadIdx.x;
-    const int cnt = (int)(d.end - d.base);
-    ts.base = d.base;
-    ts.cnt = cnt;
+    const long long base = dp->base;
+    const int cnt = (int)(dp->end - base);
     ts.codes = codes;
-    ts.staged = cnt <= TL_CAP;
-    if (cnt == 0 && ts.clean) return;  // nothing flagged here and the bitmaps are already zero
+    ts.d = dp;
+    const bool staged = cnt <= TL_CAP;
+    const bool was_clean = *ts.clean() != 0;
+    if (cnt == 0 && was_clean) return;  // nothing flagged here and the bitmaps are already zero
     const bool sep = bf != ts.bm;
     for (int k = tid; k < BITMAP_WORDS; k += blockDim.x) {
         ts.bm[k] = 0;
         if (sep) bf[k] = 0;
     }
-    __syncthreads();
-    ts.clean = cnt == 0;
+    __syncthreads();  // (also orders the read of the clean flag above before its update below)
+    if (tid == 0) *ts.clean() = cnt == 0 ? 1u : 0u;
     if (cnt == 0) return;
     for (int e = tid; e < cnt; e += blockDim.x) {
-        const uint32_t code = ts.staged ? codes[e] : __ldg(V.tl_code + d.base + e);
+        const uint32_t code = staged ? codes[e] : __ldg(V.tl_code + base + e);
         const int r = code >> 9, c = (code >> 2) & 127;
         atomicOr(&ts.bm[r * 4 + (c >> 5)], 1u << (c & 31));
         if (mode == 1 || mode == 2) atomicOr(&bf[c * 4 + (r >> 5)], 1u << (r & 31));
         if (mode == 2 || mode == 3) atomicOr(&bf[r * 4 + (c >> 5)], 1u << (c & 31));
     }
     __syncthreads();
-    if (!ts.staged) return;
+    if (!staged) return;
     // rowbase = exclusive prefix of the per-row popcounts (threads 0..127, one row each)
     __shared__ int s_wsum[4];
+    uint16_t *rowbase = ts.rowbase(), *perm = ts.perm();
     int mine = 0, incl = 0;
     if (tid < TILE) {
         const uint4 w = *reinterpret_cast<const uint4 *>(ts.bm + tid * 4);
@@ -164,22 +179,22 @@ __device__ __forceinline__ void build_tile_store(const View &V, TileStore &ts, c
     if (tid < TILE) {
         int off = 0;
         for (int q = 0; q < (tid >> 5); ++q) off += s_wsum[q];
-        ts.rowbase[tid] = (uint16_t)(off + incl - mine);
+        rowbase[tid] = (uint16_t)(off + incl - mine);
     }
     __syncthreads();
     for (int e = tid; e < cnt; e += blockDim.x) {
         const uint32_t code = codes[e];
         const int r = code >> 9, c = (code >> 2) & 127, w = c >> 5;
         const uint32_t *row = ts.bm + r * 4;
-        int rho = ts.rowbase[r] + __popc(row[w] & ((1u << (c & 31)) - 1u));
+        int rho = rowbase[r] + __popc(row[w] & ((1u << (c & 31)) - 1u));
         rho += (w > 0 ? __popc(row[0]) : 0) + (w > 1 ? __popc(row[1]) : 0) + (w > 2 ? __popc(row[2]) : 0);
-        ts.perm[rho] = (uint16_t)e;
+        perm[rho] = (uint16_t)e;
     }
     __syncthreads();
     // pull the values of this tile's entries into L2 while phase 1 runs (one line per 32 entries)
     for (int e = tid * 32; e < cnt; e += blockDim.x * 32) {
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(V.tl_a + d.base + e));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(V.tl_b + d.base + e));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(V.tl_a + base + e));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(V.tl_b + base + e));
     }
 }
 
@@ -187,15 +202,16 @@ __device__ __forceinline__ void build_tile_store(const View &V, TileStore &ts, c
 __device__ __forceinline__ uint32_t store_lookup(const View &V, const TileStore &ts, int r, int c, uint32_t glo,
                                                  uint32_t ghi, float &a, float &b)
 {
-    if (!ts.staged) return hash_lookup(V, pair_key(glo, ghi), a, b);
+    const long long base = ts.d->base;
+    if (ts.d->end - base > TL_CAP) return hash_lookup(V, pair_key(glo, ghi), a, b);
     const uint32_t *row = ts.bm + r * 4;
     const int w = c >> 5;
-    int rho = ts.rowbase[r] + __popc(row[w] & ((1u << (c & 31)) - 1u));
+    int rho = ts.rowbase()[r] + __popc(row[w] & ((1u << (c & 31)) - 1u));
     rho += (w > 0 ? __popc(row[0]) : 0) + (w > 1 ? __popc(row[1]) : 0) + (w > 2 ? __popc(row[2]) : 0);
-    const int e = ts.perm[rho];
+    const int e = ts.perm()[rho];
     const uint32_t kind = ts.codes[e] & 3u;
-    a = __ldg(V.tl_a + ts.base + e);
-    b = kind == KIND_TIGHT ? __ldg(V.tl_b + ts.base + e) : 0.0f;
+    a = __ldg(V.tl_a + base + e);
+    b = kind == KIND_TIGHT ? __ldg(V.tl_b + base + e) : 0.0f;
     return kind;
 }
 

@@ -55,11 +55,10 @@ __global__ void __launch_bounds__(256, 1) score_sweep_kernel(const __grid_consta
     PointMeta *sM0j = sM0i + TILE;
     PointMeta *sM1i = sM0j + TILE;
     PointMeta *sM1j = sM1i + TILE;
-    uint32_t *sBm = reinterpret_cast<uint32_t *>(sM1j + TILE);  // flag bitmap of the current tile
-    uint32_t *sCode = sBm + BITMAP_WORDS;                       // [2][TL_CAP] staged store codes
-    uint16_t *sPerm = reinterpret_cast<uint16_t *>(sCode + 2 * TL_CAP);
-    uint16_t *sRowBase = sPerm + TL_CAP;
-    TileDesc *sDesc = reinterpret_cast<TileDesc *>(sRowBase + TILE);  // [4] descriptors in flight
+    unsigned char *sTS = reinterpret_cast<unsigned char *>(sM1j + TILE);  // store state of the current tile
+    uint32_t *sBm = reinterpret_cast<uint32_t *>(sTS);                    // its flag bitmap
+    uint32_t *sCode = reinterpret_cast<uint32_t *>(sTS + TS_BYTES);       // [2][TL_CAP] staged store codes
+    TileDesc *sDesc = reinterpret_cast<TileDesc *>(sCode + 2 * TL_CAP);   // [4] descriptors in flight
     unsigned char *sp = reinterpret_cast<unsigned char *>(sDesc + 4);
     Survivor *queue = reinterpret_cast<Survivor *>(sp) + warp * A.qcap;
     sp += (size_t)8 * A.qcap * sizeof(Survivor);
@@ -109,10 +108,7 @@ __global__ void __launch_bounds__(256, 1) score_sweep_kernel(const __grid_consta
     };
     auto tile_no = [&](int64_t m) { return (A.q_begin + m * A.q_stride) * A.world + A.rank; };
     TileStore ts;
-    ts.bm = sBm;
-    ts.rowbase = sRowBase;
-    ts.perm = sPerm;
-    ts.clean = false;
+    ts.init(sTS);
     if (m0 < m1) {
         // descriptors of the first two tiles directly, everything later through cp.async one tile ahead
         if (tid < 2 && m0 + tid < m1) {
@@ -125,7 +121,7 @@ __global__ void __launch_bounds__(256, 1) score_sweep_kernel(const __grid_consta
         tile_of(m0, ti, tj);
         load_point_tile(V, ti, sD0i, sM0i);
         load_point_tile(V, tj, sD0j, sM0j);
-        load_tile_codes(V, sDesc[0], sCode);
+        load_tile_codes(V, &sDesc[0], sCode);
         if (tid < TILE) {
             thI[tid] = A.thresh[(int64_t)ti * TILE + tid];
             thJ[tid] = A.thresh[(int64_t)tj * TILE + tid];
@@ -143,7 +139,7 @@ __global__ void __launch_bounds__(256, 1) score_sweep_kernel(const __grid_consta
             tile_of(m + 1, ni, nj);
             load_point_tile(V, ni, buf ? sD0i : sD1i, buf ? sM0i : sM1i);
             load_point_tile(V, nj, buf ? sD0j : sD1j, buf ? sM0j : sM1j);
-            load_tile_codes(V, sDesc[(m + 1 - m0) & 3], sCode + (buf ^ 1) * TL_CAP);
+            load_tile_codes(V, &sDesc[(m + 1 - m0) & 3], sCode + (buf ^ 1) * TL_CAP);
             if (m + 2 < m1) load_tile_desc(V, tile_no(m + 2), &sDesc[(m + 2 - m0) & 3]);
             if (tid < TILE) {
                 thI[(buf ^ 1) * TILE + tid] = A.thresh[(int64_t)ni * TILE + tid];
@@ -153,7 +149,7 @@ __global__ void __launch_bounds__(256, 1) score_sweep_kernel(const __grid_consta
         }
         const float *sDi = buf ? sD1i : sD0i, *sDj = buf ? sD1j : sD0j;
         const PointMeta *sMi = buf ? sM1i : sM0i, *sMj = buf ? sM1j : sM0j;
-        build_tile_store(V, ts, sDesc[(m - m0) & 3], sCode + buf * TL_CAP, sBm, 0);
+        build_tile_store(V, ts, &sDesc[(m - m0) & 3], sCode + buf * TL_CAP, sBm, 0);
         const uint32_t *bm = sBm;
         const float *tI = thI + buf * TILE, *tJ = thJ + buf * TILE;
         // ---- phase 1: bounds + clipped prediction; keep (pred < cut-off) | flagged ----
@@ -316,7 +312,7 @@ int launch_score_sweep(annb_ctx *c, ScoreArgs &A)
 {
     const size_t lim = 227 * 1024;
     const size_t base = (size_t)4 * A.V.na * SROW * 4 + 4 * TILE * sizeof(PointMeta) +
-                        BITMAP_WORDS * 4 + 2 * TL_CAP * 4 + TL_CAP * 2 + TILE * 2 + 4 * sizeof(TileDesc) +
+                        TS_BYTES + 2 * TL_CAP * 4 + 4 * sizeof(TileDesc) +
                         (size_t)8 * EMIT_CAP * 10 + 4 * TILE * 4 + sizeof(TileModel) +
                         8 * 4 + (size_t)A.nlevels * 4 + 64;
     const size_t tables = ((size_t)A.n_errs * 4 + (size_t)(A.n_errs + A.M.nb) * 2 + 15) & ~(size_t)15;
@@ -357,17 +353,13 @@ __global__ void __launch_bounds__(256, 2) sample_sweep_kernel(const SampleArgs A
     float *sDj = sDi + na * SROW;
     PointMeta *sMi = reinterpret_cast<PointMeta *>(sDj + na * SROW);
     PointMeta *sMj = sMi + TILE;
-    uint32_t *bm = reinterpret_cast<uint32_t *>(sMj + TILE);
-    uint32_t *sCode = bm + BITMAP_WORDS;  // [TL_CAP]
-    uint16_t *sPerm = reinterpret_cast<uint16_t *>(sCode + TL_CAP);
-    uint16_t *sRowBase = sPerm + TL_CAP;
-    TileDesc *sDesc = reinterpret_cast<TileDesc *>(sRowBase + TILE);
+    unsigned char *sTS = reinterpret_cast<unsigned char *>(sMj + TILE);
+    uint32_t *bm = reinterpret_cast<uint32_t *>(sTS);
+    uint32_t *sCode = reinterpret_cast<uint32_t *>(sTS + TS_BYTES);  // [TL_CAP]
+    TileDesc *sDesc = reinterpret_cast<TileDesc *>(sCode + TL_CAP);
     uint32_t *queue = reinterpret_cast<uint32_t *>(sDesc + 1) + warp * QCAP;  // li | lj << 8
     TileStore ts;
-    ts.bm = bm;
-    ts.rowbase = sRowBase;
-    ts.perm = sPerm;
-    ts.clean = false;
+    ts.init(sTS);
     const int64_t NT = (int64_t)V.T * (V.T + 1) / 2;
     const int64_t nq = (NT - A.rank + A.world - 1) / A.world;
     const int64_t per = (nq + gridDim.x - 1) / gridDim.x;
@@ -390,11 +382,11 @@ __global__ void __launch_bounds__(256, 2) sample_sweep_kernel(const SampleArgs A
         __syncthreads();
         load_point_tile(V, ti, sDi, sMi);
         load_point_tile(V, tj, sDj, sMj);
-        load_tile_codes(V, *sDesc, sCode);
+        load_tile_codes(V, sDesc, sCode);
         cp_async_commit();
         cp_async_wait_all();
         __syncthreads();
-        build_tile_store(V, ts, *sDesc, sCode, bm, 0);
+        build_tile_store(V, ts, sDesc, sCode, bm, 0);
         const bool diag = ti == tj;
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
@@ -454,8 +446,7 @@ __global__ void __launch_bounds__(256, 2) sample_sweep_kernel(const SampleArgs A
 int launch_sample_sweep(annb_ctx *c, const SampleArgs &A)
 {
     const size_t smem = (size_t)2 * A.V.na * SROW * 4 + 2 * TILE * sizeof(PointMeta) +
-                        BITMAP_WORDS * 4 + TL_CAP * 4 + TL_CAP * 2 + TILE * 2 + sizeof(TileDesc) +
-                        (size_t)8 * QCAP * 4 + 64;
+                        TS_BYTES + TL_CAP * 4 + sizeof(TileDesc) + (size_t)8 * QCAP * 4 + 64;
     ANNB_CUDA(cudaFuncSetAttribute(sample_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)smem));
     const int64_t NT = (int64_t)A.V.T * (A.V.T + 1) / 2;

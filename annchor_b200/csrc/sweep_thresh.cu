@@ -72,12 +72,10 @@ __global__ void __launch_bounds__(256, 1) thresh_sweep_kernel(const __grid_const
     PointMeta *sMi = reinterpret_cast<PointMeta *>(sDj1 + na * SROW);
     PointMeta *sMj0 = sMi + TILE;
     PointMeta *sMj1 = sMj0 + TILE;
-    uint32_t *sBm = reinterpret_cast<uint32_t *>(sMj1 + TILE);  // flags, canonical orientation (lower endpoint = row)
-    uint32_t *sBF = sBm + BITMAP_WORDS;  // flags oriented (row = this CTA's point, col = column point)
-    uint32_t *sCode = sBF + BITMAP_WORDS;  // [2][TL_CAP] staged store codes
-    uint16_t *sPerm = reinterpret_cast<uint16_t *>(sCode + 2 * TL_CAP);
-    uint16_t *sRowBase = sPerm + TL_CAP;
-    TileDesc *sDesc = reinterpret_cast<TileDesc *>(sRowBase + TILE);  // [4]
+    unsigned char *sTS = reinterpret_cast<unsigned char *>(sMj1 + TILE);  // store state (flags in canonical orientation)
+    uint32_t *sBF = reinterpret_cast<uint32_t *>(sTS + TS_BYTES);  // flags oriented (row = this CTA's point, col = column point)
+    uint32_t *sCode = sBF + BITMAP_WORDS;                          // [2][TL_CAP] staged store codes
+    TileDesc *sDesc = reinterpret_cast<TileDesc *>(sCode + 2 * TL_CAP);  // [4]
     TileModel *tm = reinterpret_cast<TileModel *>(sDesc + 4);
     Survivor *queue = reinterpret_cast<Survivor *>(tm + 1) + warp * A.qcap;
     float *thr1 = reinterpret_cast<float *>(reinterpret_cast<Survivor *>(tm + 1) + 8 * A.qcap);
@@ -92,10 +90,7 @@ __global__ void __launch_bounds__(256, 1) thresh_sweep_kernel(const __grid_const
     build_tile_model(M, tm);
     if (lane == 0) *qcnt = 0;
     TileStore ts;
-    ts.bm = sBm;
-    ts.rowbase = sRowBase;
-    ts.perm = sPerm;
-    ts.clean = false;
+    ts.init(sTS);
     const int n_rb = A.rb_list ? A.n_rb : V.T;
     for (int rq = blockIdx.x * A.world + A.rank; rq < n_rb; rq += gridDim.x * A.world) {
         const int rb = A.rb_list ? A.rb_list[rq] : rq;
@@ -123,10 +118,9 @@ __global__ void __launch_bounds__(256, 1) thresh_sweep_kernel(const __grid_const
         load_point_tile(V, rb, sDi, sMi);
         if (A.col_phase < V.T) {
             load_point_tile(V, A.col_phase, sDj0, sMj0);
-            load_tile_codes(V, sDesc[0], sCode);
+            load_tile_codes(V, &sDesc[0], sCode);
         }
         cp_async_commit();
-        ts.clean = false;
 
         int par = 0;  // buffer parity
         int step_no = 0;
@@ -137,14 +131,14 @@ __global__ void __launch_bounds__(256, 1) thresh_sweep_kernel(const __grid_const
             __syncthreads();
             if (tc + A.col_stride < V.T) {  // prefetch the next column tile into the other buffer
                 load_point_tile(V, tc + A.col_stride, par ? sDj0 : sDj1, par ? sMj0 : sMj1);
-                load_tile_codes(V, sDesc[(step_no + 1) & 3], sCode + (par ^ 1) * TL_CAP);
+                load_tile_codes(V, &sDesc[(step_no + 1) & 3], sCode + (par ^ 1) * TL_CAP);
                 if (tc + 2 * A.col_stride < V.T)
                     load_tile_desc(V, canon(tc + 2 * A.col_stride), &sDesc[(step_no + 2) & 3]);
                 cp_async_commit();
             }
             // entries are stored once per pair, in the tile of (lo, hi): the flags phase 1 reads are
             // re-oriented so that bit (row, col) of sBF is the flag of (this CTA's row point, column point)
-            build_tile_store(V, ts, sDesc[step_no & 3], sCode + par * TL_CAP, sBF, tc < rb ? 1 : (tc == rb ? 2 : 3));
+            build_tile_store(V, ts, &sDesc[step_no & 3], sCode + par * TL_CAP, sBF, tc < rb ? 1 : (tc == rb ? 2 : 3));
             // ---- phase 1: bounds + clipped prediction, two passes of 4 x 8 pairs per thread ----
             int cAj[8];
 #pragma unroll
@@ -258,8 +252,8 @@ __global__ void __launch_bounds__(256, 1) thresh_sweep_kernel(const __grid_const
 
 static size_t thresh_smem_base(int na, int k1, int k2)
 {
-    return (size_t)3 * na * SROW * 4 + 3 * TILE * sizeof(PointMeta) + 2 * BITMAP_WORDS * 4 + 2 * TL_CAP * 4 +
-           TL_CAP * 2 + TILE * 2 + 4 * sizeof(TileDesc) + sizeof(TileModel) + 3 * TILE * 4 + 8 * 4 + (size_t)TILE * k1 * 4 + (size_t)TILE * k2 * 8 + 64;
+    return (size_t)3 * na * SROW * 4 + 3 * TILE * sizeof(PointMeta) + TS_BYTES + BITMAP_WORDS * 4 + 2 * TL_CAP * 4 +
+           4 * sizeof(TileDesc) + sizeof(TileModel) + 3 * TILE * 4 + 8 * 4 + (size_t)TILE * k1 * 4 + (size_t)TILE * k2 * 8 + 64;
 }
 
 int launch_thresh_sweep(annb_ctx *c, ThreshArgs &A)
@@ -316,11 +310,10 @@ __global__ void __launch_bounds__(256, 1) thresh_pairs_kernel(const __grid_const
     PointMeta *sM0j = sM0i + TILE;
     PointMeta *sM1i = sM0j + TILE;
     PointMeta *sM1j = sM1i + TILE;
-    uint32_t *sBm = reinterpret_cast<uint32_t *>(sM1j + TILE);
-    uint32_t *sCode = sBm + BITMAP_WORDS;  // [2][TL_CAP]
-    uint16_t *sPerm = reinterpret_cast<uint16_t *>(sCode + 2 * TL_CAP);
-    uint16_t *sRowBase = sPerm + TL_CAP;
-    TileDesc *sDesc = reinterpret_cast<TileDesc *>(sRowBase + TILE);  // [4]
+    unsigned char *sTS = reinterpret_cast<unsigned char *>(sM1j + TILE);
+    uint32_t *sBm = reinterpret_cast<uint32_t *>(sTS);
+    uint32_t *sCode = reinterpret_cast<uint32_t *>(sTS + TS_BYTES);  // [2][TL_CAP]
+    TileDesc *sDesc = reinterpret_cast<TileDesc *>(sCode + 2 * TL_CAP);  // [4]
     Survivor *queue = reinterpret_cast<Survivor *>(sDesc + 4) + warp * A.qcap;
     float *c1I = reinterpret_cast<float *>(reinterpret_cast<Survivor *>(sDesc + 4) + 8 * A.qcap);
     float *c1J = c1I + 2 * TILE;  // [2][128] each: cut1 / cut2 of the row and column tiles (double-buffered)
@@ -346,10 +339,7 @@ __global__ void __launch_bounds__(256, 1) thresh_pairs_kernel(const __grid_const
         }
     };
     TileStore ts;
-    ts.bm = sBm;
-    ts.rowbase = sRowBase;
-    ts.perm = sPerm;
-    ts.clean = false;
+    ts.init(sTS);
     if (m0 < m1) {
         if (tid < 2 && m0 + tid < m1) {
             const int64_t t = (m0 + tid) * A.world + A.rank;
@@ -361,7 +351,7 @@ __global__ void __launch_bounds__(256, 1) thresh_pairs_kernel(const __grid_const
         tile_from_index(m0 * A.world + A.rank, V.T, ti, tj);
         load_point_tile(V, ti, sD0i, sM0i);
         load_point_tile(V, tj, sD0j, sM0j);
-        load_tile_codes(V, sDesc[0], sCode);
+        load_tile_codes(V, &sDesc[0], sCode);
         stage_cuts(ti, tj, 0);
         cp_async_commit();
     }
@@ -383,7 +373,7 @@ __global__ void __launch_bounds__(256, 1) thresh_pairs_kernel(const __grid_const
         }
         const float *sDi = buf ? sD1i : sD0i, *sDj = buf ? sD1j : sD0j;
         const PointMeta *sMi = buf ? sM1i : sM0i, *sMj = buf ? sM1j : sM0j;
-        build_tile_store(V, ts, sDesc[(m - m0) & 3], sCode + buf * TL_CAP, sBm, 0);
+        build_tile_store(V, ts, &sDesc[(m - m0) & 3], sCode + buf * TL_CAP, sBm, 0);
         const uint32_t *bm = sBm;
         const float *k1I = c1I + buf * TILE, *k1J = c1J + buf * TILE;
         const float *k2I = c2I + buf * TILE, *k2J = c2J + buf * TILE;
@@ -465,9 +455,8 @@ __global__ void __launch_bounds__(256, 1) thresh_pairs_kernel(const __grid_const
 int launch_thresh_pairs(annb_ctx *c, ThreshPairArgs &A)
 {
     const size_t lim = 227 * 1024;
-    const size_t base = (size_t)4 * A.V.na * SROW * 4 + 4 * TILE * sizeof(PointMeta) + BITMAP_WORDS * 4 +
-                        2 * TL_CAP * 4 + TL_CAP * 2 + TILE * 2 + 4 * sizeof(TileDesc) + 8 * TILE * 4 +
-                        sizeof(TileModel) + 8 * 4 + 64;
+    const size_t base = (size_t)4 * A.V.na * SROW * 4 + 4 * TILE * sizeof(PointMeta) + TS_BYTES +
+                        2 * TL_CAP * 4 + 4 * sizeof(TileDesc) + 8 * TILE * 4 + sizeof(TileModel) + 8 * 4 + 64;
     ANNB_REQUIRE(base + (size_t)8 * (QROW + 32) * sizeof(Survivor) <= lim, ANNB_ERANGE,
                  "threshold pair sweep needs %zu bytes of shared memory (n_anchors=%d)",
                  base + (size_t)8 * (QROW + 32) * sizeof(Survivor), A.V.na);
