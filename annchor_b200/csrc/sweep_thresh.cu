@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(256, 1) thresh_pairs_kernel(const __grid_const
             tile_from_index((m + 1) * A.world + A.rank, V.T, ni, nj);
             load_point_tile(V, ni, buf ? sD0i : sD1i, buf ? sM0i : sM1i);
             load_point_tile(V, nj, buf ? sD0j : sD1j, buf ? sM0j : sM1j);
-            load_tile_codes(V, sDesc[(m + 1 - m0) & 3], sCode + (buf ^ 1) * TL_CAP);
+            load_tile_codes(V, &sDesc[(m + 1 - m0) & 3], sCode + (buf ^ 1) * TL_CAP);
             if (m + 2 < m1) load_tile_desc(V, (m + 2) * A.world + A.rank, &sDesc[(m + 2 - m0) & 3]);
             stage_cuts(ni, nj, buf ^ 1);
             cp_async_commit();
