@@ -583,19 +583,35 @@ __global__ void scatter_by_lo_kernel(const int32_t *__restrict__ I, const int32_
     }
 }
 
-// rows ordered by closest anchor (counting sort over <= 64 buckets)
-__global__ void cA_hist_kernel(const PointMeta *__restrict__ meta, int64_t n, int32_t *__restrict__ hist)
+// rows ordered by (closest anchor, distance to it): a counting sort over 64 x 1024 buckets.  Points that
+// are close to each other get close positions, so the CTAs that run at the same time work on rows whose
+// partner lists overlap and the streamed lists hit in L2.
+constexpr int ROW_BUCKETS = kMaxAnchors * 1024;
+__device__ __forceinline__ int row_bucket(const PointMeta &m, const float *__restrict__ D32, int64_t npad, int64_t i,
+                                          float inv_scale)
 {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
-         i += (int64_t)gridDim.x * blockDim.x)
-        atomicAdd(&hist[meta[i].cA], 1);
+    const float d = D32[(int64_t)m.cA * npad + i];
+    int q = (int)(d * inv_scale);
+    q = q < 0 ? 0 : (q > 1023 ? 1023 : q);
+    return m.cA * 1024 + q;
 }
-__global__ void cA_scatter_kernel(const PointMeta *__restrict__ meta, int64_t n, int32_t *__restrict__ cursor,
-                                  int32_t *__restrict__ order)
+__global__ void row_bucket_hist_kernel(const PointMeta *__restrict__ meta, const float *__restrict__ D32,
+                                       int64_t npad, int64_t n, float inv_scale, int32_t *__restrict__ hist)
 {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x)
-        order[atomicAdd(&cursor[meta[i].cA], 1)] = (int32_t)i;
+        atomicAdd(&hist[row_bucket(meta[i], D32, npad, i, inv_scale)], 1);
+}
+__global__ void row_bucket_scatter_kernel(const PointMeta *__restrict__ meta, const float *__restrict__ D32,
+                                          int64_t npad, int64_t n, float inv_scale,
+                                          const int64_t *__restrict__ ptr, int32_t *__restrict__ cursor,
+                                          int32_t *__restrict__ order)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int b = row_bucket(meta[i], D32, npad, i, inv_scale);
+        order[ptr[b] + atomicAdd(&cursor[b], 1)] = (int32_t)i;
+    }
 }
 
 __global__ void tighten_work_kernel(const int64_t *__restrict__ kptr, const int64_t *__restrict__ gptr,
@@ -816,6 +832,200 @@ tighten_grouped_kernel(View V, const int64_t *__restrict__ kptr, const int32_t *
                     improved[p] = (lb > l0 || ub < u0) ? 1 : 0;
                 }
             }
+        }
+    }
+}
+
+// K2b, bitmap variant (the default while N bits fit shared memory).  The key row's known-neighbour set
+// N(i) is a bit per point id in shared memory plus a per-word prefix count, so membership of a streamed
+// id is ONE shared load and a bit test, and a hit finds its distance by bit rank (prefix + popcount) in a
+// dense value array -- ~25 issue slots per 32 streamed entries against ~100 for the bucket-hash probe
+// above.  Bits are set and cleared per row from the row's own list (no full clears); rows with more than
+// TB_CHUNK known distances go through in chunks whose partial bounds are combined.
+constexpr int TB_CHUNK = 4096;
+
+template <int NT_>
+__global__ void __launch_bounds__(NT_)
+tighten_bitmap_kernel(View V, const int64_t *__restrict__ kptr, const int32_t *__restrict__ kids,
+                      const float *__restrict__ kds, const int64_t *__restrict__ gptr,
+                      const int32_t *__restrict__ gJ, const int32_t *__restrict__ gsrc,
+                      const int32_t *__restrict__ row_order, const int32_t *__restrict__ heavy,
+                      const unsigned long long *__restrict__ sched /* [0] n_heavy, [1] next ticket */,
+                      const unsigned long long *__restrict__ work, unsigned long long heavy_thr,
+                      int has_tight, float *__restrict__ out_lb, float *__restrict__ out_ub,
+                      uint8_t *__restrict__ improved, int W /* bitmap words, multiple of 32 */,
+                      int chunk /* entries of N(i) per pass, <= TB_CHUNK */)
+{
+    extern __shared__ __align__(16) unsigned char tb_smem[];
+    uint32_t *bits = reinterpret_cast<uint32_t *>(tb_smem);
+    float *vals = reinterpret_cast<float *>(bits + W);
+    uint16_t *pre = reinterpret_cast<uint16_t *>(vals + TB_CHUNK);
+    __shared__ long long s_ticket;
+    __shared__ int s_next;
+    __shared__ int s_wtot[NT_ / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = NT_ / 32;
+    const int S = ((W + NW - 1) / NW + 31) / 32 * 32;  // words per warp segment of the prefix pass
+    for (int k = tid; k < W; k += NT_) bits[k] = 0;
+    const long long n_heavy = (long long)sched[0];
+    unsigned long long *ticket = const_cast<unsigned long long *>(sched) + 1;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_ticket = (long long)atomicAdd(ticket, 1ull);
+        __syncthreads();
+        const long long tk = s_ticket;
+        if (tk >= n_heavy + V.n) break;
+        int64_t i;
+        if (tk < n_heavy) {
+            i = heavy[tk];
+        } else {
+            i = row_order[tk - n_heavy];
+            if (work[i] >= heavy_thr) continue;  // already done from the heavy queue
+        }
+        const int64_t g0 = gptr[i], g1 = gptr[i + 1];
+        if (g0 == g1) continue;
+        const int64_t bi = kptr[i];
+        const int mi = (int)(kptr[i + 1] - bi);
+        float xa[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) xa[q] = (lane + 32 * q < V.na) ? __ldg(V.Dpm + i * V.dpitch + lane + 32 * q) : 0.0f;
+        for (int c0 = 0; c0 == 0 || c0 < mi; c0 += chunk) {
+            const int mc = min(chunk, mi - c0);
+            const bool first = c0 == 0, last = c0 + chunk >= mi;
+            // 1. membership bits of this chunk of N(i)
+            for (int k = tid; k < mc; k += NT_) {
+                const uint32_t id = (uint32_t)kids[bi + c0 + k];
+                atomicOr(&bits[id >> 5], 1u << (id & 31));
+            }
+            if (tid == 0) s_next = 0;
+            __syncthreads();
+            // 2. pre[w] = set bits in the words before w: each warp scans its own segment, then adds
+            //    the totals of the segments before it
+            {
+                const int w0 = warp * S, w1 = min(W, w0 + S);
+                int run = 0;
+                for (int b = w0; b < w1; b += 32) {
+                    const int w = b + lane;
+                    const int c = w < w1 ? __popc(bits[w]) : 0;
+                    int x = c;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int y = __shfl_up_sync(0xffffffffu, x, o);
+                        if (lane >= o) x += y;
+                    }
+                    if (w < w1) pre[w] = (uint16_t)(run + x - c);
+                    run += __shfl_sync(0xffffffffu, x, 31);
+                }
+                if (lane == 0) s_wtot[warp] = run;
+                __syncthreads();
+                int off = 0;
+                for (int q = 0; q < warp; ++q) off += s_wtot[q];
+                if (off)
+                    for (int w = w0 + lane; w < w1; w += 32) pre[w] = (uint16_t)(pre[w] + off);
+            }
+            __syncthreads();
+            // 3. distances by bit rank
+            for (int k = tid; k < mc; k += NT_) {
+                const uint32_t id = (uint32_t)kids[bi + c0 + k];
+                const uint32_t w = id >> 5;
+                vals[pre[w] + __popc(bits[w] & ((1u << (id & 31)) - 1u))] = kds[bi + c0 + k];
+            }
+            __syncthreads();
+            // 4. every warp streams the lists of the row's partners
+            for (;;) {
+                int gq = 0;
+                if (lane == 0) gq = atomicAdd(&s_next, 1);
+                gq = __shfl_sync(0xffffffffu, gq, 0);
+                const int64_t g = g0 + gq;
+                if (g >= g1) break;
+                const int j = gJ[g];
+                const int64_t bj = kptr[j];
+                const int mj = (int)(kptr[j + 1] - bj);
+                float lb = 0.0f, ub = INFINITY;
+                uint32_t idv[TGU], idn[TGU];
+                float yv[TGU], yn[TGU];
+#pragma unroll
+                for (int u = 0; u < TGU; ++u) {
+                    const int k = u * 32 + lane;
+                    idv[u] = k < mj ? (uint32_t)__ldg(kids + bj + k) : 0xffffffffu;
+                    yv[u] = k < mj ? __ldg(kds + bj + k) : 0.0f;
+                }
+                for (int k0 = 0; k0 < mj; k0 += 32 * TGU) {
+                    if (k0 + 32 * TGU < mj) {
+#pragma unroll
+                        for (int u = 0; u < TGU; ++u) {
+                            const int k = k0 + 32 * TGU + u * 32 + lane;
+                            idn[u] = k < mj ? (uint32_t)__ldg(kids + bj + k) : 0xffffffffu;
+                            yn[u] = k < mj ? __ldg(kds + bj + k) : 0.0f;
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < TGU; ++u) {
+                        const uint32_t id = idv[u];
+                        const bool valid = id != 0xffffffffu;
+                        const uint32_t w = valid ? (id >> 5) : 0u;
+                        const uint32_t word = bits[w];
+                        if (valid && ((word >> (id & 31)) & 1u)) {
+                            const float x = vals[pre[w] + __popc(word & ((1u << (id & 31)) - 1u))];
+                            lb = fmaxf(lb, fabsf(x - yv[u]));
+                            ub = fminf(ub, x + yv[u]);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < TGU; ++u) {
+                        idv[u] = idn[u];
+                        yv[u] = yn[u];
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    lb = fmaxf(lb, __shfl_xor_sync(0xffffffffu, lb, o));
+                    ub = fminf(ub, __shfl_xor_sync(0xffffffffu, ub, o));
+                }
+                const int32_t p = gsrc[g];
+                if (!first) {  // combine with the earlier chunks of N(i)
+                    lb = fmaxf(lb, out_lb[p]);
+                    ub = fminf(ub, out_ub[p]);
+                }
+                if (!last) {
+                    if (lane == 0) {
+                        out_lb[p] = lb;
+                        out_ub[p] = ub;
+                    }
+                    continue;
+                }
+                // anchor bounds + any earlier tightening of this pair: lanes over anchors
+                float l0 = 0.0f, u0 = INFINITY;
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+                    if (lane + 32 * q < V.na) {
+                        const float y = __ldg(V.Dpm + (int64_t)j * V.dpitch + lane + 32 * q);
+                        l0 = fmaxf(l0, fabsf(xa[q] - y));
+                        u0 = fminf(u0, xa[q] + y);
+                    }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    l0 = fmaxf(l0, __shfl_xor_sync(0xffffffffu, l0, o));
+                    u0 = fminf(u0, __shfl_xor_sync(0xffffffffu, u0, o));
+                }
+                if (lane == 0) {
+                    if (has_tight) {
+                        float ta = 0.0f, tb = 0.0f;
+                        const uint32_t plo = (uint32_t)min((int64_t)j, i), phi = (uint32_t)max((int64_t)j, i);
+                        if (hash_lookup(V, pair_key(plo, phi), ta, tb) == KIND_TIGHT) {
+                            l0 = fmaxf(l0, ta);
+                            u0 = fminf(u0, tb);
+                        }
+                    }
+                    out_lb[p] = fmaxf(lb, l0);
+                    out_ub[p] = fminf(ub, u0);
+                    improved[p] = (lb > l0 || ub < u0) ? 1 : 0;
+                }
+            }
+            __syncthreads();
+            // 5. clear this chunk's bits again (cheaper than zeroing W words per row)
+            for (int k = tid; k < mc; k += NT_) bits[(uint32_t)kids[bi + c0 + k] >> 5] = 0;
+            __syncthreads();
         }
     }
 }
@@ -2400,20 +2610,24 @@ ANNB_API int annb_index_update_bounds(annb_index *ix, int64_t *n_updated)
     }
     if (ix->row_order.p == nullptr) {
         ANNB_TRY(ix->row_order.ensure((size_t)n * 4));
-        int32_t hcnt[kMaxAnchors], hoff[kMaxAnchors];
-        ANNB_CUDA(cudaMemsetAsync(ix->counters.p, 0, 256, c->stream));
-        ANNB_LAUNCH(cA_hist_kernel, grid_for_n(c, n), 256, 0, c->stream, ix->meta.as<PointMeta>(), n,
-                    ix->counters.as<int32_t>());
-        ANNB_CUDA(cudaMemcpyAsync(hcnt, ix->counters.p, sizeof(hcnt), cudaMemcpyDeviceToHost, c->stream));
+        ANNB_TRY(ix->t5.ensure((size_t)std::max<int64_t>(m * 4, (ROW_BUCKETS + 1) * 16)));  // hist | ptr, reused below
+        int32_t *rb_hist = ix->t5.as<int32_t>();
+        int64_t *rb_ptr = reinterpret_cast<int64_t *>(rb_hist + ROW_BUCKETS + 2);
+        // scale of the distance buckets: the largest anchor distance
+        ANNB_CUDA(cudaMemsetAsync(ix->counters.p, 0, 64, c->stream));
+        ANNB_LAUNCH(max_f32_kernel, grid_for_n(c, (int64_t)ix->na * ix->npad), 256, 0, c->stream,
+                    ix->D32.as<float>(), (int64_t)ix->na * ix->npad, ix->counters.as<unsigned int>());
+        float dmax = 0.0f;
+        ANNB_CUDA(cudaMemcpyAsync(&dmax, ix->counters.p, 4, cudaMemcpyDeviceToHost, c->stream));
         ANNB_CUDA(cudaStreamSynchronize(c->stream));
-        int32_t acc = 0;
-        for (int a = 0; a < kMaxAnchors; ++a) {
-            hoff[a] = acc;
-            acc += hcnt[a];
-        }
-        ANNB_CUDA(cudaMemcpyAsync(ix->counters.p, hoff, sizeof(hoff), cudaMemcpyHostToDevice, c->stream));
-        ANNB_LAUNCH(cA_scatter_kernel, grid_for_n(c, n), 256, 0, c->stream, ix->meta.as<PointMeta>(), n,
-                    ix->counters.as<int32_t>(), ix->row_order.as<int32_t>());
+        const float inv_scale = dmax > 0.0f && std::isfinite(dmax) ? 1023.0f / dmax : 0.0f;
+        ANNB_CUDA(cudaMemsetAsync(rb_hist, 0, (size_t)(ROW_BUCKETS + 2) * 4, c->stream));
+        ANNB_LAUNCH(row_bucket_hist_kernel, grid_for_n(c, n), 256, 0, c->stream, ix->meta.as<PointMeta>(),
+                    ix->D32.as<float>(), ix->npad, n, inv_scale, rb_hist);
+        ANNB_TRY(launch_scan_i32_i64(c, rb_hist, rb_ptr, ROW_BUCKETS, ix->scan_tmp));
+        ANNB_CUDA(cudaMemsetAsync(rb_hist, 0, (size_t)(ROW_BUCKETS + 2) * 4, c->stream));
+        ANNB_LAUNCH(row_bucket_scatter_kernel, grid_for_n(c, n), 256, 0, c->stream, ix->meta.as<PointMeta>(),
+                    ix->D32.as<float>(), ix->npad, n, inv_scale, rb_ptr, rb_hist, ix->row_order.as<int32_t>());
     }
     // per-row streaming work (from the grouping pass) -> heavy rows first, then closest-anchor order
     ANNB_CUDA(cudaStreamSynchronize(c->stream));
@@ -2423,13 +2637,43 @@ ANNB_API int annb_index_update_bounds(annb_index *ix, int64_t *n_updated)
     ANNB_CUDA(cudaMemsetAsync(ix->counters.p, 0, 64, c->stream));
     ANNB_LAUNCH(tighten_heavy_kernel, grid_for_n(c, n), 256, 0, c->stream, ix->twork.as<unsigned long long>(), n,
                 heavy_thr, ix->theavy.as<int32_t>(), ix->counters.as<unsigned long long>() + 4);
-    ANNB_CUDA(cudaFuncSetAttribute(tighten_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   TG_SLOTS * 8));
-    ANNB_LAUNCH(tighten_grouped_kernel, tg_grid, 512, TG_SLOTS * 8, c->stream, V, ix->kptr.as<int64_t>(),
-                ix->kids.as<int32_t>(), ix->kds.as<float>(), ix->gptr.as<int64_t>(), ix->gJ.as<int32_t>(),
-                ix->gsrc.as<int32_t>(), ix->row_order.as<int32_t>(), ix->theavy.as<int32_t>(),
-                ix->counters.as<unsigned long long>() + 4, ix->twork.as<unsigned long long>(), heavy_thr,
-                ix->n_tight > 0 ? 1 : 0, ix->t0.as<float>(), ix->t1.as<float>(), ix->t2.as<uint8_t>());
+    // membership-bitmap kernel while a bit per point fits shared memory (N <~ 1.2 M), else the bucket hash
+    const int W = (int)((n + 1023) / 1024 * 32);
+    const size_t tb_smem = (size_t)W * 4 + TB_CHUNK * 4 + (size_t)W * 2 + 64;
+    const bool force_hash = getenv("ANNB_TIGHTEN_HASH") != nullptr;  // test knob: bucket-hash kernel
+    int tb_chunk = getenv("ANNB_TB_CHUNK") ? atoi(getenv("ANNB_TB_CHUNK")) : TB_CHUNK;  // test knob: small chunks
+    tb_chunk = std::max(32, std::min(tb_chunk, TB_CHUNK));
+    if (tb_smem <= 220 * 1024 && !force_hash) {
+        // as many 512-thread CTAs per SM as the table allows (<= 4); one 1024-thread CTA for large N
+        const int per_sm = (int)std::min<size_t>(4, (227 * 1024) / (tb_smem + 1024));
+        if (per_sm >= 2) {
+            ANNB_CUDA(cudaFuncSetAttribute(tighten_bitmap_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)tb_smem));
+            ANNB_LAUNCH(tighten_bitmap_kernel<512>, c->num_sms * per_sm, 512, tb_smem, c->stream, V,
+                        ix->kptr.as<int64_t>(), ix->kids.as<int32_t>(), ix->kds.as<float>(), ix->gptr.as<int64_t>(),
+                        ix->gJ.as<int32_t>(), ix->gsrc.as<int32_t>(), ix->row_order.as<int32_t>(),
+                        ix->theavy.as<int32_t>(), ix->counters.as<unsigned long long>() + 4,
+                        ix->twork.as<unsigned long long>(), heavy_thr, ix->n_tight > 0 ? 1 : 0, ix->t0.as<float>(),
+                        ix->t1.as<float>(), ix->t2.as<uint8_t>(), W, tb_chunk);
+        } else {
+            ANNB_CUDA(cudaFuncSetAttribute(tighten_bitmap_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)tb_smem));
+            ANNB_LAUNCH(tighten_bitmap_kernel<1024>, c->num_sms, 1024, tb_smem, c->stream, V,
+                        ix->kptr.as<int64_t>(), ix->kids.as<int32_t>(), ix->kds.as<float>(), ix->gptr.as<int64_t>(),
+                        ix->gJ.as<int32_t>(), ix->gsrc.as<int32_t>(), ix->row_order.as<int32_t>(),
+                        ix->theavy.as<int32_t>(), ix->counters.as<unsigned long long>() + 4,
+                        ix->twork.as<unsigned long long>(), heavy_thr, ix->n_tight > 0 ? 1 : 0, ix->t0.as<float>(),
+                        ix->t1.as<float>(), ix->t2.as<uint8_t>(), W, tb_chunk);
+        }
+    } else {
+        ANNB_CUDA(cudaFuncSetAttribute(tighten_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       TG_SLOTS * 8));
+        ANNB_LAUNCH(tighten_grouped_kernel, tg_grid, 512, TG_SLOTS * 8, c->stream, V, ix->kptr.as<int64_t>(),
+                    ix->kids.as<int32_t>(), ix->kds.as<float>(), ix->gptr.as<int64_t>(), ix->gJ.as<int32_t>(),
+                    ix->gsrc.as<int32_t>(), ix->row_order.as<int32_t>(), ix->theavy.as<int32_t>(),
+                    ix->counters.as<unsigned long long>() + 4, ix->twork.as<unsigned long long>(), heavy_thr,
+                    ix->n_tight > 0 ? 1 : 0, ix->t0.as<float>(), ix->t1.as<float>(), ix->t2.as<uint8_t>());
+    }
     ANNB_CUDA(cudaMemsetAsync(ix->counters.p, 0, 64, c->stream));
     ANNB_LAUNCH(compact_improved_kernel, grid_for_n(c, m), 256, 0, c->stream, ix->nxt_i.as<int32_t>(),
                 ix->nxt_j.as<int32_t>(), ix->t0.as<float>(), ix->t1.as<float>(), ix->t2.as<uint8_t>(), m,
@@ -2554,7 +2798,6 @@ ANNB_API int annb_index_sample_pool(annb_index *ix, uint64_t seed, int64_t max_p
     ix->n_pool = 0;
     *n_pool = 0;
     if (n_nc <= 0) return ANNB_OK;
-    ANNB_TRY(tile_lists_rebuild(ix));
     SampleArgs A;
     A.V = ix->view();
     A.seed = (uint32_t)(mix64(seed) >> 32);

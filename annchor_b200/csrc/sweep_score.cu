@@ -353,13 +353,7 @@ __global__ void __launch_bounds__(256, 2) sample_sweep_kernel(const SampleArgs A
     float *sDj = sDi + na * SROW;
     PointMeta *sMi = reinterpret_cast<PointMeta *>(sDj + na * SROW);
     PointMeta *sMj = sMi + TILE;
-    unsigned char *sTS = reinterpret_cast<unsigned char *>(sMj + TILE);
-    uint32_t *bm = reinterpret_cast<uint32_t *>(sTS);
-    uint32_t *sCode = reinterpret_cast<uint32_t *>(sTS + TS_BYTES);  // [TL_CAP]
-    TileDesc *sDesc = reinterpret_cast<TileDesc *>(sCode + TL_CAP);
-    uint32_t *queue = reinterpret_cast<uint32_t *>(sDesc + 1) + warp * QCAP;  // li | lj << 8
-    TileStore ts;
-    ts.init(sTS);
+    uint32_t *queue = reinterpret_cast<uint32_t *>(sMj + TILE) + warp * QCAP;  // li | lj << 8
     const int64_t NT = (int64_t)V.T * (V.T + 1) / 2;
     const int64_t nq = (NT - A.rank + A.world - 1) / A.world;
     const int64_t per = (nq + gridDim.x - 1) / gridDim.x;
@@ -374,19 +368,11 @@ __global__ void __launch_bounds__(256, 2) sample_sweep_kernel(const SampleArgs A
         int ti, tj;
         tile_from_index(m * A.world + A.rank, V.T, ti, tj);
         __syncthreads();
-        if (tid == 0) {
-            const int64_t t = m * A.world + A.rank;
-            sDesc->base = V.tl_ptr[t];
-            sDesc->end = V.tl_ptr[t + 1];
-        }
-        __syncthreads();
         load_point_tile(V, ti, sDi, sMi);
         load_point_tile(V, tj, sDj, sMj);
-        load_tile_codes(V, sDesc, sCode);
         cp_async_commit();
         cp_async_wait_all();
         __syncthreads();
-        build_tile_store(V, ts, sDesc, sCode, bm, 0);
         const bool diag = ti == tj;
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
@@ -414,11 +400,10 @@ __global__ void __launch_bounds__(256, 2) sample_sweep_kernel(const SampleArgs A
                     const int gi2 = ti * TILE + li2, gj = tj * TILE + lj;
                     const PointMeta pi = sMi[li2], pj = sMj[lj];
                     if (pi.slot < 0 && pj.slot < 0 && is_candidate(pi, pj)) {  // anchor pairs are computed
-                        bool known = false;
-                        if (flag_bit(bm, li2, lj)) {
-                            float a, b;
-                            known = store_lookup(V, ts, li2, lj, (uint32_t)gi2, (uint32_t)gj, a, b) == KIND_KNOWN;
-                        }
+                        // only the hash-selected sub-sample gets here: the known-pair check goes to the hash
+                        // map directly, so the per-tile lists need not be current for this sweep
+                        float a, b;
+                        const bool known = hash_lookup(V, pair_key((uint32_t)gi2, (uint32_t)gj), a, b) == KIND_KNOWN;
                         if (!known) {
                             emit = true;
                             key = pair_key((uint32_t)gi2, (uint32_t)gj);
@@ -446,7 +431,7 @@ __global__ void __launch_bounds__(256, 2) sample_sweep_kernel(const SampleArgs A
 int launch_sample_sweep(annb_ctx *c, const SampleArgs &A)
 {
     const size_t smem = (size_t)2 * A.V.na * SROW * 4 + 2 * TILE * sizeof(PointMeta) +
-                        TS_BYTES + TL_CAP * 4 + sizeof(TileDesc) + (size_t)8 * QCAP * 4 + 64;
+                        (size_t)8 * QCAP * 4 + 64;
     ANNB_CUDA(cudaFuncSetAttribute(sample_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)smem));
     const int64_t NT = (int64_t)A.V.T * (A.V.T + 1) / 2;

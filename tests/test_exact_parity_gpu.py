@@ -257,10 +257,16 @@ def test_tighten_kernel_strings_bit_exact(gpu_ctx):
     assert np.all(again[:, 0] >= got[:, 0]) and np.all(again[:, 1] <= got[:, 1])
 
 
-def test_tighten_kernel_hub_rows_in_chunks(gpu_ctx):
-    """Rows with more than 2048 known distances go through the kernel's shared-memory table in
-    several chunks whose partial results are combined; float32 data, device-evaluated distances,
-    equality with the float32 restatement."""
+@pytest.mark.parametrize("variant", ["bitmap", "bitmap_small_chunks", "bucket_hash"])
+def test_tighten_kernel_hub_rows_in_chunks(gpu_ctx, monkeypatch, variant):
+    """Rows with many known distances go through the kernels' shared-memory tables in several
+    chunks whose partial results are combined (membership-bitmap kernel: ANNB_TB_CHUNK entries per
+    pass; bucket-hash kernel used beyond N ~ 1.2 M: 2048); float32 data, device-evaluated
+    distances, equality with the float32 restatement."""
+    if variant == "bitmap_small_chunks":
+        monkeypatch.setenv("ANNB_TB_CHUNK", "512")
+    if variant == "bucket_hash":
+        monkeypatch.setenv("ANNB_TIGHTEN_HASH", "1")
     n = 3000
     X = bench_blobs(n, 16, 10, 1, np.float32)
     import annchor_b200 as ab
