@@ -444,6 +444,45 @@ class Annchor:
         return self
 
 
+class BruteForce:
+    """Exact k-NN graph on the B200 -- the reference's ``BruteForce`` (annchor/annchor.py:943-1023):
+    ``BruteForce(X, func).fit().neighbor_graph``.
+
+    The reference materialises the full (nx, nx) distance matrix and returns its row-wise argsort /
+    sort.  Here ``n_neighbors`` columns are returned (column 0 = the point itself at distance 0, like
+    the rows of the reference's graph); ``n_neighbors=None`` means all ``nx`` columns, which is only
+    accepted for nx <= 4096.  Euclidean / cosine rows of up to 128 dimensions go through the
+    tensor-core path (bf16-split GEMM prunes, the exact metric kernel re-ranks, a per-row
+    certificate guarantees exactness; csrc/bruteforce.cu); everything else is all-pairs through the
+    metric kernels.  Ties are ordered by neighbour id.
+    """
+
+    def __init__(self, X, func, func_kwargs=None, verbose=False, get_exact_ijs=None, backend="loky",
+                 n_neighbors=None, device=0, ctx=None, _dataset=None):
+        if not isinstance(func, str) or func not in _lib.METRIC_IDS:
+            raise NotImplementedError("annchor_b200.BruteForce evaluates one of %s on the GPU; there is no CPU "
+                                      "fallback for callables" % sorted(_lib.METRIC_IDS))
+        if get_exact_ijs is not None and not isinstance(get_exact_ijs, GpuExactIJs):
+            raise NotImplementedError("get_exact_ijs must be None or an annchor_b200.GpuExactIJs")
+        cost = (func_kwargs or {}).get("cost_matrix") if func == "wasserstein" else None
+        self.X = X
+        self.nx = len(X)
+        self.f = func
+        self.verbose = verbose
+        if n_neighbors is None:
+            if self.nx > 4096:
+                raise ValueError("BruteForce on %d points: pass n_neighbors (the full (nx, nx) sorted matrix "
+                                 "the reference returns is not materialised beyond nx = 4096)" % self.nx)
+            n_neighbors = self.nx
+        self.n_neighbors = int(n_neighbors)
+        self.ctx = ctx or default_context(device)
+        self._dataset = _dataset if _dataset is not None else Dataset(self.ctx, X, func, cost_matrix=cost)
+
+    def fit(self):
+        self.neighbor_graph = self._dataset.bruteforce_knn(self.n_neighbors)
+        return self
+
+
 def compare_neighbor_graphs(nng_1, nng_2, n_neighbors):
     """Tie-aware number of incorrect NN pairs (annchor/annchor.py:1026-1066): per row the multiset
     difference of the first n_neighbors distances rounded to 3 decimals."""

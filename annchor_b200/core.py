@@ -131,6 +131,14 @@ class Dataset:
                                       ptr(out)))
         return out
 
+    def bruteforce_knn(self, k):
+        """Exact k-NN graph (annchor/annchor.py:943-1023): (idx int64 (n, k), dist float64 (n, k)),
+        column 0 = the point itself; ties ordered by neighbour id."""
+        idx = np.empty((self.n, int(k)), dtype=np.int64)
+        dist = np.empty((self.n, int(k)), dtype=np.float64)
+        check(self._L.annb_bruteforce_knn(self.ctx.handle, self.handle, self.metric, int(k), ptr(idx), ptr(dist)))
+        return idx, dist
+
     def maxmin_anchors(self, n_anchors, first):
         """MaxMinAnchorPicker core (annchor/pickers.py:18-52) -> (A int64[na], D float64 (n, na))."""
         A = np.empty(n_anchors, dtype=np.int64)

@@ -961,15 +961,16 @@ tighten_bitmap_kernel(View V, const int64_t *__restrict__ kptr, const int32_t *_
                     }
 #pragma unroll
                     for (int u = 0; u < TGU; ++u) {
+                        // branch-free: the rank of a miss is still a valid index into vals (<= mc), its
+                        // contribution is masked; padding lanes (id = 0xffffffff) probe word 0 and never hit
                         const uint32_t id = idv[u];
-                        const bool valid = id != 0xffffffffu;
-                        const uint32_t w = valid ? (id >> 5) : 0u;
+                        const uint32_t w = min(id >> 5, (uint32_t)(W - 1));
                         const uint32_t word = bits[w];
-                        if (valid && ((word >> (id & 31)) & 1u)) {
-                            const float x = vals[pre[w] + __popc(word & ((1u << (id & 31)) - 1u))];
-                            lb = fmaxf(lb, fabsf(x - yv[u]));
-                            ub = fminf(ub, x + yv[u]);
-                        }
+                        const uint32_t bit = 1u << (id & 31);
+                        const bool hit = (word & bit) != 0u && id != 0xffffffffu;
+                        const float x = vals[pre[w] + __popc(word & (bit - 1u))];
+                        lb = fmaxf(lb, hit ? fabsf(x - yv[u]) : 0.0f);
+                        ub = fminf(ub, hit ? x + yv[u] : INFINITY);
                     }
 #pragma unroll
                     for (int u = 0; u < TGU; ++u) {

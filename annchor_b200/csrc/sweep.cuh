@@ -23,6 +23,16 @@
 
 namespace annb {
 
+// Threads per sweep CTA: 256 (each thread takes two 4 x 8 half passes of the 128 x 128 tile, <= 255
+// registers) or 512 (one half pass each, <= 128 registers, 16 warps per SM to hide the fixed-latency
+// and barrier stalls ncu shows at 8 warps).
+#ifndef ANNB_SWEEP_THREADS
+#define ANNB_SWEEP_THREADS 256
+#endif
+constexpr int SWT = ANNB_SWEEP_THREADS;
+constexpr int SWW = SWT / 32;         // warps per sweep CTA
+constexpr int SW_HALVES = 512 / SWT;  // half passes per thread
+constexpr int SW_PASSES = SW_HALVES * 5;  // per half pass: 4 row steps + 1 drain-only step
 constexpr int QCAP = 512;   // per-warp survivor queue; drained when a row step (<= 256 new) might overflow it
 constexpr int QROW = 256;   // survivors one micro-tile row step can add: 8 pairs x 32 lanes
 

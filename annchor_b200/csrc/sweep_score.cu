@@ -16,7 +16,7 @@
 
 namespace annb {
 
-constexpr int EMIT_CAP = 256;  // per-warp emission staging (entries)
+constexpr int EMIT_CAP = SWT == 512 ? 128 : 256;  // per-warp emission staging (entries)
 
 
 // flush a warp's staged emissions with ONE global atomic
@@ -39,7 +39,7 @@ __device__ __forceinline__ void flush_emit(const ScoreArgs &A, uint64_t *ek, uin
 // shared-memory queue; phase 2 (ONE code instance: the row steps and the end-of-tile flush are
 // cases of a rolled 9-step loop) drains the queue in full 32-lane batches when the tile is done,
 // or earlier if the next row step could overflow it.
-__global__ void __launch_bounds__(256, 1) score_sweep_kernel(const __grid_constant__ ScoreArgs A)
+__global__ void __launch_bounds__(SWT, 1) score_sweep_kernel(const __grid_constant__ ScoreArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const View &V = A.V;
@@ -61,16 +61,16 @@ __global__ void __launch_bounds__(256, 1) score_sweep_kernel(const __grid_consta
     TileDesc *sDesc = reinterpret_cast<TileDesc *>(sCode + 2 * TL_CAP);   // [4] descriptors in flight
     unsigned char *sp = reinterpret_cast<unsigned char *>(sDesc + 4);
     Survivor *queue = reinterpret_cast<Survivor *>(sp) + warp * A.qcap;
-    sp += (size_t)8 * A.qcap * sizeof(Survivor);
+    sp += (size_t)SWW * A.qcap * sizeof(Survivor);
     uint64_t *ek = reinterpret_cast<uint64_t *>(sp) + warp * EMIT_CAP;  // per-warp emission staging
-    sp += 8 * EMIT_CAP * sizeof(uint64_t);
+    sp += SWW * EMIT_CAP * sizeof(uint64_t);
     uint16_t *el = reinterpret_cast<uint16_t *>(sp) + warp * EMIT_CAP;
-    sp += 8 * EMIT_CAP * sizeof(uint16_t);
+    sp += SWW * EMIT_CAP * sizeof(uint16_t);
     float *thI = reinterpret_cast<float *>(sp);  // [2][128] thresh of the row tile (double-buffered)
     float *thJ = thI + 2 * TILE;                 // [2][128] thresh of the column tile
     TileModel *tm = reinterpret_cast<TileModel *>(thJ + 2 * TILE);
-    int *qcnt = reinterpret_cast<int *>(tm + 1) + warp;  // [8] queue lengths
-    uint32_t *sHist = reinterpret_cast<uint32_t *>(reinterpret_cast<int *>(tm + 1) + 8);
+    int *qcnt = reinterpret_cast<int *>(tm + 1) + warp;  // [SWW] queue lengths
+    uint32_t *sHist = reinterpret_cast<uint32_t *>(reinterpret_cast<int *>(tm + 1) + SWW);
     float *sErr = reinterpret_cast<float *>(sHist + A.nlevels);       // error tables + level ranks, if they fit
     uint16_t *sRank = reinterpret_cast<uint16_t *>(sErr + A.n_errs);
     const float *errs = A.tables_in_smem ? sErr : A.errs;
@@ -165,9 +165,9 @@ __global__ void __launch_bounds__(256, 1) score_sweep_kernel(const __grid_consta
         }
         float lb[4][8], ub[4][8];
 #pragma unroll 1
-        for (int pass = 0; pass < 10; ++pass) {  // 2 x (4 row steps + 1 drain-only step)
+        for (int pass = 0; pass < SW_PASSES; ++pass) {  // per half pass: 4 row steps + 1 drain-only step
             const int h = pass >= 5 ? 1 : 0, step = pass - 5 * h;
-            const int row0 = h * 64 + ty * 4;
+            const int row0 = h * (SWT / 4) + ty * 4;
             if (step == 0) {
                 bounds_half(sDi, sDj, na, row0, tx, lb, ub);
                 if (ti == tj) mask_diagonal<true>(row0, tx, lb, ub);
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(256, 1) score_sweep_kernel(const __grid_consta
             }
             __syncwarp();
             const int qn = *reinterpret_cast<volatile int *>(qcnt);
-            if (pass < 9 && qn <= A.qcap - QROW) continue;  // room for another row step
+            if (pass < SW_PASSES - 1 && qn <= A.qcap - QROW) continue;  // room for another row step
             // ---- phase 2: drain the queue, one survivor per lane ----
             if (lane == 0) n_staged += qn;
             for (int e0 = 0; e0 < qn; e0 += 32) {
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(256, 1) score_sweep_kernel(const __grid_consta
             if (lane == 0) *qcnt = 0;
             __syncwarp();
         }
-        n_swept += 64;
+        n_swept += 32 * SW_HALVES;
     }
     if (A.emit_key) flush_emit(A, ek, el, en, lane);
     __syncthreads();
@@ -313,25 +313,25 @@ int launch_score_sweep(annb_ctx *c, ScoreArgs &A)
     const size_t lim = 227 * 1024;
     const size_t base = (size_t)4 * A.V.na * SROW * 4 + 4 * TILE * sizeof(PointMeta) +
                         TS_BYTES + 2 * TL_CAP * 4 + 4 * sizeof(TileDesc) +
-                        (size_t)8 * EMIT_CAP * 10 + 4 * TILE * 4 + sizeof(TileModel) +
-                        8 * 4 + (size_t)A.nlevels * 4 + 64;
+                        (size_t)SWW * EMIT_CAP * 10 + 4 * TILE * 4 + sizeof(TileModel) +
+                        SWW * 4 + (size_t)A.nlevels * 4 + 64;
     const size_t tables = ((size_t)A.n_errs * 4 + (size_t)(A.n_errs + A.M.nb) * 2 + 15) & ~(size_t)15;
-    const size_t qmin = (size_t)8 * (QROW + 32) * sizeof(Survivor);
+    const size_t qmin = (size_t)SWW * (QROW + 32) * sizeof(Survivor);
     ANNB_REQUIRE(base + qmin <= lim, ANNB_ERANGE,
                  "score sweep needs %zu bytes of shared memory (n_anchors=%d, %d levels)", base + qmin,
                  A.V.na, A.nlevels);
     A.tables_in_smem = base + qmin + tables <= lim ? 1 : 0;
     size_t avail = lim - base - (A.tables_in_smem ? tables : 0);
-    int qcap = (int)(avail / (8 * sizeof(Survivor))) / 32 * 32;
+    int qcap = (int)(avail / (SWW * sizeof(Survivor))) / 32 * 32;
     if (qcap > QCAP) qcap = QCAP;
     A.qcap = qcap;
-    const size_t smem = base + (A.tables_in_smem ? tables : 0) + (size_t)8 * qcap * sizeof(Survivor);
+    const size_t smem = base + (A.tables_in_smem ? tables : 0) + (size_t)SWW * qcap * sizeof(Survivor);
     ANNB_CUDA(cudaFuncSetAttribute(score_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)smem));
     const int64_t nq = (A.q_end - A.q_begin + A.q_stride - 1) / A.q_stride;
     int grid = c->num_sms;
     if (nq < grid) grid = nq < 1 ? 1 : (int)nq;
-    ANNB_LAUNCH(score_sweep_kernel, grid, 256, smem, c->stream, A);
+    ANNB_LAUNCH(score_sweep_kernel, grid, SWT, smem, c->stream, A);
     return ANNB_OK;
 }
 

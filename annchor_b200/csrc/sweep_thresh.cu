@@ -57,7 +57,7 @@ struct SortedRow {
 };
 
 template <bool L2ON>
-__global__ void __launch_bounds__(256, 1) thresh_sweep_kernel(const __grid_constant__ ThreshArgs A)
+__global__ void __launch_bounds__(SWT, 1) thresh_sweep_kernel(const __grid_constant__ ThreshArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const View &V = A.V;
@@ -78,11 +78,11 @@ __global__ void __launch_bounds__(256, 1) thresh_sweep_kernel(const __grid_const
     TileDesc *sDesc = reinterpret_cast<TileDesc *>(sCode + 2 * TL_CAP);  // [4]
     TileModel *tm = reinterpret_cast<TileModel *>(sDesc + 4);
     Survivor *queue = reinterpret_cast<Survivor *>(tm + 1) + warp * A.qcap;
-    float *thr1 = reinterpret_cast<float *>(reinterpret_cast<Survivor *>(tm + 1) + 8 * A.qcap);
+    float *thr1 = reinterpret_cast<float *>(reinterpret_cast<Survivor *>(tm + 1) + SWW * A.qcap);
     float *thr2 = thr1 + TILE;
     float *cut = thr2 + TILE;  // max(thr1, thr2): phase-1 cut-off per row
-    int *qcnt = reinterpret_cast<int *>(cut + TILE) + warp;  // [8]
-    float *L1 = reinterpret_cast<float *>(reinterpret_cast<int *>(cut + TILE) + 8);
+    int *qcnt = reinterpret_cast<int *>(cut + TILE) + warp;  // [SWW]
+    float *L1 = reinterpret_cast<float *>(reinterpret_cast<int *>(cut + TILE) + SWW);
     float *L2v = L1 + TILE * A.k1;
     int32_t *L2i = reinterpret_cast<int32_t *>(L2v + TILE * A.k2);
     const bool filter = V.is_metric != 0;  // is_metric=False overrides anchor pairs with raw D (annchor.py:368-372)
@@ -145,9 +145,9 @@ __global__ void __launch_bounds__(256, 1) thresh_sweep_kernel(const __grid_const
             for (int c = 0; c < 8; ++c) cAj[c] = sMj[micro_off(tx, c)].cA * SROW;
             float lb[4][8], ub[4][8];
 #pragma unroll 1
-            for (int pass = 0; pass < 10; ++pass) {  // 2 x (4 row steps + 1 drain-only step)
+            for (int pass = 0; pass < SW_PASSES; ++pass) {  // per half pass: 4 row steps + 1 drain-only step
                 const int h = pass >= 5 ? 1 : 0, step = pass - 5 * h;
-                const int row0 = h * 64 + ty * 4;
+                const int row0 = h * (SWT / 4) + ty * 4;
                 if (step == 0) {
                     bounds_half(sDi, sDj, na, row0, tx, lb, ub);
                     if (tc == rb) mask_diagonal<false>(row0, tx, lb, ub);
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(256, 1) thresh_sweep_kernel(const __grid_const
                 }
                 __syncwarp();
                 const int qn = *reinterpret_cast<volatile int *>(qcnt);
-                if (pass < 9 && qn <= A.qcap - QROW) continue;  // room for another row step
+                if (pass < SW_PASSES - 1 && qn <= A.qcap - QROW) continue;  // room for another row step
                 // ---- phase 2: drain the queue, one survivor per lane ----
                 for (int e0 = 0; e0 < qn; e0 += 32) {
                     const int e = e0 + lane;
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(256, 1) thresh_sweep_kernel(const __grid_const
                 }
                 __syncwarp();
                 // refresh the phase-1 cut-offs of this warp's 16 rows ({8w..8w+7} U {64+8w..})
-                if (lane < 16) {
+                if (lane < 8 * SW_HALVES) {  // this warp's rows: {8w..8w+7} (and {64+8w..} with 256 threads)
                     const int row = (lane < 8) ? (warp * 8 + lane) : (64 + warp * 8 + (lane - 8));
                     cut[row] = fmaxf(thr1[row], thr2[row]);
                 }
@@ -253,23 +253,23 @@ __global__ void __launch_bounds__(256, 1) thresh_sweep_kernel(const __grid_const
 static size_t thresh_smem_base(int na, int k1, int k2)
 {
     return (size_t)3 * na * SROW * 4 + 3 * TILE * sizeof(PointMeta) + TS_BYTES + BITMAP_WORDS * 4 + 2 * TL_CAP * 4 +
-           4 * sizeof(TileDesc) + sizeof(TileModel) + 3 * TILE * 4 + 8 * 4 + (size_t)TILE * k1 * 4 + (size_t)TILE * k2 * 8 + 64;
+           4 * sizeof(TileDesc) + sizeof(TileModel) + 3 * TILE * 4 + SWW * 4 + (size_t)TILE * k1 * 4 + (size_t)TILE * k2 * 8 + 64;
 }
 
 int launch_thresh_sweep(annb_ctx *c, ThreshArgs &A)
 {
     const size_t lim = 227 * 1024;
     const size_t base = thresh_smem_base(A.V.na, A.k1, A.k2);
-    ANNB_REQUIRE(base + (size_t)8 * (QROW + 32) * sizeof(Survivor) <= lim, ANNB_ERANGE,
+    ANNB_REQUIRE(base + (size_t)SWW * (QROW + 32) * sizeof(Survivor) <= lim, ANNB_ERANGE,
                  "thresh sweep needs %zu bytes of shared memory (n_anchors=%d, lists %d/%d)",
-                 base + (size_t)8 * (QROW + 32) * sizeof(Survivor), A.V.na, A.k1, A.k2);
+                 base + (size_t)SWW * (QROW + 32) * sizeof(Survivor), A.V.na, A.k1, A.k2);
     ANNB_REQUIRE(A.k1 <= MAX_LIST && A.k2 <= MAX_LIST, ANNB_ERANGE,
                  "n_neighbors too large for the device row lists (k1=%d, k2=%d, max %d)", A.k1, A.k2,
                  MAX_LIST);
-    int qcap = (int)((lim - base) / (8 * sizeof(Survivor))) / 32 * 32;
+    int qcap = (int)((lim - base) / (SWW * sizeof(Survivor))) / 32 * 32;
     if (qcap > QCAP) qcap = QCAP;
     A.qcap = qcap;
-    const size_t smem = base + (size_t)8 * qcap * sizeof(Survivor);
+    const size_t smem = base + (size_t)SWW * qcap * sizeof(Survivor);
     const int n_rb = A.rb_list ? A.n_rb : A.V.T;
     const int rows_here = (n_rb - A.rank + A.world - 1) / A.world;
     const int grid = rows_here < 1 ? 1 : rows_here;
@@ -277,11 +277,11 @@ int launch_thresh_sweep(annb_ctx *c, ThreshArgs &A)
     if (A.k2 > 0) {
         ANNB_CUDA(cudaFuncSetAttribute(thresh_sweep_kernel<true>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ANNB_LAUNCH(thresh_sweep_kernel<true>, grid, 256, smem, c->stream, A);
+        ANNB_LAUNCH(thresh_sweep_kernel<true>, grid, SWT, smem, c->stream, A);
     } else {
         ANNB_CUDA(cudaFuncSetAttribute(thresh_sweep_kernel<false>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ANNB_LAUNCH(thresh_sweep_kernel<false>, grid, 256, smem, c->stream, A);
+        ANNB_LAUNCH(thresh_sweep_kernel<false>, grid, SWT, smem, c->stream, A);
     }
     return ANNB_OK;
 }
@@ -294,7 +294,7 @@ int launch_thresh_sweep(annb_ctx *c, ThreshArgs &A)
 // record list of either endpoint whose bound it does not exceed; thresh_select_kernel finishes per
 // row.  Rows whose record list overflowed are recomputed by the row sweep (launch with rb_list).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 1) thresh_pairs_kernel(const __grid_constant__ ThreshPairArgs A)
+__global__ void __launch_bounds__(SWT, 1) thresh_pairs_kernel(const __grid_constant__ ThreshPairArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const View &V = A.V;
@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(256, 1) thresh_pairs_kernel(const __grid_const
     uint32_t *sCode = reinterpret_cast<uint32_t *>(sTS + TS_BYTES);  // [2][TL_CAP]
     TileDesc *sDesc = reinterpret_cast<TileDesc *>(sCode + 2 * TL_CAP);  // [4]
     Survivor *queue = reinterpret_cast<Survivor *>(sDesc + 4) + warp * A.qcap;
-    float *c1I = reinterpret_cast<float *>(reinterpret_cast<Survivor *>(sDesc + 4) + 8 * A.qcap);
+    float *c1I = reinterpret_cast<float *>(reinterpret_cast<Survivor *>(sDesc + 4) + SWW * A.qcap);
     float *c1J = c1I + 2 * TILE;  // [2][128] each: cut1 / cut2 of the row and column tiles (double-buffered)
     float *c2I = c1J + 2 * TILE;
     float *c2J = c2I + 2 * TILE;
@@ -387,9 +387,9 @@ __global__ void __launch_bounds__(256, 1) thresh_pairs_kernel(const __grid_const
         }
         float lb[4][8], ub[4][8];
 #pragma unroll 1
-        for (int pass = 0; pass < 10; ++pass) {  // 2 x (4 row steps + 1 drain-only step)
+        for (int pass = 0; pass < SW_PASSES; ++pass) {  // per half pass: 4 row steps + 1 drain-only step
             const int h = pass >= 5 ? 1 : 0, step = pass - 5 * h;
-            const int row0 = h * 64 + ty * 4;
+            const int row0 = h * (SWT / 4) + ty * 4;
             if (step == 0) {
                 bounds_half(sDi, sDj, na, row0, tx, lb, ub);
                 if (ti == tj) mask_diagonal<true>(row0, tx, lb, ub);
@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(256, 1) thresh_pairs_kernel(const __grid_const
             }
             __syncwarp();
             const int qn = *reinterpret_cast<volatile int *>(qcnt);
-            if (pass < 9 && qn <= A.qcap - QROW) continue;
+            if (pass < SW_PASSES - 1 && qn <= A.qcap - QROW) continue;
             for (int e0 = 0; e0 < qn; e0 += 32) {
                 const int e = e0 + lane;
                 if (e < qn) {
@@ -456,20 +456,20 @@ int launch_thresh_pairs(annb_ctx *c, ThreshPairArgs &A)
 {
     const size_t lim = 227 * 1024;
     const size_t base = (size_t)4 * A.V.na * SROW * 4 + 4 * TILE * sizeof(PointMeta) + TS_BYTES +
-                        2 * TL_CAP * 4 + 4 * sizeof(TileDesc) + 8 * TILE * 4 + sizeof(TileModel) + 8 * 4 + 64;
-    ANNB_REQUIRE(base + (size_t)8 * (QROW + 32) * sizeof(Survivor) <= lim, ANNB_ERANGE,
+                        2 * TL_CAP * 4 + 4 * sizeof(TileDesc) + 8 * TILE * 4 + sizeof(TileModel) + SWW * 4 + 64;
+    ANNB_REQUIRE(base + (size_t)SWW * (QROW + 32) * sizeof(Survivor) <= lim, ANNB_ERANGE,
                  "threshold pair sweep needs %zu bytes of shared memory (n_anchors=%d)",
-                 base + (size_t)8 * (QROW + 32) * sizeof(Survivor), A.V.na);
-    int qcap = (int)((lim - base) / (8 * sizeof(Survivor))) / 32 * 32;
+                 base + (size_t)SWW * (QROW + 32) * sizeof(Survivor), A.V.na);
+    int qcap = (int)((lim - base) / (SWW * sizeof(Survivor))) / 32 * 32;
     if (qcap > QCAP) qcap = QCAP;
     A.qcap = qcap;
-    const size_t smem = base + (size_t)8 * qcap * sizeof(Survivor);
+    const size_t smem = base + (size_t)SWW * qcap * sizeof(Survivor);
     ANNB_CUDA(cudaFuncSetAttribute(thresh_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t NT = (int64_t)A.V.T * (A.V.T + 1) / 2;
     const int64_t nq = (NT - A.rank + A.world - 1) / A.world;
     int grid = c->num_sms;
     if (nq < grid) grid = nq < 1 ? 1 : (int)nq;
-    ANNB_LAUNCH(thresh_pairs_kernel, grid, 256, smem, c->stream, A);
+    ANNB_LAUNCH(thresh_pairs_kernel, grid, SWT, smem, c->stream, A);
     return ANNB_OK;
 }
 

@@ -8,14 +8,20 @@ A "step" is one complete fit() over that data set.
   value        : N / (device-timed fit with X already resident in HBM)
   e2e          : N / (fit through the public API from host X: H2D of X and D2H of the graph inside
                  the timed region)
-  roofline     : dominant kernel = the fused scoring sweep (bounds + dad + predict + label + prob
-                 + emit, sweep_score.cu); achieved = 25 B/pair "materialised-equivalent" algorithmic
-                 bytes (K2+K3 fused) x pairs per launch / CUDA-event launch duration
+  roofline     : dominant kernel of the launch list = the fused scoring sweep (bounds + dad + predict +
+                 label + prob + emit, sweep_score.cu).  ncu shows it bound by the FP32/ALU issue rate
+                 (DRAM < 3 % of peak), so achieved = algorithmic lane-operations per pair x pairs per
+                 launch / CUDA-event launch duration against 148 SMs x 128 lanes x SM clock; SURVEY 8(d)'s
+                 25 B/pair materialised-equivalent HBM figure is kept under `hbm_equivalent`
   cpu_baseline : the CPU oracle port of the reference's fit() timed on this box's host cores on a
-                 bounded sub-sample, extrapolated with the measured t ~ c*N^2 law (stated in `sample`)
+                 bounded sample of the workload (N=6000 of the same generator); `value` is that
+                 MEASURED figure, the t ~ c*N^2 extrapolation to the full N is a separate labelled field
+  same_n_leg   : the GPU arm on that same N=6000 sample (same effective p_work): the like-for-like
+                 measured pair
 
-`--impl reference` times the same oracle port (the reference itself is numba/joblib Python that
-cannot travel to the GPU box) and prints the same JSON line with impl=reference.
+`--impl reference` times the same oracle port (the reference itself is numba/joblib Python whose
+wheels cannot travel to the GPU box), one fit of the sample per step, and prints the
+same JSON line with impl=reference and the measured sample figures.
 """
 import argparse
 import json
@@ -89,45 +95,57 @@ def oracle_fit_time(n, w, threads_note):
     return time.time() - t, o
 
 
-def cpu_baseline(w, n_sample=6000):
-    """Oracle port on a bounded sample; extrapolate pts/s to the full N with t = c*N^2 (the
-    reference's measured scaling)."""
+N_SAMPLE = 6000  # the bounded sample of the workload the CPU arm can finish in ~12 s per fit
+
+
+def cpu_baseline(w, n_sample=N_SAMPLE):
+    """The CPU port of the reference's fit() timed on this box's host cores on a bounded sample of the
+    workload (same generator, N = n_sample).  `value` is what was MEASURED there; the t = c*N^2
+    extrapolation to the full N (the reference's measured scaling) is reported
+    separately and labelled."""
     cores = os.cpu_count()
     oracle_fit_time(600, w, cores)  # warm-up (page-in, OpenMP pool)
     dt, o = oracle_fit_time(n_sample, w, cores)
-    c = dt / (n_sample ** 2)
-    t_full = c * w["N"] ** 2
-    return {"value": w["N"] / t_full, "unit": "points/s", "cores": cores, "kind": "port",
-            "sample": "oracle (numpy + C/OpenMP port of the reference fit(), %d threads) on N=%d of the "
-                      "same generator: %.2f s = %.0f points/s measured; value is extrapolated to N=%d "
-                      "with t=c*N^2 (the reference needs ~0.7 TB host RAM at this N and cannot run)"
-                      % (cores, n_sample, dt, n_sample / dt, w["N"]),
-            "measured_points_per_s_at_sample": n_sample / dt, "sample_n": n_sample, "sample_seconds": dt,
-            "p_work_effective": o.p_work}
+    t_full = dt / (n_sample ** 2) * w["N"] ** 2
+    return {"value": n_sample / dt, "unit": "points/s", "cores": cores, "kind": "port",
+            "sample": "oracle (numpy + C/OpenMP port of the reference fit(), %d threads) on N=%d of the same "
+                      "generator: one fit = %.2f s, measured; the reference's p_work floor makes the effective "
+                      "p_work %.4f at this N" % (cores, n_sample, dt, o.p_work),
+            "sample_n": n_sample, "sample_seconds": dt, "p_work_effective": o.p_work,
+            "extrapolated_to_workload": {"points_per_s": w["N"] / t_full, "seconds": t_full,
+                                         "how": "t = c*N^2 from the measured sample (NOT a measurement: the "
+                                                "reference needs ~0.7 TB of host RAM at N=100000)"}}
 
 
 def run_reference(args, w):
+    """--impl reference: the reference's CPU path (oracle port; the reference itself is numba/joblib
+    Python whose wheels are absent here) on this box's host cores.  Every step is one
+    fit() on the bounded sample; value / ms_per_step are the MEASURED sample figures."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     vals = []
-    n_s = 6000
+    n_s = N_SAMPLE
     oracle_fit_time(600, w, None)
+    o = None
     for it in range(args.warmup + args.steps):
         dt, o = oracle_fit_time(n_s, w, None)
         if it >= args.warmup:
             vals.append(dt)
     dt = float(np.mean(vals))
+    value = n_s / dt
     t_full = dt / n_s ** 2 * w["N"] ** 2
-    value = w["N"] / t_full
     cores = os.cpu_count()
+    sample = ("each step = one oracle fit() on N=%d of the workload's generator (%.2f s measured, effective "
+              "p_work %.4f); value and ms_per_step are those measured sample figures" % (n_s, dt, o.p_work))
     line = {"impl": "reference", "metric": "k-NN graph points/sec", "value": value, "unit": "points/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_full * 1e3,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": config_dict(w, args.gpus),
-            "cpu_baseline": {"value": value, "unit": "points/s", "cores": cores, "kind": "port",
-                             "sample": "each step = oracle fit() on N=%d (%.2f s); value extrapolated to "
-                                       "N=%d with t=c*N^2" % (n_s, dt, w["N"])},
+            "cpu_baseline": {"value": value, "unit": "points/s", "cores": cores, "kind": "port", "sample": sample,
+                             "sample_n": n_s, "p_work_effective": o.p_work},
+            "extrapolated_to_workload": {"points_per_s": w["N"] / t_full, "seconds": t_full,
+                                         "how": "t = c*N^2 from the measured sample; not a measurement"},
             "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -140,6 +158,33 @@ def config_dict(w, gpus):
             "N": w["N"], "d": w["d"], "k": w["n_neighbors"], "n_anchors": w["n_anchors"],
             "p_work": w["p_work"], "parallelism": "1 process per GPU, tiles sharded across %d rank(s)" % gpus,
             "l2": "256 MiB scratch buffer written between timed steps (L2 flush)"}
+
+
+def same_n_leg(ab, Annchor, ctx, w, n_s=N_SAMPLE):
+    """The GPU arm on exactly what the CPU arm (--impl reference / cpu_baseline) measures: N = n_s of
+    the same generator, same arguments, hence the same effective p_work -- a like-for-like pair of
+    MEASURED numbers."""
+    Xs = make_blobs(n_s, w["d"], w["centers"], w["seed"])
+    ds = ab.Dataset(ctx, Xs, "euclidean")
+    kw = dict(n_anchors=w["n_anchors"], n_neighbors=w["n_neighbors"], n_samples=w["n_samples"],
+              p_work=w["p_work"], niters=w["niters"])
+    ms, ann = [], None
+    for it in range(4):
+        if ann is not None:
+            ann._index.close()
+        ann = Annchor(Xs, "euclidean", ctx=ctx, _dataset=ds, **kw)
+        ctx.timer_start()
+        ann.fit()
+        t = ctx.timer_stop()
+        if it >= 1:
+            ms.append(t)
+    out = {"N": n_s, "p_work_effective": ann.p_work, "ms_per_fit": float(np.mean(ms)),
+           "points_per_s": n_s / (float(np.mean(ms)) * 1e-3), "evals": int(ann.evals),
+           "note": "device-timed fit() with X resident, mean of 3 after 1 warm-up; compare with "
+                   "cpu_baseline.value / the --impl reference line (same N, same effective p_work)"}
+    ann._index.close()
+    ds.close()
+    return out
 
 
 def recall_at_k(ds, X, graph, k, rows):
@@ -252,7 +297,7 @@ def run_ours(args, w):
     sw_pairs = float(np.sum([s[1] for s in sweeps])) / n_sw
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["traffic_bytes_per_launch_mean"]
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))["traffic_bytes_per_launch_mean"]
         if w["N"] != WORKLOAD["N"] or world != 1:
             traffic = None  # the capture is of the default single-GPU workload
     except Exception:
@@ -262,11 +307,16 @@ def run_ours(args, w):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = ALG_BYTES_PER_PAIR * sw_pairs / (sw_ms * 1e-3) / 1e9
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_equiv = ALG_BYTES_PER_PAIR * sw_pairs / (sw_ms * 1e-3) / 1e9
     sm_clk = (clk.get("sm_mhz") or 1965) * 1e6
-    alu_peak = 148 * 128 * sm_clk  # lane-instructions per second
-    alu_ops = 3.0 * w["n_anchors"] * sw_pairs / (sw_ms * 1e-3)  # 2 FADD + 1 FMNMX3 (2 anchors) per pair-anchor
+    # ncu: DRAM < 3 % of peak, issue-active 55-60 %: the sweep is bound by the FP32/ALU issue rate.
+    # Algorithmic lane-operations per pair: per anchor 2 FADD + one 3-input
+    # min/max shared by two anchors for each of lb / ub = 3; plus ~25 for dad, bin, 3 FMA, clip, margin test.
+    ops_per_pair = 3.0 * w["n_anchors"] + 25.0
+    issue_peak = 148 * 128 * sm_clk / 1e12          # T lane-op/s (4 warp instructions / clk / SM)
+    issue_achieved = ops_per_pair * sw_pairs / (sw_ms * 1e-3) / 1e12
+    same_n = same_n_leg(ab, Annchor, ctx, w)
     rng = np.random.default_rng(1)
     rows = rng.integers(0, w["N"], size=200)
     rec = recall_at_k(ds, X, last_graph, w["n_neighbors"], rows)
@@ -279,19 +329,24 @@ def run_ours(args, w):
                 "d2h_bytes_per_step": int(w["N"] * w["n_neighbors"] * 16), "seconds": e2e_s},
         "gpu_launches": int(launches),
         "clocks": clk,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic,
+        "roofline": {"bound": "issue", "achieved": issue_achieved, "peak": issue_peak, "unit": "Tlane-op/s",
+                     "frac": issue_achieved / issue_peak, "traffic": traffic,
                      "kernel": "score_sweep_kernel", "pairs_per_launch": sw_pairs, "ms_per_launch": sw_ms,
-                     "algorithmic_bytes_per_pair": ALG_BYTES_PER_PAIR,
-                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+                     "algorithmic_ops_per_pair": ops_per_pair,
+                     "peak_source": "148 SMs x 128 FP32 lanes x SM clock under load (%.0f MHz): one lane-op per "
+                                    "lane and clock; FADD / FMNMX have no 2x FMA credit" % (sm_clk / 1e6),
                      "launches_averaged": n_sw,
-                     "traffic_source": "ncu --set full capture committed as profiles/r01_ncu_full_summary.txt "
-                                       "(dram read+write, mean of the 2 full sweeps of a fit)" if traffic else None,
-                     "note": "the streaming sweep stores nothing per pair: 25 B/pair is SURVEY 8(d)'s "
-                             "materialised-equivalent figure (what a reference-shaped K2+K3 pass would move), "
-                             "so `achieved` is an HBM-equivalent rate, not DRAM traffic (see `traffic`).  The "
-                             "kernel is FP32/ALU issue-bound: bound-assembly lane-ops/s over 148 SM x 128 lanes "
-                             "x sm clock = %.3f" % (alu_ops / alu_peak)},
+                     "traffic_source": "dram__bytes_read+write per launch, ncu --set full capture "
+                                       "(profiles/r02_ncu_full_summary.txt), mean of the 2 full sweeps of a fit"
+                                       if traffic else None,
+                     "hbm_equivalent": {"achieved": hbm_equiv, "peak": hbm_peak, "unit": "GB/s",
+                                        "frac": hbm_equiv / hbm_peak,
+                                        "algorithmic_bytes_per_pair": ALG_BYTES_PER_PAIR,
+                                        "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                                        "note": "SURVEY 8(d)'s materialised-equivalent figure: what a reference-"
+                                                "shaped K2+K3 pass would have to move; the streaming sweep stores "
+                                                "nothing per pair (see traffic), so this is NOT its bound"}},
+        "same_n_leg": same_n,
         "recall_at_k": rec, "evals": int(last_evals), "stage_seconds": last_stage,
         "index_stats": last_stats,
     }
