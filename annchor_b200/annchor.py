@@ -175,6 +175,15 @@ class Index:
         return dict(zip(["pairs_swept", "n_known", "n_tight", "sweeps", "n_candidates", "hash_capacity",
                          "n_anchor_pairs", "n_not_computed"], out.tolist()))
 
+    def query(self, both, nq, nn, p_work):
+        """annb_index_query: `both` = Dataset of X followed by the nq queries -> (ngi, ngd, n_evals)."""
+        ngi = np.empty((nq, nn), dtype=np.int64)
+        ngd = np.empty((nq, nn), dtype=np.float64)
+        ne = C.c_int64()
+        check(self._L.annb_index_query(self.handle, both.handle, int(nq), int(nn), float(p_work), ptr(ngi), ptr(ngd),
+                                       C.byref(ne)))
+        return ngi, ngd, ne.value
+
     def last_sweep(self):
         ms, pairs = C.c_float(), C.c_int64()
         check(self._L.annb_index_last_sweep(self.handle, C.byref(ms), C.byref(pairs)))
@@ -408,6 +417,35 @@ class Annchor:
 
     def get_ann(self):
         self.neighbor_graph = self._index.neighbor_graph()
+
+    def query(self, Q, nn=15, p_work=0.3, get_exact_query_ijs=None):
+        """Query new data against the fitted index (annchor/annchor.py:643-683): returns
+        (ngi int64 (len(Q), nn), ngd float64 (len(Q), nn)), the nn approximate nearest points of X per
+        query.  ``p_work`` is the fraction of the len(Q) * len(X) brute-force evaluations to spend."""
+        if get_exact_query_ijs is not None:
+            raise NotImplementedError("annchor_b200 evaluates the metric with its CUDA kernels; a host "
+                                      "get_exact_query_ijs would be a CPU fallback")
+        if not hasattr(self, "neighbor_graph"):
+            raise RuntimeError("query() needs a fitted index: call fit() first")
+        nq = len(Q)
+        na = self.n_anchors * nq
+        nbf = nq * self.nx
+        limit = ((nq * nn * 3) // 2 - 1 + na) / nbf
+        if p_work < limit:
+            print("Warning: p_work too low")
+            print("Increasing p_work to %5.3f" % limit)
+            p_work = limit
+        if isinstance(self.X, np.ndarray) and self.X.dtype.kind not in "US":
+            both = np.concatenate([np.asarray(self.X), np.asarray(Q, dtype=self.X.dtype)])
+        else:
+            both = list(self.X) + list(Q)
+        ds = Dataset(self.ctx, both, self.f, cost_matrix=self._cost)
+        try:
+            ngi, ngd, evals = self._index.query(ds, nq, nn, p_work)
+        finally:
+            ds.close()
+        self.query_evals = evals
+        return ngi, ngd
 
     def fit(self):
         """Computes the approx nearest neighbour graph (annchor/annchor.py:532-623)."""

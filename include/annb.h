@@ -92,6 +92,12 @@ int annb_pair_dists(annb_ctx *ctx, const annb_dataset *ds, int metric, const int
 int annb_pair_dists_dev(annb_ctx *ctx, const annb_dataset *ds, int metric, const int32_t *i,
                         const int32_t *j, int64_t n, float *out);
 
+/* query twin get_exact_query_ijs(f, X, Z, IJ) (annchor/utils.py:180-245, annchor/annchor.py:657-661):
+ * out[p] = metric(X[ij[p][0]], Z[ij[p][1]]).  `both` is ONE data set holding the nx items of X followed
+ * by the items of Z (so that both sides share the device layout of the metric kernels). */
+int annb_pair_dists_query(annb_ctx *ctx, const annb_dataset *both, int metric, int64_t nx, const int64_t *ij,
+                          int64_t n, double *out);
+
 /* ---- K1: anchor pickers (annchor/pickers.py) ------------------------------- */
 /* MaxMinAnchorPicker.get_anchors (annchor/pickers.py:18-52): `first` is the caller's
  * np.random.randint(nx) draw; A int64[na]; D float64 (n, na) row-major (the layout of the
@@ -213,6 +219,12 @@ int annb_index_update_bounds(annb_index *ix, int64_t *n_updated);
 /* get_ann / get_nn (annchor/annchor.py:514-530): idx int64 (n, nn), dist float64 (n, nn),
  * column 0 = self / 0 */
 int annb_index_neighbor_graph(annb_index *ix, int64_t *idx, double *dist);
+/* Annchor.query (annchor/annchor.py:643-683, annchor/query_functions.py:183-212) against a fitted
+ * index: `both` holds X followed by the nq query items; ngi int64 (nq, nn) / ngd float64 (nq, nn) are the
+ * nn approximate nearest points of X per query; *n_evals = metric evaluations spent
+ * (n_anchors * nq + n_refine).  p_work is the fraction of the nq * nx brute-force evaluations. */
+int annb_index_query(annb_index *ix, const annb_dataset *both, int64_t nq, int64_t nn, double p_work,
+                     int64_t *ngi, double *ngd, int64_t *n_evals);
 /* counters: [0] pairs swept, [1] known pairs, [2] tightened pairs, [3] sweep launches,
  * [4] candidate pairs, [5] hash capacity, [6] anchor pairs, [7] not-computed candidates */
 int annb_index_stats(annb_index *ix, int64_t *out, int64_t n);

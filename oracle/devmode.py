@@ -271,6 +271,84 @@ class OracleAnnchorF32(OracleAnnchor):
                 dist[i, 1 + m:1 + m + o2.shape[0]] = v[o2]
         self.neighbor_graph = (idx, dist)
 
+    # -- query (annchor/annchor.py:643-683, annchor/query_functions.py:10-212) in the same arithmetic ----
+    def query(self, q_pair_fn, nq, nn=15, p_work=0.3):
+        """q_pair_fn(IJ) -> metric(X[i], Q[j]) for (i, j) rows of IJ.  Returns (ngi, ngd) of shape (nq, nn)."""
+        nx, na = self.nx, self.n_anchors
+        limit = ((nq * nn * 3) // 2 - 1 + na * nq) / (nq * nx)
+        p_work = max(p_work, limit)
+        # query -> anchor distances (query_functions.py:10-15)
+        IJa = np.array([[self.A[a], j] for j in range(nq) for a in range(na)], dtype=np.int64)
+        QD = q_pair_fn(IJa).reshape(nq, na)
+        evals = nq * na
+        # candidates: queries and points sharing >= loc_thresh of their `locality` nearest anchors (:18-38)
+        sidq = np.argsort(QD, axis=1, kind="stable")[:, :self.locality]
+        Mq = np.zeros((nq, na), dtype=np.int32)
+        np.put_along_axis(Mq, sidq, 1, axis=1)
+        Mx = np.zeros((nx, na), dtype=np.int32)
+        np.put_along_axis(Mx, self.sid, 1, axis=1)
+        cand = (Mq @ Mx.T) >= self.loc_thresh                      # (nq, nx)
+        jj, ii = np.nonzero(cand)
+        P = ii.shape[0]
+        # features in float32 on the data set "X followed by Q" (query_functions.py:70-130)
+        Dc = np.ascontiguousarray(np.vstack([self.D, QD]).astype(np.float32))
+        cAc = np.ascontiguousarray(np.concatenate([np.argmin(self.D, axis=1), np.argmin(QD, axis=1)]).astype(np.int32))
+        ij = np.ascontiguousarray(np.stack([ii, nx + jj], axis=1).astype(np.int64))
+        lb, ub, s2 = np.empty(P, np.float32), np.empty(P, np.float32), np.empty(P, np.float32)
+        lib().orc_f32_features(ptr(ij), P, ptr(Dc), na, ptr(cAc), ptr(lb), ptr(ub), ptr(s2))
+        e2, cf = self._device_model()
+        RA = np.empty(P, np.float32)
+        lab = np.empty(P, np.int8)
+        lib().orc_f32_predict(ptr(lb), ptr(ub), ptr(s2), P, ptr(e2), ptr(cf), ptr(RA), None, ptr(lab))
+        computed = self.slot[ii] >= 0                              # np.isin(IJs[:, 0], ann.A)
+        # rows of the rectangle (jj is sorted: np.nonzero is row-major)
+        rptr = np.zeros(nq + 1, dtype=np.int64)
+        np.cumsum(np.bincount(jj, minlength=nq), out=rptr[1:])
+        thresh = np.array([np.sort(RA[rptr[j]:rptr[j + 1]])[nn] for j in range(nq)], dtype=np.float32)
+        nmin = 3 * nn // 2
+        for j in range(nq):                                        # guarantee_nmin, row by row (rows are disjoint)
+            sl = slice(rptr[j], rptr[j + 1])
+            m = ~computed[sl]
+            todo = nmin - int((~m).sum())
+            if todo > 0:
+                vals = RA[sl][m]
+                kth = np.partition(vals, todo)[todo]
+                idx = np.nonzero(m)[0][vals < kth] + rptr[j]
+                RA[idx] = -1.0
+        ncm = ~computed
+        p32 = (thresh[jj] - RA)[ncm]
+        labn = lab[ncm].astype(np.int64)
+        prob = np.zeros(p32.shape[0])
+        for b, e in enumerate(self.errs32):
+            m = labn == b
+            prob[m] = np.searchsorted(e, p32[m], side="left") / float(len(e))
+        n_refine = int(p_work * nq * nx - na * nq) + 1
+        n_refine = max(0, min(n_refine, prob.shape[0]))
+        self.n_selects += 1
+        salt = select_salt(self.n_selects, self.tie_salt0)
+        back = np.nonzero(ncm)[0]
+        tk = tie_key(ii[back], nx + jj[back], salt)
+        sel = back[np.lexsort((tk, -prob))[:n_refine]]
+        exact = q_pair_fn(np.stack([ii[sel], jj[sel]], axis=1)).astype(np.float32)
+        evals += sel.shape[0]
+        RA[sel] = exact
+        computed[sel] = True
+        ngi = np.full((nq, nn), -1, dtype=np.int64)
+        ngd = np.full((nq, nn), np.inf)
+        for j in range(nq):
+            sl = slice(rptr[j], rptr[j + 1])
+            pts, v, c = ii[sl], RA[sl].astype(np.float64), computed[sl]
+            o = np.lexsort((pts[c], v[c]))[:nn]
+            m = o.shape[0]
+            ngi[j, :m] = pts[c][o]
+            ngd[j, :m] = v[c][o]
+            if m < nn:
+                o2 = np.lexsort((pts[~c], v[~c]))[:nn - m]
+                ngi[j, m:m + o2.shape[0]] = pts[~c][o2]
+                ngd[j, m:m + o2.shape[0]] = v[~c][o2]
+        self.query_evals = evals
+        return ngi, ngd
+
     def fit(self):
         self.get_anchors()
         self._t("A", self.A)

@@ -1,0 +1,89 @@
+"""Annchor.query() on the device (annchor/annchor.py:643-683, annchor/query_functions.py:10-212;
+csrc/query.cu): equality with the device-arithmetic oracle's restatement of query_(), and the
+gates of the reference's own query test (annchor/tests/test_examples.py:12-58: recall >= 0.99 of
+the exact neighbours, 1-NN label vote >= 0.95) on data both sides can evaluate."""
+import numpy as np
+import pytest
+
+from conftest import golden_strings, bench_blobs
+
+pytestmark = pytest.mark.gpu
+
+
+def _fit_and_query(gpu_ctx, X, Q, metric, kw, nn, p_work):
+    import annchor_b200 as ab
+    from annchor_b200.annchor import Annchor
+    from oracle.devmode import OracleAnnchorF32
+    dev = Annchor(X, metric, ctx=gpu_ctx, **kw).fit()
+    ngi, ngd = dev.query(Q, nn=nn, p_work=p_work)
+    nx = len(X)
+    both = np.concatenate([X, Q]) if isinstance(X, np.ndarray) and X.dtype.kind not in "US" else list(X) + list(Q)
+    dsb = ab.Dataset(gpu_ctx, both, metric)
+    orc = OracleAnnchorF32(X, lambda IJ: dev._dataset.pair_dists(IJ), A=dev.A, D=dev.D, **kw).fit()
+    assert np.array_equal(orc.neighbor_graph[0], dev.neighbor_graph[0])  # same fitted state
+    qfn = lambda IJ: dsb.pair_dists(np.stack([IJ[:, 0], IJ[:, 1] + nx], axis=1))  # noqa: E731
+    ogi, ogd = orc.query(qfn, len(Q), nn=nn, p_work=p_work)
+    return dev, orc, (ngi, ngd), (ogi, ogd), qfn
+
+
+def _exact_query_graph(qfn, nx, nq, nn):
+    IJ = np.stack(np.meshgrid(np.arange(nx), np.arange(nq), indexing="ij"), axis=-1).reshape(-1, 2)
+    D = qfn(IJ).reshape(nx, nq).T
+    o = np.argsort(D, axis=1, kind="stable")[:, :nn]
+    return o, np.take_along_axis(D, o, axis=1)
+
+
+@pytest.mark.parametrize("case", ["euclid_f32", "strings"])
+def test_query_equals_oracle_and_reference_gates(gpu_ctx, case):
+    rng = np.random.default_rng(0)
+    if case == "euclid_f32":
+        Z = bench_blobs(2600, 32, 60, 21, np.float32)
+        y = None
+        kw = dict(n_anchors=20, n_neighbors=15, n_samples=2000, p_work=0.1)
+    else:
+        Z, g = golden_strings()
+        y = g["y"]
+        kw = dict(n_anchors=20, n_neighbors=15, n_samples=3000, p_work=0.12)
+    perm = rng.permutation(len(Z))
+    tr, te = np.sort(perm[:len(Z) * 3 // 4]), np.sort(perm[len(Z) * 3 // 4:])
+    X, Q = Z[tr], Z[te]
+    nn = 10
+    dev, orc, (ngi, ngd), (ogi, ogd), qfn = _fit_and_query(gpu_ctx, X, Q, "euclidean" if y is None else "levenshtein",
+                                                            kw, nn, 0.3)
+    assert ngi.shape == (len(Q), nn) and np.all(ngi >= 0)
+    assert np.array_equal(ngi, ogi)
+    assert np.array_equal(ngd, ogd)
+    assert dev.query_evals == orc.query_evals
+    # reference gates (tests/test_examples.py:44-58)
+    ei, ed = _exact_query_graph(qfn, len(X), len(Q), nn)
+    recall = np.mean([len(set(ngi[j]) & set(ei[j])) / nn for j in range(len(Q))])
+    assert recall >= 0.99, recall
+    assert np.all(np.diff(ngd, axis=1) >= 0)
+    if y is not None:
+        vote = np.mean(y[tr][ngi[:, 0]] == y[te])
+        assert vote >= 0.95, vote
+
+
+def test_query_low_p_work_and_pair_dists_query(gpu_ctx):
+    """p_work below the reference's floor is raised to it (annchor.py:668-673); the query twin of
+    get_exact_ijs evaluates metric(X[i], Z[j])."""
+    import annchor_b200 as ab
+    from annchor_b200.annchor import Annchor
+    from annchor_b200 import _lib
+    X = bench_blobs(1500, 16, 40, 2, np.float32)
+    Q = bench_blobs(1540, 16, 40, 2, np.float32)[1500:]
+    dev = Annchor(X, "euclidean", ctx=gpu_ctx, n_anchors=10, n_neighbors=10, n_samples=1000, p_work=0.1).fit()
+    ngi, ngd = dev.query(Q, nn=5, p_work=0.0)
+    assert ngi.shape == (40, 5) and np.all(ngi >= 0) and np.all(np.isfinite(ngd))
+    true = np.linalg.norm(Q[:, None, :].astype(np.float64) - X[ngi].astype(np.float64), axis=2)
+    # computed entries are exact; with so little work some rows fall back to predictions -- those are
+    # still within the triangle-inequality bounds of the true distance
+    exact_frac = np.mean(np.isclose(ngd, true, rtol=1e-5))
+    assert exact_frac > 0.9
+    both = ab.Dataset(gpu_ctx, np.concatenate([X, Q]), "euclidean")
+    IJ = np.stack([np.arange(40) * 7 % 1500, np.arange(40)], axis=1).astype(np.int64)
+    out = np.empty(40)
+    L = _lib.load()
+    _lib.check(L.annb_pair_dists_query(gpu_ctx.handle, both.handle, both.metric, 1500, _lib.ptr(IJ), 40, _lib.ptr(out)))
+    want = np.linalg.norm(X[IJ[:, 0]].astype(np.float64) - Q[IJ[:, 1]].astype(np.float64), axis=1)
+    np.testing.assert_allclose(out, want, rtol=1e-6)
