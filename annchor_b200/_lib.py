@@ -62,6 +62,7 @@ _SIGS = {
     "annb_index_get_D": [_P, _P],
     "annb_index_locality": [_P, C.POINTER(_I64), C.POINTER(_I64)],
     "annb_index_sample_pool": [_P, _U64, _I64, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(C.c_int)],
+    "annb_index_sample_pool_bins": [_P, _U64, _P, _P, _I64, _I64, C.POINTER(_I64)],
     "annb_index_get_pool": [_P, _P, _P],
     "annb_index_pair_features": [_P, _P, _I64, _P],
     "annb_index_pair_state": [_P, _P, _I64, _P, _P, _P],

@@ -83,6 +83,15 @@ class Index:
         self._n_pool = n.value
         return n.value, nc.value, bool(ex.value)
 
+    def sample_pool_bins(self, seed, bins, rate, max_pool):
+        """Stratified refill (annb_index_sample_pool_bins) -> n_pool; read it with get_pool()."""
+        bins, rate = as_c(bins, np.float64), as_c(rate, np.float64)
+        n = C.c_int64()
+        check(self._L.annb_index_sample_pool_bins(self.handle, int(seed) & 0xFFFFFFFFFFFFFFFF, ptr(bins), ptr(rate),
+                                                  rate.shape[0], int(max_pool), C.byref(n)))
+        self._n_pool = n.value
+        return n.value
+
     def get_pool(self):
         ij = np.empty((self._n_pool, 2), dtype=np.int64)
         dad = np.empty(self._n_pool, dtype=np.float64)

@@ -2711,6 +2711,7 @@ ANNB_API int annb_index_sample_pool(annb_index *ix, uint64_t seed, int64_t max_p
     if (n_nc <= 0) return ANNB_OK;
     SampleArgs A;
     A.V = ix->view();
+    A.nb = 0;
     A.seed = (uint32_t)(mix64(seed) >> 32);
     double frac = all ? 1.0 : 0.8 * (double)max_pool / (double)n_nc;
     for (int attempt = 0;; ++attempt) {
@@ -2747,6 +2748,48 @@ ANNB_API int annb_index_sample_pool(annb_index *ix, uint64_t seed, int64_t max_p
         ANNB_REQUIRE(ix->n_pool == n_nc, ANNB_ESTATE,
                      "pool sweep found %lld not-computed candidates, bookkeeping says %lld",
                      (long long)ix->n_pool, (long long)n_nc);
+    *n_pool = ix->n_pool;
+    return ANNB_OK;
+}
+
+// Stratified refill of the pool: a bin of the sampler's partition that the uniform pool left (nearly)
+// empty is re-sampled at its own rate over ALL tiles, so that rare dad ranges are represented the way
+// the reference's per-bin draw over the materialised pair list represents them.
+ANNB_API int annb_index_sample_pool_bins(annb_index *ix, uint64_t seed, const double *bins, const double *rate,
+                                         int64_t nb, int64_t max_pool, int64_t *n_pool)
+{
+    TraceScope _ts("annb_index_sample_pool_bins");
+    ANNB_REQUIRE(ix && bins && rate && n_pool, ANNB_EINVAL, "NULL argument");
+    ANNB_REQUIRE(ix->have_locality, ANNB_ESTATE, "locality must run before sampling");
+    ANNB_REQUIRE(nb >= 1 && nb <= MAX_BINS && max_pool >= 1024, ANNB_ERANGE, "bad bin count / pool size");
+    annb_ctx *c = ix->ctx;
+    ANNB_CUDA(cudaSetDevice(c->device));
+    SampleArgs A;
+    A.V = ix->view();
+    A.seed = (uint32_t)(mix64(seed ^ 0x5851f42d4c957f2dull) >> 32);
+    A.thr = 0;
+    A.tile_thr = 0xffffffffu;
+    A.nb = (int)nb;
+    for (int b = 0; b <= nb; ++b) A.edge[b] = (float)bins[b];
+    for (int b = 0; b < MAX_BINS; ++b) {
+        const double r = b < nb ? rate[b] : 0.0;
+        A.bthr[b] = r <= 0.0 ? 0u : (r >= 1.0 ? 0xffffffffu : (uint32_t)std::max(1.0, r * 4294967295.0));
+    }
+    ANNB_TRY(ix->pool_key.ensure((size_t)max_pool * 8));
+    ANNB_TRY(ix->pool_dad.ensure((size_t)max_pool * 4));
+    A.out_key = ix->pool_key.as<uint64_t>();
+    A.out_dad = ix->pool_dad.as<float>();
+    A.out_cap = (unsigned long long)max_pool;
+    ANNB_CUDA(cudaMemsetAsync(ix->counters.p, 0, 64, c->stream));
+    A.counter = ix->counters.as<unsigned long long>();
+    A.rank = 0;
+    A.world = 1;
+    ANNB_TRY(launch_sample_sweep(c, A));
+    ix->sweeps += 1;
+    unsigned long long got = 0;
+    ANNB_CUDA(cudaMemcpyAsync(&got, ix->counters.p, 8, cudaMemcpyDeviceToHost, c->stream));
+    ANNB_CUDA(cudaStreamSynchronize(c->stream));
+    ix->n_pool = (int64_t)std::min<unsigned long long>(got, (unsigned long long)max_pool);
     *n_pool = ix->n_pool;
     return ANNB_OK;
 }

@@ -69,6 +69,11 @@ struct SampleArgs {
     uint32_t thr;       // a pair of a visited tile takes part iff hash_pair32(i, j, seed) <= thr
     uint32_t tile_thr;  // a tile is visited iff hash of its index <= tile_thr (0xffffffff: every tile)
     uint32_t seed;
+    // stratified mode (nb > 0): the pair's threshold depends on its dad bin [edge[b], edge[b+1]) --
+    // bthr[b] = 0 skips the bin; thr / tile_thr are ignored, every tile is visited
+    int nb;
+    float edge[MAX_BINS + 1];
+    uint32_t bthr[MAX_BINS];
     uint64_t *out_key;
     float *out_dad;
     unsigned long long out_cap;

@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(256, 2) sample_sweep_kernel(const SampleArgs A
         // two-stage uniform sub-sample: tiles first (point ids carry no geometry, so a tile is a random
         // block of pairs), then pairs inside the visited tiles
         const uint64_t tix = (uint64_t)(m * A.world + A.rank);
-        if (A.tile_thr != 0xffffffffu &&
+        if (A.nb == 0 && A.tile_thr != 0xffffffffu &&
             hash_pair32((uint32_t)tix, (uint32_t)(tix >> 32), A.seed ^ 0x5bd1e995u) > A.tile_thr)
             continue;
         int ti, tj;
@@ -383,7 +383,16 @@ __global__ void __launch_bounds__(256, 2) sample_sweep_kernel(const SampleArgs A
             for (int c = 0; c < 8; ++c) {
                 const int lj = micro_off(tx, c);
                 const uint32_t gj = (uint32_t)(tj * TILE + lj);
-                const bool keep = hash_pair32(gi, gj, A.seed) <= A.thr && (!diag || li < lj) && gj < (uint32_t)V.n;
+                uint32_t thr = A.thr;
+                if (A.nb > 0) {
+                    // sampler bins [lo, hi) (utils.py:547-549) on the pair's double anchor distance
+                    const float dad = 0.5f * (sDi[sMj[lj].cA * SROW + li] + sDj[sMi[li].cA * SROW + lj]);
+                    int b = 0;
+                    for (int k = 1; k < A.nb; ++k) b += dad >= A.edge[k];
+                    thr = A.bthr[b];
+                }
+                const bool keep = thr != 0u && hash_pair32(gi, gj, A.seed) <= thr && (!diag || li < lj) &&
+                                  gj < (uint32_t)V.n;
                 const unsigned mm = __ballot_sync(0xffffffffu, keep);
                 if (keep) queue[qn + __popc(mm & ((1u << lane) - 1))] = (uint32_t)li | ((uint32_t)lj << 8);
                 qn += __popc(mm);

@@ -193,6 +193,29 @@ class SimpleStratifiedSampler:
                 z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
                 z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
                 prio = z ^ (z >> np.uint64(31))
+        if not exact:
+            # bins the uniform pool left short are re-sampled at their own rate over all tiles (the
+            # reference draws per bin from the materialised pair list, so a rare dad range is as well
+            # represented as a common one)
+            want_b = n_samples // self.n_partitions + 1
+            cnt = np.array([np.count_nonzero((sf >= bins[b]) & (sf < bins[b + 1])) for b in range(self.n_partitions)])
+            short = cnt < want_b
+            if short.any():
+                frac = max(n_pool / float(n_nc), 1e-12)
+                rate = np.where(short, np.minimum(1.0, 8.0 * want_b * frac / np.maximum(cnt, 0.25)), 0.0)
+                n2 = ix.sample_pool_bins(seed, bins, rate, self.pool_size)
+                if n2 > 0:
+                    ijs2, dad2 = ix.get_pool()
+                    keep = ~np.isin(np.digitize(sf, bins[1:-1]), np.nonzero(short)[0])
+                    ijs = np.concatenate([ijs[keep], ijs2])
+                    sf = np.concatenate([sf[keep], dad2])
+                    key = (ijs[:, 0].astype(np.uint64) << np.uint64(32)) | ijs[:, 1].astype(np.uint64)
+                    with np.errstate(over="ignore"):
+                        z = key + np.uint64((seed * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF)
+                        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+                        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+                        prio = z ^ (z >> np.uint64(31))
+                    indices = np.arange(sf.shape[0])
         self.loop_num += 1
         parts = []
         for b in range(self.n_partitions):

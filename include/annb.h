@@ -176,6 +176,11 @@ int annb_index_locality(annb_index *ix, int64_t *n_candidates, int64_t *n_relaxe
  * and reproduce the reference's sampler bit for bit); otherwise a hash-selected uniform sub-sample. */
 int annb_index_sample_pool(annb_index *ix, uint64_t seed, int64_t max_pool, int64_t *n_pool,
                            int64_t *n_not_computed, int *exact);
+/* stratified refill: replaces the pool by the not-computed candidates whose double anchor distance
+ * falls into bin b = [bins[b], bins[b+1]) (annchor/utils.py:547-549), each kept with probability
+ * rate[b] (0 skips the bin) -- used when the uniform pool holds too few pairs of a bin */
+int annb_index_sample_pool_bins(annb_index *ix, uint64_t seed, const double *bins, const double *rate,
+                                int64_t nb, int64_t max_pool, int64_t *n_pool);
 /* copy the pool out: ij (n_pool, 2) int64, dad float64[n_pool] */
 int annb_index_get_pool(annb_index *ix, int64_t *ij, double *dad);
 /* features [lb, ub, dad] of explicit pairs in the sweeps' float32 arithmetic: feat (n, 3) */
