@@ -41,6 +41,7 @@ _SIGS = {
     "annb_dataset_dense": [_P, _P, _I64, _I64, _I32, _I32, _PP],
     "annb_dataset_strings": [_P, _P, _P, _I64, _PP],
     "annb_dataset_hist": [_P, _P, _I64, _I64, _I32, _PP],
+    "annb_dataset_gather": [_P, _P, _P, _I64, _PP],
     "annb_dataset_free": [_P],
     "annb_pair_dists": [_P, _P, _I32, _P, _I64, _P],
     "annb_pair_dists_dev": [_P, _P, _I32, _P, _P, _I64, _P],
@@ -59,6 +60,8 @@ _SIGS = {
     "annb_index_reserve_pairs": [_P, _I64],
     "annb_index_maxmin": [_P, _I64, _P],
     "annb_index_set_anchors": [_P, _P, _I64, _P],
+    "annb_index_spatial_order": [_P, _P],
+    "annb_index_adopt_anchors": [_P, _P, _P],
     "annb_index_get_D": [_P, _P],
     "annb_index_locality": [_P, C.POINTER(_I64), C.POINTER(_I64)],
     "annb_index_sample_pool": [_P, _U64, _I64, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(C.c_int)],

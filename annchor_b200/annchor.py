@@ -7,6 +7,7 @@ design, is that nothing Theta(N^2) is materialised: ``IJs``, ``features``, ``Ref
 ``not_computed_mask`` do not exist; the plug-ins see the protocols in ``annchor_b200.plugins``.
 """
 import ctypes as C
+import os
 import time
 from collections import Counter
 
@@ -19,6 +20,9 @@ from . import plugins
 from .plugins import (FEATURE_NAMES, NothingToSample, MaxMinAnchorPicker, SimpleStratifiedSampler,
                       SimpleStratifiedLinearRegression, SimpleStratifiedErrorRegression,
                       regression_device_spec, error_device_spec)
+
+
+REORDER_MIN_POINTS = 16384  # spatial renumbering from this size on (the two-stage thresholds start at 128 tiles)
 
 
 class Index:
@@ -64,6 +68,16 @@ class Index:
         if D.shape != (self.n, self.na):
             raise ValueError("D must have shape (nx, n_anchors) = %r, got %r" % ((self.n, self.na), D.shape))
         check(self._L.annb_index_set_anchors(self.handle, ptr(A), A.shape[0], ptr(D)))
+
+    def spatial_order(self):
+        """order[new] = old: points by (closest anchor, distance to it, id) (annb_index_spatial_order)."""
+        order = np.empty(self.n, dtype=np.int64)
+        check(self._L.annb_index_spatial_order(self.handle, ptr(order)))
+        return order
+
+    def adopt_anchors(self, src, order):
+        order = as_c(order, np.int64)
+        check(self._L.annb_index_adopt_anchors(self.handle, src.handle, ptr(order)))
 
     def get_D(self):
         D = np.empty((self.n, self.na), dtype=np.float64)
@@ -332,14 +346,24 @@ class Annchor:
         # update_anchor_points may tighten (annchor.py:440,444-457)
         budget = int(self.p_work * self.N)
         n_ref = max(budget // max(niters, 1), 0)
-        self._index.reserve_pairs(min(budget + n_ref * (lookahead - 1) * max(niters - 1, 0) + n_samples * niters,
-                                      self.N) + 1024)
+        if not (self.nx >= REORDER_MIN_POINTS and is_metric and os.environ.get("ANNB_NO_REORDER") is None):
+            # (with spatial renumbering the store is sized on the index that replaces this one)
+            self._index.reserve_pairs(min(budget + n_ref * (lookahead - 1) * max(niters - 1, 0) + n_samples * niters,
+                                          self.N) + 1024)
         self._xchg = None
         if comm is not None and world > 1:
             from .dist import IndexExchange
             self._index.set_reducer(comm.reducer)
             self._xchg = IndexExchange(self._index, comm)
         self._D = None
+        # Spatial renumbering (large problems): after the anchors are known the points are sorted by
+        # (closest anchor, distance to it), the data set is gathered in that order on the device and the
+        # fit runs on the relabelled points; results are mapped back.  Tiles of the sweeps are then
+        # geometrically coherent and most tile pairs are pruned from per-tile bounds.
+        self._reorder = (self.nx >= REORDER_MIN_POINTS and is_metric and os.environ.get("ANNB_NO_REORDER") is None)
+        self._order = None
+        self._index_args = (n_anchors, n_neighbors, locality, loc_thresh, self.loc_min, is_metric, rank, world)
+        self._reserve = min(budget + n_ref * (lookahead - 1) * max(niters - 1, 0) + n_samples * niters, self.N) + 1024
         self.stage_times = {}
         # _trace: a dict that receives per-stage results (sample, thresholds, selected / look-ahead
         # sets, ...) -- used by the stage-parity tests; costs device-to-host copies, off by default
@@ -354,11 +378,35 @@ class Annchor:
             self._index.set_anchors(self.A.astype(np.int64) if self.A.size else np.zeros(0, np.int64),
                                     np.asarray(D, dtype=np.float64))
         self.evals += evals
+        if self._reorder:
+            self._renumber()
+
+    def _renumber(self):
+        """Replace the index by one over the points in spatial order (device-side gather)."""
+        order = self._index.spatial_order()
+        ds2 = self._dataset.gather(order)
+        ix2 = Index(self.ctx, ds2, *self._index_args)
+        ix2.reserve_pairs(self._reserve)
+        ix2.adopt_anchors(self._index, order)
+        if self._xchg is not None:
+            from .dist import IndexExchange
+            ix2.set_reducer(self.comm.reducer)
+            self._xchg = IndexExchange(ix2, self.comm)
+        self._index.close()
+        self._index, self._dataset_ordered, self._order = ix2, ds2, order
+
+    def _to_user_ids(self, ij):
+        return ij if self._order is None else self._order[ij]
 
     @property
     def D(self):
         if self._D is None:
-            self._D = self._index.get_D()
+            D = self._index.get_D()
+            if self._order is not None:
+                Du = np.empty_like(D)
+                Du[self._order] = D
+                D = Du
+            self._D = D
         return self._D
 
     def get_locality(self):
@@ -374,7 +422,7 @@ class Annchor:
         self.sample_y = self._index.eval_pairs(ijs)  # evaluates the metric and marks the pairs computed
         self.evals += self.sample_y.shape[0]
         if self._trace is not None:
-            self._trace["sample_ijs%d" % self._it] = ijs.copy()
+            self._trace["sample_ijs%d" % self._it] = self._to_user_ids(ijs)
             self._trace["sample_bins%d" % self._it] = np.array(bins, copy=True)
             self._trace["sample_features%d" % self._it] = self.sample_features.copy()
 
@@ -405,9 +453,14 @@ class Annchor:
         self._index.select(n_refine, self.lookahead)
         if self._trace is not None:
             sel, nxt = self._index.get_selected()
-            self._trace["thresh%d" % it] = self._index.get_thresh()
-            self._trace["selected%d" % it] = sel
-            self._trace["next%d" % it] = nxt
+            th = self._index.get_thresh()
+            if self._order is not None:
+                tu = np.empty_like(th)
+                tu[self._order] = th
+                th = tu
+            self._trace["thresh%d" % it] = th
+            self._trace["selected%d" % it] = self._to_user_ids(sel)
+            self._trace["next%d" % it] = self._to_user_ids(nxt)
             if it == 0:
                 self._trace["n_forced"] = self.n_forced
         n_eval = self._index.refine_selected()
@@ -425,7 +478,14 @@ class Annchor:
             self._trace["n_tightened%d" % self._it] = self.n_tightened
 
     def get_ann(self):
-        self.neighbor_graph = self._index.neighbor_graph()
+        idx, dist = self._index.neighbor_graph()
+        if self._order is not None:  # back to the caller's numbering: rows and neighbour ids
+            o = self._order
+            iu, du = np.empty_like(idx), np.empty_like(dist)
+            iu[o] = np.where(idx >= 0, o[np.maximum(idx, 0)], -1)
+            du[o] = dist
+            idx, dist = iu, du
+        self.neighbor_graph = (idx, dist)
 
     def query(self, Q, nn=15, p_work=0.3, get_exact_query_ijs=None):
         """Query new data against the fitted index (annchor/annchor.py:643-683): returns
@@ -444,15 +504,19 @@ class Annchor:
             print("Warning: p_work too low")
             print("Increasing p_work to %5.3f" % limit)
             p_work = limit
+        o = self._order
         if isinstance(self.X, np.ndarray) and self.X.dtype.kind not in "US":
-            both = np.concatenate([np.asarray(self.X), np.asarray(Q, dtype=self.X.dtype)])
+            Xo = np.asarray(self.X) if o is None else np.asarray(self.X)[o]
+            both = np.concatenate([Xo, np.asarray(Q, dtype=self.X.dtype)])
         else:
-            both = list(self.X) + list(Q)
+            both = (list(self.X) if o is None else [self.X[i] for i in o]) + list(Q)
         ds = Dataset(self.ctx, both, self.f, cost_matrix=self._cost)
         try:
             ngi, ngd, evals = self._index.query(ds, nq, nn, p_work)
         finally:
             ds.close()
+        if o is not None:
+            ngi = np.where(ngi >= 0, o[np.maximum(ngi, 0)], -1)
         self.query_evals = evals
         return ngi, ngd
 

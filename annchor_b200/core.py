@@ -131,6 +131,16 @@ class Dataset:
                                       ptr(out)))
         return out
 
+    def gather(self, order):
+        """A new Dataset holding the items in the given order (device to device, annb_dataset_gather)."""
+        order = as_c(order, np.int64)
+        g = object.__new__(Dataset)
+        g.ctx, g._L, g.metric, g.n = self.ctx, self._L, self.metric, order.shape[0]
+        h = C.c_void_p()
+        check(self._L.annb_dataset_gather(self.ctx.handle, self.handle, ptr(order), order.shape[0], C.byref(h)))
+        g.handle = h
+        return g
+
     def bruteforce_knn(self, k):
         """Exact k-NN graph (annchor/annchor.py:943-1023): (idx int64 (n, k), dist float64 (n, k)),
         column 0 = the point itself; ties ordered by neighbour id."""

@@ -346,6 +346,89 @@ ANNB_API int annb_dataset_hist(annb_ctx *c, const void *H, int64_t n, int64_t nb
     return ANNB_OK;
 }
 
+namespace annb {
+// out row q = in row order[q]; rows are row_vec 8-byte words long, one warp per row
+__global__ void gather_rows_kernel(const uint2 *__restrict__ src, int64_t row_vec, const int64_t *__restrict__ order,
+                                   int64_t n, uint2 *__restrict__ dst)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t q = warp; q < n; q += nwarps) {
+        const uint2 *s = src + order[q] * row_vec;
+        uint2 *d = dst + q * row_vec;
+        for (int64_t k = lane; k < row_vec; k += 32) d[k] = __ldg(s + k);
+    }
+}
+// strings: 16-byte aligned starts on both sides
+__global__ void gather_strings_kernel(const uint8_t *__restrict__ src, const int64_t *__restrict__ soffs,
+                                      const int32_t *__restrict__ slens, const int64_t *__restrict__ order,
+                                      const int64_t *__restrict__ doffs, int64_t n, uint8_t *__restrict__ dst,
+                                      int32_t *__restrict__ dlens)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t q = warp; q < n; q += nwarps) {
+        const int64_t o = order[q];
+        const int32_t len = slens[o];
+        const uint4 *s = reinterpret_cast<const uint4 *>(src + soffs[o]);
+        uint4 *d = reinterpret_cast<uint4 *>(dst + doffs[q]);
+        for (int k = lane; k < (len + 15) / 16; k += 32) d[k] = __ldg(s + k);
+        if (lane == 0) dlens[q] = len;
+    }
+}
+}  // namespace annb
+
+// A new data set holding the items of `ds` in the order given (out item q = item order[q]); device to
+// device.  Used to renumber the points of a fit in spatial order (annb_index_spatial_order).
+ANNB_API int annb_dataset_gather(annb_ctx *c, const annb_dataset *ds, const int64_t *order, int64_t n,
+                                 annb_dataset **out)
+{
+    ANNB_REQUIRE(c && ds && order && out, ANNB_EINVAL, "NULL argument");
+    ANNB_REQUIRE(n > 0 && n < (1ll << 31), ANNB_EINVAL, "bad n");
+    for (int64_t q = 0; q < n; ++q)
+        ANNB_REQUIRE(order[q] >= 0 && order[q] < ds->n, ANNB_EINVAL, "gather index out of range");
+    ANNB_CUDA(cudaSetDevice(c->device));
+    ANNB_TRY(c->s_in[1].ensure((size_t)n * 8));
+    ANNB_CUDA(cudaMemcpyAsync(c->s_in[1].p, order, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+    annb_dataset *g = new annb_dataset(*ds);
+    g->ctx = c;
+    g->n = n;
+    g->data = nullptr;
+    g->offs = nullptr;
+    g->lens = nullptr;
+    const int grid = c->num_sms * 8;
+    if (ds->kind == ANNB_DS_STRINGS) {
+        std::vector<int32_t> lens(ds->n);
+        ANNB_CUDA(cudaMemcpy(lens.data(), ds->lens, (size_t)ds->n * 4, cudaMemcpyDeviceToHost));
+        std::vector<int64_t> offs(n + 1);
+        int64_t pos = 0;
+        for (int64_t q = 0; q < n; ++q) {
+            offs[q] = pos;
+            pos += ((int64_t)lens[order[q]] + 15) / 16 * 16;
+        }
+        offs[n] = pos;
+        ANNB_CUDA(cudaMalloc(&g->data, (size_t)pos + 16));
+        ANNB_CUDA(cudaMalloc((void **)&g->offs, (size_t)(n + 1) * 8));
+        ANNB_CUDA(cudaMalloc((void **)&g->lens, (size_t)n * 4));
+        ANNB_CUDA(cudaMemcpyAsync(g->offs, offs.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+        ANNB_LAUNCH(gather_strings_kernel, grid, 256, 0, c->stream, (const uint8_t *)ds->data, ds->offs, ds->lens,
+                    c->s_in[1].as<int64_t>(), g->offs, n, (uint8_t *)g->data, g->lens);
+        ANNB_CUDA(cudaStreamSynchronize(c->stream));  // offs (host vector) is read by the async copy
+    } else {
+        const size_t es = ds->dtype == ANNB_F32 ? 4 : 8;
+        const size_t row_bytes = (size_t)ds->ld * es;
+        ANNB_REQUIRE(row_bytes % 8 == 0, ANNB_ESTATE, "row pitch is not a multiple of 8 bytes");
+        ANNB_CUDA(cudaMalloc(&g->data, (size_t)n * row_bytes));
+        ANNB_LAUNCH(gather_rows_kernel, grid, 256, 0, c->stream, (const uint2 *)ds->data, (int64_t)(row_bytes / 8),
+                    c->s_in[1].as<int64_t>(), n, (uint2 *)g->data);
+        ANNB_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    *out = g;
+    return ANNB_OK;
+}
+
 ANNB_API int annb_dataset_free(annb_dataset *ds)
 {
     if (!ds) return ANNB_OK;

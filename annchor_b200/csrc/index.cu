@@ -1293,6 +1293,53 @@ static int hash_insert(annb_index *ix, const int32_t *I, const int32_t *J, const
     return ANNB_OK;
 }
 
+namespace annb {
+// per tile: min / max of every anchor's distance over the tile's (real) points, and the closest anchors present
+__global__ void __launch_bounds__(64)
+tile_bounds_kernel(const float *__restrict__ D32, const PointMeta *__restrict__ meta, int64_t n, int64_t npad, int na,
+                   float *__restrict__ lo, float *__restrict__ hi, uint64_t *__restrict__ cm)
+{
+    const int t = blockIdx.x, a = threadIdx.x;
+    const int64_t p0 = (int64_t)t * TILE;
+    const int cnt = (int)min((int64_t)TILE, n - p0);
+    float mn = INFINITY, mx = -INFINITY;
+    if (a < na)
+        for (int p = 0; p < cnt; ++p) {
+            const float v = D32[(int64_t)a * npad + p0 + p];
+            mn = fminf(mn, v);
+            mx = fmaxf(mx, v);
+        }
+    lo[(int64_t)t * kMaxAnchors + a] = a < na ? mn : 0.0f;
+    hi[(int64_t)t * kMaxAnchors + a] = a < na ? mx : 0.0f;
+    unsigned long long m = 0;
+    for (int p = a; p < cnt; p += 64) m |= 1ull << meta[p0 + p].cA;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m |= __shfl_xor_sync(0xffffffffu, m, o);
+    __shared__ unsigned long long s_m[2];
+    if ((a & 31) == 0) s_m[a >> 5] = m;
+    __syncthreads();
+    if (a == 0) cm[t] = s_m[0] | s_m[1];
+}
+
+// sort key of the spatial order: (closest anchor, distance to it quantised to 1024 steps, point id)
+__global__ void spatial_key_kernel(const PointMeta *__restrict__ meta, const float *__restrict__ D32, int64_t npad,
+                                   int64_t n, float inv_scale, uint64_t *__restrict__ key)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        key[i] = ((uint64_t)row_bucket(meta[i], D32, npad, i, inv_scale) << 32) | (uint64_t)i;
+}
+
+__global__ void permute_D_kernel(const double *__restrict__ src, int64_t n, int na, const int32_t *__restrict__ order,
+                                 double *__restrict__ dst)
+{
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < (int64_t)na * n;
+         q += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t a = q / n, p = q % n;
+        dst[q] = src[a * n + order[p]];
+    }
+}
+}  // namespace annb
+
 static int launch_scan_i32_i64(annb_ctx *c, const int32_t *in, int64_t *out, int64_t n, DevBuf &tmp)
 {
     const int64_t nb = (n + SCAN_CHUNK - 1) / SCAN_CHUNK;
@@ -1344,9 +1391,70 @@ static int finish_anchors(annb_index *ix)
     if (!ix->A_host.empty())
         ANNB_LAUNCH(set_slots_kernel, 1, 32, 0, c->stream, ix->A_dev.as<int32_t>(),
                     (int)ix->A_host.size(), ix->meta.as<PointMeta>());
+    ANNB_LAUNCH(tile_bounds_kernel, ix->T, 64, 0, c->stream, ix->D32.as<float>(), ix->meta.as<PointMeta>(), ix->n,
+                ix->npad, ix->na, ix->tb_lo.as<float>(), ix->tb_hi.as<float>(), ix->tb_cm.as<uint64_t>());
     ix->have_anchors = true;
     ix->have_locality = false;
     return ANNB_OK;
+}
+
+// Spatial order: points sorted by (closest anchor, distance to it, id).  Points that are close to each
+// other get close positions, so a 128-point tile covers a small region of the anchor-distance space and
+// the sweeps can skip most tile pairs from the per-tile bounds.  order[new] = old.
+ANNB_API int annb_index_spatial_order(annb_index *ix, int64_t *order)
+{
+    TraceScope _ts("annb_index_spatial_order");
+    ANNB_REQUIRE(ix && order, ANNB_EINVAL, "NULL argument");
+    ANNB_REQUIRE(ix->have_anchors, ANNB_ESTATE, "anchors not computed yet");
+    annb_ctx *c = ix->ctx;
+    ANNB_CUDA(cudaSetDevice(c->device));
+    const int64_t n = ix->n;
+    ANNB_CUDA(cudaMemsetAsync(ix->counters.p, 0, 64, c->stream));
+    ANNB_LAUNCH(max_f32_kernel, grid_for_n(c, (int64_t)ix->na * ix->npad), 256, 0, c->stream, ix->D32.as<float>(),
+                (int64_t)ix->na * ix->npad, ix->counters.as<unsigned int>());
+    float dmax = 0.0f;
+    ANNB_CUDA(cudaMemcpyAsync(&dmax, ix->counters.p, 4, cudaMemcpyDeviceToHost, c->stream));
+    ANNB_CUDA(cudaStreamSynchronize(c->stream));
+    const float inv_scale = dmax > 0.0f && std::isfinite(dmax) ? 1023.0f / dmax : 0.0f;
+    ANNB_TRY(ix->t0.ensure((size_t)n * 8));
+    ANNB_LAUNCH(spatial_key_kernel, grid_for_n(c, n), 256, 0, c->stream, ix->meta.as<PointMeta>(), ix->D32.as<float>(),
+                ix->npad, n, inv_scale, ix->t0.as<uint64_t>());
+    std::vector<uint64_t> key(n);
+    ANNB_CUDA(cudaMemcpyAsync(key.data(), ix->t0.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+    ANNB_CUDA(cudaStreamSynchronize(c->stream));
+    std::sort(key.begin(), key.end());  // deterministic: ties inside a bucket by point id
+    for (int64_t p = 0; p < n; ++p) order[p] = (int64_t)(key[p] & 0xffffffffull);
+    return ANNB_OK;
+}
+
+// Take over the anchors of `src` (an index over the same items in their original order) into `ix`, an
+// index over the items gathered by `order` (annb_dataset_gather): D is permuted, A is renumbered.
+ANNB_API int annb_index_adopt_anchors(annb_index *ix, annb_index *src, const int64_t *order)
+{
+    TraceScope _ts("annb_index_adopt_anchors");
+    ANNB_REQUIRE(ix && src && order, ANNB_EINVAL, "NULL argument");
+    ANNB_REQUIRE(src->have_anchors && src->n == ix->n && src->na == ix->na, ANNB_ESTATE,
+                 "source index has no anchors or a different shape");
+    annb_ctx *c = ix->ctx;
+    ANNB_CUDA(cudaSetDevice(c->device));
+    const int64_t n = ix->n;
+    std::vector<int32_t> o32(n), inv(n);
+    for (int64_t p = 0; p < n; ++p) {
+        ANNB_REQUIRE(order[p] >= 0 && order[p] < n, ANNB_EINVAL, "order is not a permutation");
+        o32[p] = (int32_t)order[p];
+        inv[order[p]] = (int32_t)p;
+    }
+    ANNB_TRY(ix->t0.ensure((size_t)n * 4));
+    ANNB_CUDA(cudaMemcpyAsync(ix->t0.p, o32.data(), (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+    ANNB_LAUNCH(permute_D_kernel, grid_for_n(c, (int64_t)ix->na * n), 256, 0, c->stream, src->D64.as<double>(), n, ix->na,
+                ix->t0.as<int32_t>(), ix->D64.as<double>());
+    ix->A_host.clear();
+    for (int32_t a : src->A_host) ix->A_host.push_back(inv[a]);
+    if (!ix->A_host.empty())
+        ANNB_CUDA(cudaMemcpyAsync(ix->A_dev.p, ix->A_host.data(), ix->A_host.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    ANNB_CUDA(cudaStreamSynchronize(c->stream));
+    ix->ordered = true;
+    return finish_anchors(ix);
 }
 
 ANNB_API int annb_index_create(annb_ctx *c, const annb_dataset *ds, int metric,
@@ -1384,6 +1492,9 @@ ANNB_API int annb_index_create(annb_ctx *c, const annb_dataset *ds, int metric,
         if ((rc = ix->meta.ensure((size_t)ix->npad * sizeof(PointMeta)))) break;
         if ((rc = ix->tl_ptr.ensure((size_t)(ix->NT + 1) * 8))) break;
         if ((rc = ix->tl_code.ensure(256))) break;
+        if ((rc = ix->tb_lo.ensure((size_t)ix->T * kMaxAnchors * 4))) break;
+        if ((rc = ix->tb_hi.ensure((size_t)ix->T * kMaxAnchors * 4))) break;
+        if ((rc = ix->tb_cm.ensure((size_t)ix->T * 8))) break;
         if ((rc = ix->tl_a.ensure(256))) break;
         if ((rc = ix->tl_b.ensure(256))) break;
         if ((rc = ix->thresh.ensure((size_t)ix->npad * 4))) break;
@@ -1395,6 +1506,7 @@ ANNB_API int annb_index_create(annb_ctx *c, const annb_dataset *ds, int metric,
         return rc;
     }
     ANNB_CUDA(cudaMemsetAsync(ix->tl_ptr.p, 0, (size_t)(ix->NT + 1) * 8, c->stream));  // every tile list empty
+    ix->cull_enabled = getenv("ANNB_NO_CULL") == nullptr;  // test knob: sweeps without tile-level pruning
     ANNB_TRY(hash_alloc(ix, 1 << 16));
     *out = ix;
     return ANNB_OK;
@@ -1417,7 +1529,7 @@ ANNB_API int annb_index_destroy(annb_index *ix)
     if (!ix) return ANNB_OK;
     cudaSetDevice(ix->ctx->device);
     cudaStreamSynchronize(ix->ctx->stream);
-    DevBuf *all[] = {&ix->A_dev, &ix->D64, &ix->D32, &ix->Dpm, &ix->meta, &ix->scratch, &ix->htab, &ix->tl_ptr, &ix->tl_cnt, &ix->tl_code, &ix->tl_a, &ix->tl_b, &ix->scan_tmp,
+    DevBuf *all[] = {&ix->A_dev, &ix->D64, &ix->D32, &ix->Dpm, &ix->meta, &ix->scratch, &ix->htab, &ix->tl_ptr, &ix->tl_cnt, &ix->tl_code, &ix->tl_a, &ix->tl_b, &ix->scan_tmp, &ix->tb_lo, &ix->tb_hi, &ix->tb_cm,
                      &ix->errs_dev, &ix->rank_dev, &ix->thresh, &ix->l2val, &ix->l2id, &ix->hist,
                      &ix->counters, &ix->emit_key, &ix->emit_lvl, &ix->sel_i, &ix->sel_j, &ix->nxt_i,
                      &ix->nxt_j, &ix->tiehist, &ix->tiekeys, &ix->pool_key, &ix->pool_dad, &ix->t0,
@@ -1752,6 +1864,7 @@ static int run_thresh_rows(annb_index *ix, int k2, int col_stride, float *cut2, 
     A.l2id = k2 > 0 ? ix->l2id.as<int32_t>() : nullptr;
     A.col_stride = col_stride;
     A.col_phase = 0;
+    A.band = (ix->ordered && col_stride > 1) ? 8 : 0;  // spatial order: a row's near neighbours sit around the diagonal
     A.cut2 = cut2;
     A.rb_list = rb_list;
     A.n_rb = n_rb;
@@ -2016,7 +2129,7 @@ static void fill_efloor(const annb_index *ix, int floor_level, float *efloor, fl
 }
 
 static int run_score(annb_index *ix, int floor_level, uint64_t floor_mix_thr, int stride, bool emit,
-                     int64_t emit_cap, std::vector<uint64_t> &hist, unsigned long long cnt[5])
+                     int64_t emit_cap, std::vector<uint64_t> &hist, unsigned long long cnt[6])
 {
     annb_ctx *c = ix->ctx;
     ANNB_TRY(tile_lists_rebuild(ix));
@@ -2063,12 +2176,12 @@ static int run_score(annb_index *ix, int floor_level, uint64_t floor_mix_thr, in
     ANNB_CUDA(cudaEventRecord(c->ev1, c->stream));
     std::vector<uint32_t> h32(ix->nlevels);
     ANNB_CUDA(cudaMemcpyAsync(h32.data(), ix->hist.p, (size_t)ix->nlevels * 4, cudaMemcpyDeviceToHost, c->stream));
-    ANNB_CUDA(cudaMemcpyAsync(cnt, ix->counters.p, 40, cudaMemcpyDeviceToHost, c->stream));
+    ANNB_CUDA(cudaMemcpyAsync(cnt, ix->counters.p, 48, cudaMemcpyDeviceToHost, c->stream));
     ANNB_CUDA(cudaStreamSynchronize(c->stream));
     hist.assign(h32.begin(), h32.end());
     if (g_trace)
-        fprintf(stderr, "[annb-trace]   score sweep: stride %d floor %d pairs-in-phase2 %llu (flagged %llu) not-computed %llu emitted %llu\n",
-                stride, floor_level, cnt[3], cnt[4], cnt[1], cnt[0]);
+        fprintf(stderr, "[annb-trace]   score sweep: stride %d floor %d pairs-in-phase2 %llu (flagged %llu) not-computed %llu emitted %llu, tiles pruned %llu\n",
+                stride, floor_level, cnt[3], cnt[4], cnt[1], cnt[0], cnt[5]);
     ANNB_TRY(ix->reduce(hist.data(), (int64_t)hist.size(), ANNB_RED_U64));  // global level counts
     float ms = 0;
     ANNB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
@@ -2165,7 +2278,7 @@ ANNB_API int annb_index_select(annb_index *ix, int64_t n_refine, int64_t lookahe
     int64_t tot_target = want1 >= n_nc ? n_nc : std::min<int64_t>(want2, n_nc);
 
     std::vector<uint64_t> h1, h2;
-    unsigned long long c1v[5] = {0, 0, 0, 0, 0}, c2v[5] = {0, 0, 0, 0, 0};
+    unsigned long long c1v[6] = {0, 0, 0, 0, 0, 0}, c2v[6] = {0, 0, 0, 0, 0, 0};
     // Level 0 is probability 0.  On small problems it takes part like any other level (the
     // reference's argpartition then picks arbitrary probability-0 pairs).  On large problems
     // emitting the probability-0 bulk is pointless and Theta(N^2): the cut never goes below level 1,

@@ -69,6 +69,12 @@ struct View {
     const long long *tl_ptr;   // [NT + 1] upper-triangular tiles, row-major (tile_index)
     const uint32_t *tl_code;   // r << 9 | c << 2 | kind
     const float *tl_a, *tl_b;  // KNOWN: a = distance; TIGHT: (a, b) = (lb, ub)
+    // per-tile bounds: [T][kMaxAnchors] min / max anchor distance over the tile's points, and the set of
+    // closest anchors that occur in the tile -- a sweep skips a tile pair when they prove that no pair of
+    // it can pass the phase-1 test (sweep.cuh: tile_pred_min)
+    const float *tb_lo, *tb_hi;
+    const uint64_t *tb_cm;
+    int cull;
 };
 
 __host__ __device__ __forceinline__ int64_t tile_index(int ti, int tj, int T)

@@ -26,6 +26,9 @@ struct annb_index {
     DevBuf htab;
     // per-tile entry lists derived from the hash map (rebuilt lazily before a sweep)
     DevBuf tl_ptr, tl_cnt, tl_code, tl_a, tl_b, scan_tmp;
+    // per-tile anchor-distance intervals and closest-anchor sets (tile-level pruning in the sweeps)
+    DevBuf tb_lo, tb_hi, tb_cm;
+    bool ordered = false;  // the points were renumbered by annb_index_spatial_order (coherent tiles)
     bool tl_dirty = false;
     int64_t tl_entries = 0;
     uint64_t hcap = 0;
@@ -103,8 +106,13 @@ struct annb_index {
         V.tl_code = tl_code.as<uint32_t>();
         V.tl_a = tl_a.as<float>();
         V.tl_b = tl_b.as<float>();
+        V.tb_lo = tb_lo.as<float>();
+        V.tb_hi = tb_hi.as<float>();
+        V.tb_cm = tb_cm.as<uint64_t>();
+        V.cull = cull_enabled ? 1 : 0;
         return V;
     }
+    bool cull_enabled = true;
     int64_t n_not_computed() const { return n_candidates - n_anchor_pairs - n_known; }
 };
 

@@ -410,6 +410,78 @@ __device__ __forceinline__ void tile_from_index(int64_t t, int T, int &ti, int &
     tj = r + (int)(t - tile_index(r, r, T));
 }
 
+// ---- tile-level pruning ------------------------------------------------------------------------
+// Lower bound of the clipped prediction over ALL pairs (i in tile ti, j in tile tj), from the per-tile
+// min / max anchor distances: interval arithmetic on the very operations phase 1 performs
+//   lb = max_a |D_ia - D_ja| >= max_a gap_a,   ub = min_a (D_ia + D_ja) >= min_a (lo_a + lo'_a),
+//   s2 = D_i,cA(j) + D_j,cA(i)  in  [s_lo, s_hi]   (over the closest anchors that occur in the tiles),
+//   y  = fma(lb, c0, fma(ub, c1, fma(s2, c2/2, icpt)))  evaluated at the interval end the sign of each
+//        coefficient selects, minimised over the regression bins the s2 interval overlaps,
+// then clipped.  Floating-point subtraction, addition, fma, min and max are monotone, so the result is
+// a true lower bound of what predict_clip2 returns for any pair of the two tiles -- no tolerance needed.
+// Every warp computes it redundantly (lanes over anchors, ~150 instructions per tile).
+__device__ __forceinline__ float tile_pred_min(const View &V, const Model &M, int ti, int tj)
+{
+    const int lane = threadIdx.x & 31;
+    const float *loI = V.tb_lo + (int64_t)ti * kMaxAnchors, *hiI = V.tb_hi + (int64_t)ti * kMaxAnchors;
+    const float *loJ = V.tb_lo + (int64_t)tj * kMaxAnchors, *hiJ = V.tb_hi + (int64_t)tj * kMaxAnchors;
+    const uint64_t cmI = V.tb_cm[ti], cmJ = V.tb_cm[tj];
+    float lbmin = 0.0f, lbmax = 0.0f, ubmin = INFINITY, ubmax = INFINITY;
+    float siLo = INFINITY, siHi = -INFINITY, sjLo = INFINITY, sjHi = -INFINITY;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int a = lane + 32 * q;
+        if (a < V.na) {
+            const float li = loI[a], hi = hiI[a], lj = loJ[a], hj = hiJ[a];
+            lbmin = fmaxf(lbmin, fmaxf(li - hj, lj - hi));
+            lbmax = fmaxf(lbmax, fmaxf(hi - lj, hj - li));
+            ubmin = fminf(ubmin, li + lj);
+            ubmax = fminf(ubmax, hi + hj);
+            if ((cmJ >> a) & 1ull) {  // D_i,cA(j): anchors that are the closest one of some point of tile j
+                siLo = fminf(siLo, li);
+                siHi = fmaxf(siHi, hi);
+            }
+            if ((cmI >> a) & 1ull) {
+                sjLo = fminf(sjLo, lj);
+                sjHi = fmaxf(sjHi, hj);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lbmin = fmaxf(lbmin, __shfl_xor_sync(0xffffffffu, lbmin, o));
+        lbmax = fmaxf(lbmax, __shfl_xor_sync(0xffffffffu, lbmax, o));
+        ubmin = fminf(ubmin, __shfl_xor_sync(0xffffffffu, ubmin, o));
+        ubmax = fminf(ubmax, __shfl_xor_sync(0xffffffffu, ubmax, o));
+        siLo = fminf(siLo, __shfl_xor_sync(0xffffffffu, siLo, o));
+        siHi = fmaxf(siHi, __shfl_xor_sync(0xffffffffu, siHi, o));
+        sjLo = fminf(sjLo, __shfl_xor_sync(0xffffffffu, sjLo, o));
+        sjHi = fmaxf(sjHi, __shfl_xor_sync(0xffffffffu, sjHi, o));
+    }
+    const float s_lo = siLo + sjLo, s_hi = siHi + sjHi;
+    float ymin = INFINITY;
+    for (int b = 0; b < M.nb; ++b) {
+        // bin b holds e2[b] < s2 <= e2[b+1]  (e2[0] = -inf, e2[nb] = +inf; reg_bin2)
+        const float blo = b == 0 ? -INFINITY : M.e2[b], bhi = b + 1 < M.nb ? M.e2[b + 1] : INFINITY;
+        if (!(s_hi > blo && s_lo <= bhi)) continue;
+        const float c0 = M.c0[b], c1 = M.c1[b], cz = 0.5f * M.c2[b];
+        const float y = fmaf(c0 >= 0.0f ? lbmin : lbmax, c0,
+                             fmaf(c1 >= 0.0f ? ubmin : ubmax, c1, fmaf(cz >= 0.0f ? s_lo : s_hi, cz, M.ic[b])));
+        ymin = fminf(ymin, y);
+    }
+    return fminf(fmaxf(ymin, lbmin), ubmin);
+}
+
+// largest of 128 shared-memory values (every warp computes it)
+__device__ __forceinline__ float tile_max128(const float *v)
+{
+    const int lane = threadIdx.x & 31;
+    float m = fmaxf(fmaxf(v[lane], v[lane + 32]), fmaxf(v[lane + 64], v[lane + 96]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    return m;
+}
+
 struct PairVal {
     float v;        // RefineApprox value (exact if computed, clipped prediction otherwise, -1 if forced)
     float dad;      // 2 * double anchor distance

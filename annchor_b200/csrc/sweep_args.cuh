@@ -16,6 +16,8 @@ struct ThreshArgs {
     int qcap;          // set by the launcher: per-warp survivor queue capacity
     int col_stride;    // visit the column tiles tc = col_phase, col_phase + col_stride, ... (1: all)
     int col_phase;
+    int band;          // > 0: first the column tiles rb - band .. rb + band (spatially ordered index: that is
+                       // where a row's near neighbours are), then the strided ones outside the band
     float *cut2;       // [npad] out (k2 > 0): k2-th smallest not-computed value of the visited columns
     const int32_t *rb_list;  // explicit row blocks to process (nullptr: all, split over the ranks)
     int n_rb;

@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(SWT, 1) score_sweep_kernel(const __grid_consta
     const int64_t per = (nq + gridDim.x - 1) / gridDim.x;
     const int64_t m0 = (int64_t)blockIdx.x * per, m1 = min(nq, m0 + per);
     unsigned long long n_nc = 0, n_swept = 0, n_staged = 0, n_flagged = 0;
+    int n_culled = 0;
     int en = 0;  // staged emissions of this warp
 
     auto tile_of = [&](int64_t m, int &ti, int &tj) {
@@ -149,9 +150,19 @@ __global__ void __launch_bounds__(SWT, 1) score_sweep_kernel(const __grid_consta
         }
         const float *sDi = buf ? sD1i : sD0i, *sDj = buf ? sD1j : sD0j;
         const PointMeta *sMi = buf ? sM1i : sM0i, *sMj = buf ? sM1j : sM0j;
+        const float *tI = thI + buf * TILE, *tJ = thJ + buf * TILE;
+        // tile-level pruning: no store entry in the tile and even the smallest possible prediction
+        // cannot reach the floor level for the largest threshold of the two tiles (the same test
+        // `cut - pred > margin` phase 1 applies per pair, at the tile's extremes)
+        if (V.cull && A.ef_min > -INFINITY && sDesc[(m - m0) & 3].end == sDesc[(m - m0) & 3].base && ti != tj) {
+            const float cutmax = fmaxf(tile_max128(tI), tile_max128(tJ));
+            if (!(cutmax - tile_pred_min(V, M, ti, tj) > A.ef_min)) {
+                n_culled += 1;
+                continue;
+            }
+        }
         build_tile_store(V, ts, &sDesc[(m - m0) & 3], sCode + buf * TL_CAP, sBm, 0);
         const uint32_t *bm = sBm;
-        const float *tI = thI + buf * TILE, *tJ = thJ + buf * TILE;
         // ---- phase 1: bounds + clipped prediction; keep (pred < cut-off) | flagged ----
         float cj[8];
         int cAj[8];
@@ -305,6 +316,7 @@ __global__ void __launch_bounds__(SWT, 1) score_sweep_kernel(const __grid_consta
         atomicAdd(&A.counters[2], n_swept);
         atomicAdd(&A.counters[3], n_staged);   // phase-1 survivors handed to phase 2
         atomicAdd(&A.counters[4], n_flagged);  // of which carried a flag bit (known / tightened / forced)
+        if (warp == 0) atomicAdd(&A.counters[5], (unsigned long long)n_culled);  // tiles skipped by the tile-level bound
     }
 }
 

@@ -108,36 +108,55 @@ __global__ void __launch_bounds__(SWT, 1) thresh_sweep_kernel(const __grid_const
         }
         // canonical (upper-triangular) tile that holds the pairs of (row block rb, column tile tc)
         auto canon = [&](int tc) { return tile_index(rb < tc ? rb : tc, rb < tc ? tc : rb, V.T); };
+        // column tile sequence: the band around the diagonal first (if any), then col_phase + k * col_stride
+        // outside the band; -1 past the end
+        const int blo = A.band > 0 ? max(0, rb - A.band) : 0, bhi = A.band > 0 ? min(V.T - 1, rb + A.band) : -1;
+        const int nband = bhi - blo + 1;
+        const int kb = (nband == 0 || blo <= A.col_phase) ? 0 : (blo - A.col_phase + A.col_stride - 1) / A.col_stride;
+        const int ka = (nband == 0 || bhi < A.col_phase) ? 0 : (bhi - A.col_phase) / A.col_stride + 1;
+        auto col_at = [&](int s) {
+            int tc;
+            if (s < nband) tc = blo + s;
+            else {
+                const int e = s - nband;
+                tc = A.col_phase + ((nband == 0 || e < kb) ? e : ka + (e - kb)) * A.col_stride;
+            }
+            return tc < V.T ? tc : -1;
+        };
         __syncthreads();  // the previous row block is done with the descriptors
-        if (tid < 2 && A.col_phase + tid * A.col_stride < V.T) {
-            const int64_t t = canon(A.col_phase + tid * A.col_stride);
+        if (tid < 2 && col_at(tid) >= 0) {
+            const int64_t t = canon(col_at(tid));
             sDesc[tid].base = V.tl_ptr[t];
             sDesc[tid].end = V.tl_ptr[t + 1];
         }
         __syncthreads();
         load_point_tile(V, rb, sDi, sMi);
-        if (A.col_phase < V.T) {
-            load_point_tile(V, A.col_phase, sDj0, sMj0);
+        if (col_at(0) >= 0) {
+            load_point_tile(V, col_at(0), sDj0, sMj0);
             load_tile_codes(V, &sDesc[0], sCode);
         }
         cp_async_commit();
 
         int par = 0;  // buffer parity
-        int step_no = 0;
-        for (int tc = A.col_phase; tc < V.T; tc += A.col_stride, par ^= 1, ++step_no) {
+        for (int step_no = 0; col_at(step_no) >= 0; par ^= 1, ++step_no) {
+            const int tc = col_at(step_no);
             const float *sDj = par ? sDj1 : sDj0;
             const PointMeta *sMj = par ? sMj1 : sMj0;
             cp_async_wait_all();
             __syncthreads();
-            if (tc + A.col_stride < V.T) {  // prefetch the next column tile into the other buffer
-                load_point_tile(V, tc + A.col_stride, par ? sDj0 : sDj1, par ? sMj0 : sMj1);
+            if (col_at(step_no + 1) >= 0) {  // prefetch the next column tile into the other buffer
+                load_point_tile(V, col_at(step_no + 1), par ? sDj0 : sDj1, par ? sMj0 : sMj1);
                 load_tile_codes(V, &sDesc[(step_no + 1) & 3], sCode + (par ^ 1) * TL_CAP);
-                if (tc + 2 * A.col_stride < V.T)
-                    load_tile_desc(V, canon(tc + 2 * A.col_stride), &sDesc[(step_no + 2) & 3]);
+                if (col_at(step_no + 2) >= 0) load_tile_desc(V, canon(col_at(step_no + 2)), &sDesc[(step_no + 2) & 3]);
                 cp_async_commit();
             }
             // entries are stored once per pair, in the tile of (lo, hi): the flags phase 1 reads are
             // re-oriented so that bit (row, col) of sBF is the flag of (this CTA's row point, column point)
+            // tile-level pruning (metrics only: the phase-1 filter `pred < cut[row]` is on): no store entry
+            // and the smallest possible prediction is not below the largest current cut of the 128 rows
+            if (V.cull && filter && sDesc[step_no & 3].end == sDesc[step_no & 3].base && tc != rb) {
+                if (tile_pred_min(V, M, rb, tc) >= tile_max128(cut)) continue;
+            }
             build_tile_store(V, ts, &sDesc[step_no & 3], sCode + par * TL_CAP, sBF, tc < rb ? 1 : (tc == rb ? 2 : 3));
             // ---- phase 1: bounds + clipped prediction, two passes of 4 x 8 pairs per thread ----
             int cAj[8];
@@ -373,10 +392,16 @@ __global__ void __launch_bounds__(SWT, 1) thresh_pairs_kernel(const __grid_const
         }
         const float *sDi = buf ? sD1i : sD0i, *sDj = buf ? sD1j : sD0j;
         const PointMeta *sMi = buf ? sM1i : sM0i, *sMj = buf ? sM1j : sM0j;
-        build_tile_store(V, ts, &sDesc[(m - m0) & 3], sCode + buf * TL_CAP, sBm, 0);
-        const uint32_t *bm = sBm;
         const float *k1I = c1I + buf * TILE, *k1J = c1J + buf * TILE;
         const float *k2I = c2I + buf * TILE, *k2J = c2J + buf * TILE;
+        // tile-level pruning: no store entry in the tile and even the smallest possible prediction
+        // exceeds every cut of the two tiles (phase 1 keeps a pair iff pred <= max(cut_i, cut_j))
+        if (V.cull && V.is_metric && sDesc[(m - m0) & 3].end == sDesc[(m - m0) & 3].base && ti != tj) {
+            const float cutmax = fmaxf(fmaxf(tile_max128(k1I), tile_max128(k2I)), fmaxf(tile_max128(k1J), tile_max128(k2J)));
+            if (tile_pred_min(V, M, ti, tj) > cutmax) continue;
+        }
+        build_tile_store(V, ts, &sDesc[(m - m0) & 3], sCode + buf * TL_CAP, sBm, 0);
+        const uint32_t *bm = sBm;
         float cj[8];
         int cAj[8];
 #pragma unroll

@@ -80,6 +80,10 @@ int annb_dataset_strings(annb_ctx *ctx, const uint8_t *chars, const int64_t *off
 /* histograms (n, nbins), dtype ANNB_F32 / ANNB_F64 / ANNB_U8; stored as unit-mass CDFs. */
 int annb_dataset_hist(annb_ctx *ctx, const void *H, int64_t n, int64_t nbins, int dtype,
                       annb_dataset **out);
+/* a new data set with the items of `ds` in the given order (item q of the result = item order[q]),
+ * copied device to device; no counterpart in the reference (its arrays live in host memory) */
+int annb_dataset_gather(annb_ctx *ctx, const annb_dataset *ds, const int64_t *order, int64_t n,
+                        annb_dataset **out);
 int annb_dataset_free(annb_dataset *ds);
 int64_t annb_dataset_len(const annb_dataset *ds);
 
@@ -165,6 +169,14 @@ int annb_index_reserve_pairs(annb_index *ix, int64_t n_pairs);
 /* stage 1: run the MaxMin picker into the index (or load caller-provided anchors) */
 int annb_index_maxmin(annb_index *ix, int64_t first, int64_t *A);
 int annb_index_set_anchors(annb_index *ix, const int64_t *A, int64_t nA, const double *D);
+/* Spatial renumbering (no counterpart in the reference; results are those of the reference algorithm
+ * on the relabelled data set).  order[new] = old: points sorted by (closest anchor, distance to it, id),
+ * so that the 128-point tiles of the sweeps are geometrically coherent and whole tile pairs can be
+ * pruned from per-tile bounds.  Use: annb_index_maxmin / set_anchors on an index over the original
+ * data set, annb_index_spatial_order, annb_dataset_gather, annb_index_create on the gathered data set,
+ * annb_index_adopt_anchors(new, old, order). */
+int annb_index_spatial_order(annb_index *ix, int64_t *order);
+int annb_index_adopt_anchors(annb_index *ix, annb_index *src, const int64_t *order);
 /* copy D out as float64 (n, na) row-major */
 int annb_index_get_D(annb_index *ix, double *D);
 /* candidate set (get_locality): returns number of candidate pairs P and the number of rows

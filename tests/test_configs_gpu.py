@@ -245,3 +245,55 @@ def test_quality_vs_oracle(kind, n, pw, k):
     e_orc = compare_neighbor_graphs(exact, orc.neighbor_graph, k)
     assert abs(dev.evals - orc.evals) <= 0.002 * orc.evals
     assert e_dev <= 1.1 * e_orc + 50, (e_dev, e_orc)
+
+
+@pytest.mark.parametrize("kind", ["euclid", "strings"])
+def test_tile_pruning_is_exact(monkeypatch, kind):
+    """Large problems renumber the points in spatial order and skip tile pairs whose per-tile bounds
+    prove that no pair can pass the phase-1 test of a sweep.  Pruning must not change anything:
+    the fit with pruning == the fit without (same numbering), bit for bit."""
+    from annchor_b200.annchor import Annchor
+    if kind == "euclid":
+        X, metric = bench_blobs(24000, 128, 100, 42, np.float32), "euclidean"
+    else:
+        X, metric = synthetic_strings(20000), "levenshtein"
+    kw = dict(n_anchors=30, n_neighbors=15, n_samples=5000, p_work=0.01)
+    monkeypatch.delenv("ANNB_NO_CULL", raising=False)
+    a = Annchor(X, metric, **kw).fit()
+    assert a._order is not None and np.array_equal(np.sort(a._order), np.arange(len(X)))
+    monkeypatch.setenv("ANNB_NO_CULL", "1")
+    b = Annchor(X, metric, **kw).fit()
+    monkeypatch.delenv("ANNB_NO_CULL")
+    assert a.evals == b.evals and a.n_forced == b.n_forced and a.n_tightened == b.n_tightened
+    assert np.array_equal(a.neighbor_graph[0], b.neighbor_graph[0])
+    assert np.array_equal(a.neighbor_graph[1], b.neighbor_graph[1])
+    assert np.array_equal(a.A, b.A)
+    np.testing.assert_array_equal(a.D, b.D)
+
+
+def test_spatial_renumbering_keeps_the_result_quality(monkeypatch):
+    """Renumbering relabels the points (ties are then broken differently, like any relabelling of
+    the reference's input would): same anchors, same D, the same structural guarantees and the same
+    recall against the exact graph."""
+    from annchor_b200.annchor import Annchor
+    from oracle.metrics import PairMetric
+    n, k = 24000, 15
+    X = bench_blobs(n, 128, 100, 42, np.float32)
+    kw = dict(n_anchors=30, n_neighbors=k, n_samples=5000, p_work=0.02)
+    a = Annchor(X, "euclidean", **kw).fit()
+    monkeypatch.setenv("ANNB_NO_REORDER", "1")
+    b = Annchor(X, "euclidean", **kw).fit()
+    monkeypatch.delenv("ANNB_NO_REORDER")
+    assert a._order is not None and b._order is None
+    assert np.array_equal(a.A, b.A)
+    np.testing.assert_array_equal(a.D, b.D)
+    assert abs(a.evals - b.evals) <= 0.002 * b.evals
+    for ann in (a, b):
+        _check_structure(ann, n, k)
+    rows = np.random.default_rng(3).choice(n, size=200, replace=False)
+    _check_distances_exact(a, PairMetric(X, "euclidean"), rows, exact_int=False)
+    exact = a._dataset.bruteforce_knn(k)
+    ra = float(np.mean(a.neighbor_graph[1][:, 1:] <= exact[1][:, k - 1:k] * (1 + 1e-6)))
+    rb = float(np.mean(b.neighbor_graph[1][:, 1:] <= exact[1][:, k - 1:k] * (1 + 1e-6)))
+    print("recall with / without renumbering: %.4f / %.4f" % (ra, rb))
+    assert abs(ra - rb) < 0.02, (ra, rb)
