@@ -487,6 +487,24 @@ class Annchor:
             idx, dist = iu, du
         self.neighbor_graph = (idx, dist)
 
+    def to_sparse_matrix(self):
+        """The k-NN graph as a dictionary-of-keys sparse distance matrix (annchor/annchor.py:625-641):
+        D[i, j] = D[j, i] = distance + the smallest positive float64, for every (i, j) of the graph."""
+        from scipy.sparse import coo_matrix
+        idx, dist = self.neighbor_graph
+        n, k = idx.shape
+        eps = np.nextafter(0, 1, dtype=np.float64)
+        rows = np.repeat(np.arange(n, dtype=np.int64), k)
+        cols = idx.ravel()
+        vals = dist.ravel() + eps
+        ok = cols >= 0
+        r = np.concatenate([rows[ok], cols[ok]])
+        c = np.concatenate([cols[ok], rows[ok]])
+        v = np.concatenate([vals[ok], vals[ok]])
+        # one entry per (row, col): the reference's loop overwrites, a symmetric metric writes equal values
+        _, first = np.unique(r * np.int64(n) + c, return_index=True)
+        return coo_matrix((v[first], (r[first], c[first])), shape=(n, n)).todok()
+
     def query(self, Q, nn=15, p_work=0.3, get_exact_query_ijs=None):
         """Query new data against the fitted index (annchor/annchor.py:643-683): returns
         (ngi int64 (len(Q), nn), ngd float64 (len(Q), nn)), the nn approximate nearest points of X per

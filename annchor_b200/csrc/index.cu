@@ -1422,8 +1422,12 @@ ANNB_API int annb_index_spatial_order(annb_index *ix, int64_t *order)
     std::vector<uint64_t> key(n);
     ANNB_CUDA(cudaMemcpyAsync(key.data(), ix->t0.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
     ANNB_CUDA(cudaStreamSynchronize(c->stream));
-    std::sort(key.begin(), key.end());  // deterministic: ties inside a bucket by point id
-    for (int64_t p = 0; p < n; ++p) order[p] = (int64_t)(key[p] & 0xffffffffull);
+    // counting sort over the 64 x 1024 buckets; ids are visited in ascending order, so ties inside a
+    // bucket stay ordered by point id (deterministic, identical on every rank)
+    std::vector<int64_t> start((size_t)ROW_BUCKETS + 1, 0);
+    for (int64_t i = 0; i < n; ++i) start[(size_t)(key[i] >> 32) + 1] += 1;
+    for (int b = 0; b < ROW_BUCKETS; ++b) start[b + 1] += start[b];
+    for (int64_t i = 0; i < n; ++i) order[start[(size_t)(key[i] >> 32)]++] = i;
     return ANNB_OK;
 }
 
@@ -2880,13 +2884,19 @@ ANNB_API int annb_index_sample_pool_bins(annb_index *ix, uint64_t seed, const do
     SampleArgs A;
     A.V = ix->view();
     A.seed = (uint32_t)(mix64(seed ^ 0x5851f42d4c957f2dull) >> 32);
-    A.thr = 0;
-    A.tile_thr = 0xffffffffu;
     A.nb = (int)nb;
     for (int b = 0; b <= nb; ++b) A.edge[b] = (float)bins[b];
+    // sparse rates: visit a fraction of the tiles and take pairs there at a higher rate (like the uniform pool), so
+    // that the sweep's cost follows the largest rate instead of being a full pass over all pairs
+    double rmax = 0.0;
+    for (int b = 0; b < nb; ++b) rmax = std::max(rmax, rate[b]);
+    const double tile_frac = std::min(1.0, std::max(1.0 / 64.0, 8.0 * rmax));
+    A.tile_thr = tile_frac >= 1.0 ? 0xffffffffu : (uint32_t)(tile_frac * 4294967295.0);
+    A.thr = 0;
     for (int b = 0; b < MAX_BINS; ++b) {
-        const double r = b < nb ? rate[b] : 0.0;
+        const double r = (b < nb ? rate[b] : 0.0) / tile_frac;
         A.bthr[b] = r <= 0.0 ? 0u : (r >= 1.0 ? 0xffffffffu : (uint32_t)std::max(1.0, r * 4294967295.0));
+        A.thr = std::max(A.thr, A.bthr[b]);
     }
     ANNB_TRY(ix->pool_key.ensure((size_t)max_pool * 8));
     ANNB_TRY(ix->pool_dad.ensure((size_t)max_pool * 4));

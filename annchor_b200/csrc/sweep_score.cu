@@ -95,19 +95,19 @@ __global__ void __launch_bounds__(SWT, 1) score_sweep_kernel(const __grid_consta
         for (int k = tid; k < A.n_errs + M.nb; k += blockDim.x) sRank[k] = A.ranktab[k];
     }
 
-    // this CTA's contiguous slice of the rank's tile sequence
+    // this CTA's share of the rank's tile sequence, interleaved (CTA b takes b, b + grid, b + 2 grid, ...):
+    // with spatially ordered points the expensive tiles sit around the diagonal, i.e. in runs of the
+    // sequence, and a contiguous slice per CTA would leave most SMs idle while a few finish
     const int64_t nq = (A.q_end - A.q_begin + A.q_stride - 1) / A.q_stride;
-    const int64_t per = (nq + gridDim.x - 1) / gridDim.x;
-    const int64_t m0 = (int64_t)blockIdx.x * per, m1 = min(nq, m0 + per);
+    const int64_t m0 = 0, m1 = (nq - (int64_t)blockIdx.x + gridDim.x - 1) / gridDim.x;
     unsigned long long n_nc = 0, n_swept = 0, n_staged = 0, n_flagged = 0;
     int n_culled = 0;
     int en = 0;  // staged emissions of this warp
 
-    auto tile_of = [&](int64_t m, int &ti, int &tj) {
-        const int64_t q = A.q_begin + m * A.q_stride;
-        tile_from_index(q * A.world + A.rank, V.T, ti, tj);
+    auto tile_no = [&](int64_t m) {
+        return (A.q_begin + ((int64_t)blockIdx.x + m * gridDim.x) * A.q_stride) * A.world + A.rank;
     };
-    auto tile_no = [&](int64_t m) { return (A.q_begin + m * A.q_stride) * A.world + A.rank; };
+    auto tile_of = [&](int64_t m, int &ti, int &tj) { tile_from_index(tile_no(m), V.T, ti, tj); };
     TileStore ts;
     ts.init(sTS);
     if (m0 < m1) {
@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(256, 2) sample_sweep_kernel(const SampleArgs A
         // two-stage uniform sub-sample: tiles first (point ids carry no geometry, so a tile is a random
         // block of pairs), then pairs inside the visited tiles
         const uint64_t tix = (uint64_t)(m * A.world + A.rank);
-        if (A.nb == 0 && A.tile_thr != 0xffffffffu &&
+        if (A.tile_thr != 0xffffffffu &&
             hash_pair32((uint32_t)tix, (uint32_t)(tix >> 32), A.seed ^ 0x5bd1e995u) > A.tile_thr)
             continue;
         int ti, tj;
@@ -395,16 +395,16 @@ __global__ void __launch_bounds__(256, 2) sample_sweep_kernel(const SampleArgs A
             for (int c = 0; c < 8; ++c) {
                 const int lj = micro_off(tx, c);
                 const uint32_t gj = (uint32_t)(tj * TILE + lj);
-                uint32_t thr = A.thr;
-                if (A.nb > 0) {
-                    // sampler bins [lo, hi) (utils.py:547-549) on the pair's double anchor distance
+                const uint32_t h = hash_pair32(gi, gj, A.seed);
+                bool keep = h <= A.thr && (!diag || li < lj) && gj < (uint32_t)V.n;
+                if (keep && A.nb > 0) {
+                    // stratified mode: A.thr is the largest per-bin threshold (cheap pre-filter); the pair's own
+                    // threshold follows from its sampler bin [lo, hi) (utils.py:547-549) on the double anchor distance
                     const float dad = 0.5f * (sDi[sMj[lj].cA * SROW + li] + sDj[sMi[li].cA * SROW + lj]);
                     int b = 0;
                     for (int k = 1; k < A.nb; ++k) b += dad >= A.edge[k];
-                    thr = A.bthr[b];
+                    keep = A.bthr[b] != 0u && h <= A.bthr[b];
                 }
-                const bool keep = thr != 0u && hash_pair32(gi, gj, A.seed) <= thr && (!diag || li < lj) &&
-                                  gj < (uint32_t)V.n;
                 const unsigned mm = __ballot_sync(0xffffffffu, keep);
                 if (keep) queue[qn + __popc(mm & ((1u << lane) - 1))] = (uint32_t)li | ((uint32_t)lj << 8);
                 qn += __popc(mm);

@@ -346,8 +346,9 @@ __global__ void __launch_bounds__(SWT, 1) thresh_pairs_kernel(const __grid_const
 
     const int64_t NT = (int64_t)V.T * (V.T + 1) / 2;
     const int64_t nq = (NT - A.rank + A.world - 1) / A.world;
-    const int64_t per = (nq + gridDim.x - 1) / gridDim.x;
-    const int64_t m0 = (int64_t)blockIdx.x * per, m1 = min(nq, m0 + per);
+    // interleaved share of the tile sequence (see score_sweep_kernel)
+    const int64_t m0 = 0, m1 = (nq - (int64_t)blockIdx.x + gridDim.x - 1) / gridDim.x;
+    auto tile_no = [&](int64_t m) { return ((int64_t)blockIdx.x + m * gridDim.x) * A.world + A.rank; };
     auto stage_cuts = [&](int ti, int tj, int b) {
         if (tid < TILE) {
             const int64_t gi = (int64_t)ti * TILE + tid, gj = (int64_t)tj * TILE + tid;
@@ -361,13 +362,13 @@ __global__ void __launch_bounds__(SWT, 1) thresh_pairs_kernel(const __grid_const
     ts.init(sTS);
     if (m0 < m1) {
         if (tid < 2 && m0 + tid < m1) {
-            const int64_t t = (m0 + tid) * A.world + A.rank;
+            const int64_t t = tile_no(m0 + tid);
             sDesc[tid].base = V.tl_ptr[t];
             sDesc[tid].end = V.tl_ptr[t + 1];
         }
         __syncthreads();
         int ti, tj;
-        tile_from_index(m0 * A.world + A.rank, V.T, ti, tj);
+        tile_from_index(tile_no(m0), V.T, ti, tj);
         load_point_tile(V, ti, sD0i, sM0i);
         load_point_tile(V, tj, sD0j, sM0j);
         load_tile_codes(V, &sDesc[0], sCode);
@@ -377,16 +378,16 @@ __global__ void __launch_bounds__(SWT, 1) thresh_pairs_kernel(const __grid_const
     for (int64_t m = m0; m < m1; ++m) {
         const int buf = (int)((m - m0) & 1);
         int ti, tj;
-        tile_from_index(m * A.world + A.rank, V.T, ti, tj);
+        tile_from_index(tile_no(m), V.T, ti, tj);
         cp_async_wait_all();
         __syncthreads();
         if (m + 1 < m1) {
             int ni, nj;
-            tile_from_index((m + 1) * A.world + A.rank, V.T, ni, nj);
+            tile_from_index(tile_no(m + 1), V.T, ni, nj);
             load_point_tile(V, ni, buf ? sD0i : sD1i, buf ? sM0i : sM1i);
             load_point_tile(V, nj, buf ? sD0j : sD1j, buf ? sM0j : sM1j);
             load_tile_codes(V, &sDesc[(m + 1 - m0) & 3], sCode + (buf ^ 1) * TL_CAP);
-            if (m + 2 < m1) load_tile_desc(V, (m + 2) * A.world + A.rank, &sDesc[(m + 2 - m0) & 3]);
+            if (m + 2 < m1) load_tile_desc(V, tile_no(m + 2), &sDesc[(m + 2 - m0) & 3]);
             stage_cuts(ni, nj, buf ^ 1);
             cp_async_commit();
         }
