@@ -478,14 +478,8 @@ class Annchor:
             self._trace["n_tightened%d" % self._it] = self.n_tightened
 
     def get_ann(self):
-        idx, dist = self._index.neighbor_graph()
-        if self._order is not None:  # back to the caller's numbering: rows and neighbour ids
-            o = self._order
-            iu, du = np.empty_like(idx), np.empty_like(dist)
-            iu[o] = np.where(idx >= 0, o[np.maximum(idx, 0)], -1)
-            du[o] = dist
-            idx, dist = iu, du
-        self.neighbor_graph = (idx, dist)
+        # (a renumbered index reports the graph in the caller's numbering: annb_index_neighbor_graph)
+        self.neighbor_graph = self._index.neighbor_graph()
 
     def to_sparse_matrix(self):
         """The k-NN graph as a dictionary-of-keys sparse distance matrix (annchor/annchor.py:625-641):

@@ -1294,6 +1294,20 @@ static int hash_insert(annb_index *ix, const int32_t *I, const int32_t *J, const
 }
 
 namespace annb {
+// neighbour graph of a renumbered index back to the caller's numbering: rows and neighbour ids
+__global__ void unpermute_graph_kernel(const int64_t *__restrict__ idx, const double *__restrict__ dist, int64_t n,
+                                       int nn, const int32_t *__restrict__ order, int64_t *__restrict__ oidx,
+                                       double *__restrict__ odist)
+{
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n * nn; q += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = q / nn, col = q % nn;
+        const int64_t id = idx[q];
+        const int64_t o = (int64_t)order[row] * nn + col;
+        oidx[o] = id >= 0 ? order[id] : -1;
+        odist[o] = dist[q];
+    }
+}
+
 // per tile: min / max of every anchor's distance over the tile's (real) points, and the closest anchors present
 __global__ void __launch_bounds__(64)
 tile_bounds_kernel(const float *__restrict__ D32, const PointMeta *__restrict__ meta, int64_t n, int64_t npad, int na,
@@ -1448,10 +1462,10 @@ ANNB_API int annb_index_adopt_anchors(annb_index *ix, annb_index *src, const int
         o32[p] = (int32_t)order[p];
         inv[order[p]] = (int32_t)p;
     }
-    ANNB_TRY(ix->t0.ensure((size_t)n * 4));
-    ANNB_CUDA(cudaMemcpyAsync(ix->t0.p, o32.data(), (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+    ANNB_TRY(ix->order_dev.ensure((size_t)n * 4));
+    ANNB_CUDA(cudaMemcpyAsync(ix->order_dev.p, o32.data(), (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
     ANNB_LAUNCH(permute_D_kernel, grid_for_n(c, (int64_t)ix->na * n), 256, 0, c->stream, src->D64.as<double>(), n, ix->na,
-                ix->t0.as<int32_t>(), ix->D64.as<double>());
+                ix->order_dev.as<int32_t>(), ix->D64.as<double>());
     ix->A_host.clear();
     for (int32_t a : src->A_host) ix->A_host.push_back(inv[a]);
     if (!ix->A_host.empty())
@@ -1533,7 +1547,7 @@ ANNB_API int annb_index_destroy(annb_index *ix)
     if (!ix) return ANNB_OK;
     cudaSetDevice(ix->ctx->device);
     cudaStreamSynchronize(ix->ctx->stream);
-    DevBuf *all[] = {&ix->A_dev, &ix->D64, &ix->D32, &ix->Dpm, &ix->meta, &ix->scratch, &ix->htab, &ix->tl_ptr, &ix->tl_cnt, &ix->tl_code, &ix->tl_a, &ix->tl_b, &ix->scan_tmp, &ix->tb_lo, &ix->tb_hi, &ix->tb_cm,
+    DevBuf *all[] = {&ix->A_dev, &ix->D64, &ix->D32, &ix->Dpm, &ix->meta, &ix->scratch, &ix->htab, &ix->tl_ptr, &ix->tl_cnt, &ix->tl_code, &ix->tl_a, &ix->tl_b, &ix->scan_tmp, &ix->tb_lo, &ix->tb_hi, &ix->tb_cm, &ix->order_dev,
                      &ix->errs_dev, &ix->rank_dev, &ix->thresh, &ix->l2val, &ix->l2id, &ix->hist,
                      &ix->counters, &ix->emit_key, &ix->emit_lvl, &ix->sel_i, &ix->sel_j, &ix->nxt_i,
                      &ix->nxt_j, &ix->tiehist, &ix->tiekeys, &ix->pool_key, &ix->pool_dad, &ix->t0,
@@ -1994,8 +2008,22 @@ static int run_thresh(annb_index *ix, int k2)
         std::vector<int32_t> rbs;
         for (int t = 0; t < ix->T; ++t)
             if (bad[t]) rbs.push_back(t);
-        if (g_trace)
-            fprintf(stderr, "[annb-trace]   two-stage thresh: R %d, %zu of %d row blocks overflowed\n", R, rbs.size(), ix->T);
+        if (g_trace) {
+            std::vector<int32_t> srt(cnt_h);
+            std::sort(srt.begin(), srt.end());
+            int64_t over = 0, over_anchor = 0;
+            std::vector<char> is_a(n, 0);
+            for (int32_t a : ix->A_host) is_a[a] = 1;
+            for (int64_t i = 0; i < n; ++i)
+                if (cnt_h[i] > R) {
+                    ++over;
+                    over_anchor += is_a[i];
+                }
+            fprintf(stderr, "[annb-trace]   two-stage thresh: R %d, %zu of %d row blocks overflowed; records per row p50 %d p99 %d "
+                            "p99.9 %d max %d; %lld rows over R (%lld anchors)\n",
+                    R, rbs.size(), ix->T, srt[n / 2], srt[n * 99 / 100], srt[n * 999 / 1000], srt[n - 1], (long long)over,
+                    (long long)over_anchor);
+        }
         if (!rbs.empty()) {
             ANNB_TRY(ix->t3.ensure(rbs.size() * 4));
             ANNB_CUDA(cudaMemcpyAsync(ix->t3.p, rbs.data(), rbs.size() * 4, cudaMemcpyHostToDevice, c->stream));
@@ -2737,12 +2765,42 @@ ANNB_API int annb_index_neighbor_graph(annb_index *ix, int64_t *idx, double *dis
                 ix->A_dev.as<int32_t>(), (int)ix->A_host.size(), ix->kptr.as<int64_t>(),
                 ix->kids.as<int32_t>(), ix->kds.as<float>(), ix->t0.as<int64_t>(), ix->t1.as<double>(),
                 ix->counters.as<int32_t>());
-    ANNB_CUDA(cudaMemcpyAsync(idx, ix->t0.p, (size_t)n * nn * 8, cudaMemcpyDeviceToHost, c->stream));
-    ANNB_CUDA(cudaMemcpyAsync(dist, ix->t1.p, (size_t)n * nn * 8, cudaMemcpyDeviceToHost, c->stream));
     int32_t n_deficient = 0;
     ANNB_CUDA(cudaMemcpyAsync(&n_deficient, ix->counters.p, 4, cudaMemcpyDeviceToHost, c->stream));
     ANNB_CUDA(cudaStreamSynchronize(c->stream));
-    if (n_deficient == 0) return ANNB_OK;
+    // a renumbered index (annb_index_adopt_anchors) reports the graph in the caller's numbering
+    const int32_t *order = ix->ordered ? ix->order_dev.as<int32_t>() : nullptr;
+    if (n_deficient == 0 && order) {
+        ANNB_TRY(ix->t2.ensure((size_t)n * nn * 8));
+        ANNB_TRY(ix->t3.ensure((size_t)n * nn * 8));
+        ANNB_LAUNCH(unpermute_graph_kernel, grid_for_n(c, n * nn), 256, 0, c->stream, ix->t0.as<int64_t>(),
+                    ix->t1.as<double>(), n, nn, order, ix->t2.as<int64_t>(), ix->t3.as<double>());
+        ANNB_CUDA(cudaMemcpyAsync(idx, ix->t2.p, (size_t)n * nn * 8, cudaMemcpyDeviceToHost, c->stream));
+        ANNB_CUDA(cudaMemcpyAsync(dist, ix->t3.p, (size_t)n * nn * 8, cudaMemcpyDeviceToHost, c->stream));
+        ANNB_CUDA(cudaStreamSynchronize(c->stream));
+        return ANNB_OK;
+    }
+    ANNB_CUDA(cudaMemcpyAsync(idx, ix->t0.p, (size_t)n * nn * 8, cudaMemcpyDeviceToHost, c->stream));
+    ANNB_CUDA(cudaMemcpyAsync(dist, ix->t1.p, (size_t)n * nn * 8, cudaMemcpyDeviceToHost, c->stream));
+    ANNB_CUDA(cudaStreamSynchronize(c->stream));
+    // (rows that need the prediction fall-back are patched on the host in the index's numbering first)
+    auto to_caller = [&]() -> int {
+        if (!order) return ANNB_OK;
+        std::vector<int32_t> o(n);
+        ANNB_CUDA(cudaMemcpy(o.data(), order, (size_t)n * 4, cudaMemcpyDeviceToHost));
+        std::vector<int64_t> ti((size_t)n * nn);
+        std::vector<double> td((size_t)n * nn);
+        for (int64_t r = 0; r < n; ++r)
+            for (int q = 0; q < nn; ++q) {
+                const int64_t id = idx[r * nn + q];
+                ti[(size_t)o[r] * nn + q] = id >= 0 ? o[id] : -1;
+                td[(size_t)o[r] * nn + q] = dist[r * nn + q];
+            }
+        memcpy(idx, ti.data(), ti.size() * 8);
+        memcpy(dist, td.data(), td.size() * 8);
+        return ANNB_OK;
+    };
+    if (n_deficient == 0) return to_caller();
     // Rows with fewer than nn-1 computed pairs: the reference's get_nn ranks the not-computed
     // candidates behind the computed ones by their RefineApprox (d[ncm] += max(d), utils.py:415-428)
     // and emits the prediction.  Same here: the row sweep's second list gives, for the affected row
@@ -2782,7 +2840,7 @@ ANNB_API int annb_index_neighbor_graph(annb_index *ix, int64_t *idx, double *dis
             ++col;
         }
     }
-    return ANNB_OK;
+    return to_caller();
 }
 
 ANNB_API int annb_index_stats(annb_index *ix, int64_t *out, int64_t m)

@@ -27,7 +27,7 @@ struct annb_index {
     // per-tile entry lists derived from the hash map (rebuilt lazily before a sweep)
     DevBuf tl_ptr, tl_cnt, tl_code, tl_a, tl_b, scan_tmp;
     // per-tile anchor-distance intervals and closest-anchor sets (tile-level pruning in the sweeps)
-    DevBuf tb_lo, tb_hi, tb_cm;
+    DevBuf tb_lo, tb_hi, tb_cm, order_dev;  // order_dev[new] = old id (int32) when the index is renumbered
     bool ordered = false;  // the points were renumbered by annb_index_spatial_order (coherent tiles)
     bool tl_dirty = false;
     int64_t tl_entries = 0;
