@@ -394,6 +394,7 @@ ANNB_API int annb_dataset_gather(annb_ctx *c, const annb_dataset *ds, const int6
     ANNB_CUDA(cudaMemcpyAsync(c->s_in[1].p, order, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
     annb_dataset *g = new annb_dataset(*ds);
     g->ctx = c;
+    g->pooled_cap = 0;
     g->n = n;
     g->data = nullptr;
     g->offs = nullptr;
@@ -420,7 +421,12 @@ ANNB_API int annb_dataset_gather(annb_ctx *c, const annb_dataset *ds, const int6
         const size_t es = ds->dtype == ANNB_F32 ? 4 : 8;
         const size_t row_bytes = (size_t)ds->ld * es;
         ANNB_REQUIRE(row_bytes % 8 == 0, ANNB_ESTATE, "row pitch is not a multiple of 8 bytes");
-        ANNB_CUDA(cudaMalloc(&g->data, (size_t)n * row_bytes));
+        {   // through the pool: a fit() per step gathers the data set anew, cudaMalloc / cudaFree would cost ms each
+            DevBuf b;
+            ANNB_TRY(b.ensure((size_t)n * row_bytes));
+            g->data = b.p;
+            g->pooled_cap = b.cap;
+        }
         ANNB_LAUNCH(gather_rows_kernel, grid, 256, 0, c->stream, (const uint2 *)ds->data, (int64_t)(row_bytes / 8),
                     c->s_in[1].as<int64_t>(), n, (uint2 *)g->data);
         ANNB_CUDA(cudaStreamSynchronize(c->stream));
@@ -433,7 +439,10 @@ ANNB_API int annb_dataset_free(annb_dataset *ds)
 {
     if (!ds) return ANNB_OK;
     cudaSetDevice(ds->ctx->device);
-    if (ds->data) cudaFree(ds->data);
+    if (ds->data) {
+        if (ds->pooled_cap) pool_give(ds->data, ds->pooled_cap);
+        else cudaFree(ds->data);
+    }
     if (ds->offs) cudaFree(ds->offs);
     if (ds->lens) cudaFree(ds->lens);
     delete ds;

@@ -1949,7 +1949,10 @@ static int run_thresh(annb_index *ix, int k2)
         // record slots per point: ~S*(k1+k2) expected (the k-th smallest of 1/S of the columns is about
         // the S*k-th smallest overall), x2 (x4 without the second list) for the spread
         static const int R_env = getenv("ANNB_THRESH_RECORDS") ? atoi(getenv("ANNB_THRESH_RECORDS")) : 0;
-        const int R = R_env > 0 ? R_env : ((k2 > 0 ? 2 : 4) * S * (k1 + k2) + 31) / 32 * 32;
+        int R = R_env > 0 ? R_env : ((k2 > 0 ? 2 : 4) * S * (k1 + k2) + 31) / 32 * 32;
+        // spatially ordered points: the typical row needs far fewer records (its neighbours are in the band
+        // of the pre-pass), but the 0.1 % of rows whose blob is spread over several tiles need more
+        if (ix->ordered && R_env <= 0) R = std::max(R, 1024);
         ANNB_TRY(ix->trec.ensure((size_t)n * R * 8));
         ANNB_TRY(ix->tcnt.ensure((size_t)n * 4));
         ANNB_CUDA(cudaMemsetAsync(ix->tcnt.p, 0, (size_t)n * 4, c->stream));

@@ -71,7 +71,7 @@ struct View {
     const float *tl_a, *tl_b;  // KNOWN: a = distance; TIGHT: (a, b) = (lb, ub)
     // per-tile bounds: [T][kMaxAnchors] min / max anchor distance over the tile's points, and the set of
     // closest anchors that occur in the tile -- a sweep skips a tile pair when they prove that no pair of
-    // it can pass the phase-1 test (sweep.cuh: tile_pred_min)
+    // it can pass the phase-1 test (sweep.cuh: tile_can_pass)
     const float *tb_lo, *tb_hi;
     const uint64_t *tb_cm;
     int cull;

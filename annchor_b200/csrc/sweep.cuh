@@ -420,7 +420,13 @@ __device__ __forceinline__ void tile_from_index(int64_t t, int T, int &ti, int &
 // then clipped.  Floating-point subtraction, addition, fma, min and max are monotone, so the result is
 // a true lower bound of what predict_clip2 returns for any pair of the two tiles -- no tolerance needed.
 // Every warp computes it redundantly (lanes over anchors, ~150 instructions per tile).
-__device__ __forceinline__ float tile_pred_min(const View &V, const Model &M, int ti, int tj)
+// Can any pair of tiles (ti, tj) pass the phase-1 test?  MODE 0 (scoring): cut - pred > margin[label];
+// MODE 1 (pair thresholds): pred <= cut; MODE 2 (row thresholds): pred < cut -- with cut <= cutmax and
+// pred >= the bound below.  The bound and the margin are taken per regression bin the tile pair's s2
+// interval overlaps (the error label of a pair is its bin b, or b + 1 when s2 sits exactly on the edge).
+template <int MODE>
+__device__ __forceinline__ bool tile_can_pass(const View &V, const Model &M, int ti, int tj, float cutmax,
+                                              const float *margin /* [MAX_BINS], MODE 0 */)
 {
     const int lane = threadIdx.x & 31;
     const float *loI = V.tb_lo + (int64_t)ti * kMaxAnchors, *hiI = V.tb_hi + (int64_t)ti * kMaxAnchors;
@@ -459,7 +465,7 @@ __device__ __forceinline__ float tile_pred_min(const View &V, const Model &M, in
         sjHi = fmaxf(sjHi, __shfl_xor_sync(0xffffffffu, sjHi, o));
     }
     const float s_lo = siLo + sjLo, s_hi = siHi + sjHi;
-    float ymin = INFINITY;
+    bool any = false;
     for (int b = 0; b < M.nb; ++b) {
         // bin b holds e2[b] < s2 <= e2[b+1]  (e2[0] = -inf, e2[nb] = +inf; reg_bin2)
         const float blo = b == 0 ? -INFINITY : M.e2[b], bhi = b + 1 < M.nb ? M.e2[b + 1] : INFINITY;
@@ -467,9 +473,17 @@ __device__ __forceinline__ float tile_pred_min(const View &V, const Model &M, in
         const float c0 = M.c0[b], c1 = M.c1[b], cz = 0.5f * M.c2[b];
         const float y = fmaf(c0 >= 0.0f ? lbmin : lbmax, c0,
                              fmaf(c1 >= 0.0f ? ubmin : ubmax, c1, fmaf(cz >= 0.0f ? s_lo : s_hi, cz, M.ic[b])));
-        ymin = fminf(ymin, y);
+        const float p = fminf(fmaxf(y, lbmin), ubmin);  // lower bound of the clipped prediction in this bin
+        if (MODE == 0) {
+            const float mg = fminf(margin[b], margin[b + 1 < M.nb ? b + 1 : b]);
+            any |= !(cutmax - p <= mg);  // (NaN counts as "can pass")
+        } else if (MODE == 1) {
+            any |= !(p > cutmax);
+        } else {
+            any |= !(p >= cutmax);
+        }
     }
-    return fminf(fmaxf(ymin, lbmin), ubmin);
+    return any;
 }
 
 // largest of 128 shared-memory values (every warp computes it)

@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(SWT, 1) score_sweep_kernel(const __grid_consta
         // `cut - pred > margin` phase 1 applies per pair, at the tile's extremes)
         if (V.cull && A.ef_min > -INFINITY && sDesc[(m - m0) & 3].end == sDesc[(m - m0) & 3].base && ti != tj) {
             const float cutmax = fmaxf(tile_max128(tI), tile_max128(tJ));
-            if (!(cutmax - tile_pred_min(V, M, ti, tj) > A.ef_min)) {
+            if (!tile_can_pass<0>(V, M, ti, tj, cutmax, A.efloor)) {
                 n_culled += 1;
                 continue;
             }

@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(SWT, 1) thresh_sweep_kernel(const __grid_const
             // tile-level pruning (metrics only: the phase-1 filter `pred < cut[row]` is on): no store entry
             // and the smallest possible prediction is not below the largest current cut of the 128 rows
             if (V.cull && filter && sDesc[step_no & 3].end == sDesc[step_no & 3].base && tc != rb) {
-                if (tile_pred_min(V, M, rb, tc) >= tile_max128(cut)) continue;
+                if (!tile_can_pass<2>(V, M, rb, tc, tile_max128(cut), nullptr)) continue;
             }
             build_tile_store(V, ts, &sDesc[step_no & 3], sCode + par * TL_CAP, sBF, tc < rb ? 1 : (tc == rb ? 2 : 3));
             // ---- phase 1: bounds + clipped prediction, two passes of 4 x 8 pairs per thread ----
@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(SWT, 1) thresh_pairs_kernel(const __grid_const
         // exceeds every cut of the two tiles (phase 1 keeps a pair iff pred <= max(cut_i, cut_j))
         if (V.cull && V.is_metric && sDesc[(m - m0) & 3].end == sDesc[(m - m0) & 3].base && ti != tj) {
             const float cutmax = fmaxf(fmaxf(tile_max128(k1I), tile_max128(k2I)), fmaxf(tile_max128(k1J), tile_max128(k2J)));
-            if (tile_pred_min(V, M, ti, tj) > cutmax) continue;
+            if (!tile_can_pass<1>(V, M, ti, tj, cutmax, nullptr)) continue;
         }
         build_tile_store(V, ts, &sDesc[(m - m0) & 3], sCode + buf * TL_CAP, sBm, 0);
         const uint32_t *bm = sBm;
