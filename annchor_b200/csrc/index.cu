@@ -2220,7 +2220,8 @@ static int run_score(annb_index *ix, int floor_level, uint64_t floor_mix_thr, in
     ANNB_TRY(ix->reduce(hist.data(), (int64_t)hist.size(), ANNB_RED_U64));  // global level counts
     float ms = 0;
     ANNB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-    const int64_t pairs = ix->n * (ix->n - 1) / 2 / ix->P.world / stride;
+    // pairs whose bounds / prediction were actually computed (tiles skipped by the tile-level test excluded)
+    const int64_t pairs = (int64_t)cnt[2];
     if (stride == 1) {  // accumulated over the full scoring sweeps of this index (bench.py: roofline)
         ix->last_sweep_ms += ms;
         ix->last_sweep_pairs += pairs;

@@ -36,8 +36,11 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = dict(name="euclidean_f32_blobs", N=100_000, d=128, centers=100, seed=42, n_anchors=30,
-                n_neighbors=15, n_samples=5000, p_work=0.01, niters=2)
+# BASELINE.json's metric is quoted on N=1M, d=128, k=15 (north star; SURVEY.md 8d: p_work=1e-3, n_anchors=30);
+# it fits one B200 since round 2.  configs[1] (N=100k, p_work=0.01) is timed as a secondary leg.
+WORKLOAD = dict(name="euclidean_f32_blobs", N=1_000_000, d=128, centers=100, seed=42, n_anchors=30,
+                n_neighbors=15, n_samples=5000, p_work=0.001, niters=2)
+CONFIG1 = dict(WORKLOAD, N=100_000, p_work=0.01)
 ALG_BYTES_PER_PAIR = 25.0  # K2+K3(+score) fused, materialised-equivalent
 
 
@@ -151,13 +154,41 @@ def run_reference(args, w):
 
 
 def config_dict(w, gpus):
+    which = ("BASELINE metric config / north star" if w["N"] == 1_000_000 else
+             "BASELINE configs[1]" if w["N"] == 100_000 else "size override")
     return {"workload": "Euclidean float32 N=%d d=%d k=%d n_anchors=%d n_samples=%d p_work=%g niters=%d, "
-                        "100-centre Gaussian blobs (BASELINE configs[1])"
+                        "100-centre Gaussian blobs (%s)"
                         % (w["N"], w["d"], w["n_neighbors"], w["n_anchors"], w["n_samples"], w["p_work"],
-                           w["niters"]),
+                           w["niters"], which),
             "N": w["N"], "d": w["d"], "k": w["n_neighbors"], "n_anchors": w["n_anchors"],
             "p_work": w["p_work"], "parallelism": "1 process per GPU, tiles sharded across %d rank(s)" % gpus,
             "l2": "256 MiB scratch buffer written between timed steps (L2 flush)"}
+
+
+def config1_leg(ab, Annchor, ctx):
+    """BASELINE configs[1] (N=100k, p_work=0.01), the round-1 bench workload, for continuity."""
+    w = CONFIG1
+    X = make_blobs(w["N"], w["d"], w["centers"], w["seed"])
+    ds = ab.Dataset(ctx, X, "euclidean")
+    kw = dict(n_anchors=w["n_anchors"], n_neighbors=w["n_neighbors"], n_samples=w["n_samples"],
+              p_work=w["p_work"], niters=w["niters"])
+    ms, ann = [], None
+    for it in range(5):
+        if ann is not None:
+            ann._index.close()
+        ann = Annchor(X, "euclidean", ctx=ctx, _dataset=ds, **kw)
+        ctx.timer_start()
+        ann.fit()
+        t = ctx.timer_stop()
+        if it >= 2:
+            ms.append(t)
+    rec = recall_at_k(ds, ann.neighbor_graph, w["n_neighbors"])
+    out = {"N": w["N"], "p_work": w["p_work"], "ms_per_fit": float(np.mean(ms)),
+           "points_per_s": w["N"] / (float(np.mean(ms)) * 1e-3), "evals": int(ann.evals), "recall_at_k": rec,
+           "note": "device-timed fit() with X resident, mean of 3 after 2 warm-ups"}
+    ann._index.close()
+    ds.close()
+    return out
 
 
 def same_n_leg(ab, Annchor, ctx, w, n_s=N_SAMPLE):
@@ -310,7 +341,8 @@ def run_ours(args, w):
     ops_per_pair = 3.0 * w["n_anchors"] + 25.0
     issue_peak = 148 * 128 * sm_clk / 1e12          # T lane-op/s (4 warp instructions / clk / SM)
     issue_achieved = ops_per_pair * sw_pairs / (sw_ms * 1e-3) / 1e12
-    same_n = same_n_leg(ab, Annchor, ctx, w)
+    same_n = same_n_leg(ab, Annchor, ctx, w) if world == 1 else None
+    cfg1 = config1_leg(ab, Annchor, ctx) if (world == 1 and w["N"] != CONFIG1["N"]) else None
     t_rec = time.time()
     rec = recall_at_k(ds, last_graph, w["n_neighbors"])
     t_rec = time.time() - t_rec
@@ -340,7 +372,7 @@ def run_ours(args, w):
                                         "note": "SURVEY 8(d)'s materialised-equivalent figure: what a reference-"
                                                 "shaped K2+K3 pass would have to move; the streaming sweep stores "
                                                 "nothing per pair (see traffic), so this is NOT its bound"}},
-        "same_n_leg": same_n,
+        "same_n_leg": same_n, "configs1_leg": cfg1,
         "recall_at_k": rec, "recall_source": "all %d rows vs device BruteForce (%.2f s)" % (w["N"], t_rec),
         "evals": int(last_evals), "stage_seconds": last_stage,
         "index_stats": last_stats,
@@ -368,7 +400,17 @@ def main():
     if args.impl == "reference":
         run_reference(args, w)
     else:
-        run_ours(args, w)
+        try:
+            run_ours(args, w)
+        except Exception as e:  # noqa: BLE001
+            # the default workload needs ~90 GB of HBM; if this GPU cannot hold it, measure configs[1] and
+            # say so in `config.workload` rather than produce no line at all
+            if int(os.environ.get("WORLD_SIZE", "1")) != 1 or w["N"] <= CONFIG1["N"]:
+                raise
+            sys.stderr.write("[bench] N=%d failed (%r); falling back to BASELINE configs[1]\n" % (w["N"], e))
+            import annchor_b200 as ab
+            ab.load_library().annb_pool_trim()
+            run_ours(args, dict(CONFIG1))
         try:
             import torch.distributed as dist
             if dist.is_initialized():
