@@ -2952,7 +2952,10 @@ ANNB_API int annb_index_sample_pool_bins(annb_index *ix, uint64_t seed, const do
     // that the sweep's cost follows the largest rate instead of being a full pass over all pairs
     double rmax = 0.0;
     for (int b = 0; b < nb; ++b) rmax = std::max(rmax, rate[b]);
-    const double tile_frac = std::min(1.0, std::max(1.0 / 64.0, 8.0 * rmax));
+    // ... and at most ~10^6 tiles are visited (bounded cost at N = 1M, where a full pass is 3*10^7 tiles):
+    // a very rare bin then gets fewer pairs than asked for, still far more than the uniform pool held
+    double tile_frac = std::min(1.0, std::max(1.0 / 64.0, 8.0 * rmax));
+    tile_frac = std::min(tile_frac, std::max(1.0 / 64.0, 1.0e6 / (double)ix->NT));
     A.tile_thr = tile_frac >= 1.0 ? 0xffffffffu : (uint32_t)(tile_frac * 4294967295.0);
     A.thr = 0;
     for (int b = 0; b < MAX_BINS; ++b) {
