@@ -8,7 +8,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get("ANNB_LIBRARY") or os.path.join(_HERE, "libannb.so")  # ANNB_LIBRARY: A/B builds
 
-EUCLIDEAN, COSINE, LEVENSHTEIN, WASSERSTEIN1D = 0, 1, 2, 3
+EUCLIDEAN, COSINE, LEVENSHTEIN, WASSERSTEIN1D, WASSERSTEIN = 0, 1, 2, 3, 4
 F32, F64, U8 = 0, 1, 2
 METRIC_IDS = {"euclidean": EUCLIDEAN, "cosine": COSINE, "levenshtein": LEVENSHTEIN,
               "wasserstein": WASSERSTEIN1D, "wasserstein1d": WASSERSTEIN1D}
@@ -41,6 +41,7 @@ _SIGS = {
     "annb_dataset_dense": [_P, _P, _I64, _I64, _I32, _I32, _PP],
     "annb_dataset_strings": [_P, _P, _P, _I64, _PP],
     "annb_dataset_hist": [_P, _P, _I64, _I64, _I32, _PP],
+    "annb_dataset_hist_cost": [_P, _P, _I64, _I64, _I32, _P, _PP],
     "annb_dataset_gather": [_P, _P, _P, _I64, _PP],
     "annb_dataset_free": [_P],
     "annb_pair_dists": [_P, _P, _I32, _P, _I64, _P],

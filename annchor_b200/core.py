@@ -98,26 +98,34 @@ class Dataset:
             check(L.annb_dataset_strings(ctx.handle, ptr(chars), ptr(offs), len(offs) - 1,
                                          C.byref(h)))
             self.n = len(offs) - 1
-        elif self.metric == _lib.WASSERSTEIN1D:
+        elif self.metric in (_lib.WASSERSTEIN1D, _lib.WASSERSTEIN):
             X = np.asarray(X)
             if X.ndim != 2:
                 raise ValueError("wasserstein needs a 2-D array of histograms")
+            nb = X.shape[1]
+            M = None
             if cost_matrix is not None:
-                M = np.asarray(cost_matrix, dtype=np.float64)
-                nb = X.shape[1]
+                M = as_c(np.asarray(cost_matrix, dtype=np.float64), np.float64)
+                if M.shape != (nb, nb):
+                    raise ValueError("cost_matrix must be (%d, %d), got %r" % (nb, nb, M.shape))
                 ref = np.abs(np.arange(nb)[:, None] - np.arange(nb)[None, :])
-                if M.shape != (nb, nb) or not np.array_equal(M, ref):
-                    raise NotImplementedError(
-                        "device 'wasserstein' implements the 1-D ground cost |a-b| only "
-                        "(annchor/utils.py:75-86 with a general cost matrix is exact OT by network "
-                        "simplex, which is not on the device path); no CPU fallback is provided")
+                if np.array_equal(M, ref):
+                    M = None  # the 1-D ground cost |a-b|: closed form sum |CDF_x - CDF_y| (w1_pair_kernel)
+            elif self.metric == _lib.WASSERSTEIN:
+                raise ValueError("the general Wasserstein metric needs a cost_matrix")
             if X.dtype == np.uint8:
                 Xc, dt = as_c(X, np.uint8), _lib.U8
             elif X.dtype == np.float32:
                 Xc, dt = as_c(X, np.float32), _lib.F32
             else:
                 Xc, dt = as_c(X, np.float64), _lib.F64
-            check(L.annb_dataset_hist(ctx.handle, ptr(Xc), Xc.shape[0], Xc.shape[1], dt, C.byref(h)))
+            if M is None:
+                self.metric = _lib.WASSERSTEIN1D
+                check(L.annb_dataset_hist(ctx.handle, ptr(Xc), Xc.shape[0], nb, dt, C.byref(h)))
+            else:
+                # general ground cost: exact optimal transport per pair on the device (ot_pair_kernel), <= 64 bins
+                self.metric = _lib.WASSERSTEIN
+                check(L.annb_dataset_hist_cost(ctx.handle, ptr(Xc), Xc.shape[0], nb, dt, ptr(M), C.byref(h)))
             self.n = Xc.shape[0]
         else:
             raise ValueError("unknown metric %r" % (metric,))

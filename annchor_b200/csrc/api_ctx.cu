@@ -96,8 +96,12 @@ int check_metric(const annb_dataset *ds, int metric)
                      "levenshtein needs a strings dataset");
         break;
     case ANNB_WASSERSTEIN1D:
-        ANNB_REQUIRE(ds->kind == ANNB_DS_HIST, ANNB_EINVAL,
-                     "wasserstein1d needs a histogram dataset");
+        ANNB_REQUIRE(ds->kind == ANNB_DS_HIST && ds->cost == nullptr, ANNB_EINVAL,
+                     "wasserstein1d needs a histogram dataset (annb_dataset_hist)");
+        break;
+    case ANNB_WASSERSTEIN:
+        ANNB_REQUIRE(ds->kind == ANNB_DS_HIST && ds->cost != nullptr, ANNB_EINVAL,
+                     "wasserstein needs a histogram dataset with a cost matrix (annb_dataset_hist_cost)");
         break;
     default:
         set_error("unknown metric id %d", metric);
@@ -347,6 +351,59 @@ ANNB_API int annb_dataset_hist(annb_ctx *c, const void *H, int64_t n, int64_t nb
 }
 
 namespace annb {
+// histogram rows -> unit masses (annchor/utils.py:82-84), one thread per row, sums in bin order
+template <typename T>
+__global__ void hist_to_mass_kernel(const T *__restrict__ H, int64_t n, int64_t nb, double *__restrict__ mass)
+{
+    int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const T *h = H + r * nb;
+    double s = 0.0;
+    for (int64_t k = 0; k < nb; ++k) s += (double)h[k];
+    for (int64_t k = 0; k < nb; ++k) mass[r * nb + k] = (double)h[k] / s;
+}
+}  // namespace annb
+
+ANNB_API int annb_dataset_hist_cost(annb_ctx *c, const void *H, int64_t n, int64_t nb, int dtype,
+                                    const double *cost, annb_dataset **out)
+{
+    ANNB_REQUIRE(c && H && cost && out, ANNB_EINVAL, "NULL argument");
+    ANNB_REQUIRE(n > 0 && nb > 0 && n < (1ll << 31), ANNB_EINVAL, "bad shape");
+    ANNB_REQUIRE(nb <= 64, ANNB_ERANGE, "the general-cost Wasserstein kernel supports at most 64 bins (got %lld)",
+                 (long long)nb);
+    for (int64_t q = 0; q < nb * nb; ++q)
+        ANNB_REQUIRE(cost[q] >= 0.0 && cost[q] < INFINITY, ANNB_EINVAL, "cost matrix entries must be finite and >= 0");
+    ANNB_CUDA(cudaSetDevice(c->device));
+    size_t es = dtype == ANNB_F32 ? 4 : dtype == ANNB_F64 ? 8 : dtype == ANNB_U8 ? 1 : 0;
+    ANNB_REQUIRE(es != 0, ANNB_EINVAL, "hist dtype must be F32/F64/U8");
+    annb_dataset *ds = new annb_dataset();
+    ds->ctx = c;
+    ds->kind = ANNB_DS_HIST;
+    ds->dtype = ANNB_F64;
+    ds->n = n;
+    ds->d = nb;
+    ds->ld = nb;
+    ANNB_CUDA(cudaMalloc(&ds->data, (size_t)n * nb * sizeof(double)));
+    ANNB_CUDA(cudaMalloc((void **)&ds->cost, (size_t)nb * nb * sizeof(double)));
+    ANNB_CUDA(cudaMemcpyAsync(ds->cost, cost, (size_t)nb * nb * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    ANNB_TRY(c->s_in[0].ensure((size_t)n * nb * es));
+    ANNB_CUDA(cudaMemcpyAsync(c->s_in[0].p, H, (size_t)n * nb * es, cudaMemcpyHostToDevice, c->stream));
+    int grid = (int)((n + 127) / 128);
+    if (dtype == ANNB_F32)
+        ANNB_LAUNCH(hist_to_mass_kernel<float>, grid, 128, 0, c->stream, c->s_in[0].as<float>(), n, nb,
+                    (double *)ds->data);
+    else if (dtype == ANNB_F64)
+        ANNB_LAUNCH(hist_to_mass_kernel<double>, grid, 128, 0, c->stream, c->s_in[0].as<double>(), n, nb,
+                    (double *)ds->data);
+    else
+        ANNB_LAUNCH(hist_to_mass_kernel<uint8_t>, grid, 128, 0, c->stream, c->s_in[0].as<uint8_t>(), n, nb,
+                    (double *)ds->data);
+    ANNB_CUDA(cudaStreamSynchronize(c->stream));
+    *out = ds;
+    return ANNB_OK;
+}
+
+namespace annb {
 // out row q = in row order[q]; rows are row_vec 8-byte words long, one warp per row
 __global__ void gather_rows_kernel(const uint2 *__restrict__ src, int64_t row_vec, const int64_t *__restrict__ order,
                                    int64_t n, uint2 *__restrict__ dst)
@@ -399,6 +456,11 @@ ANNB_API int annb_dataset_gather(annb_ctx *c, const annb_dataset *ds, const int6
     g->data = nullptr;
     g->offs = nullptr;
     g->lens = nullptr;
+    g->cost = nullptr;
+    if (ds->cost) {  // the copy owns its cost matrix
+        ANNB_CUDA(cudaMalloc((void **)&g->cost, (size_t)ds->d * ds->d * 8));
+        ANNB_CUDA(cudaMemcpyAsync(g->cost, ds->cost, (size_t)ds->d * ds->d * 8, cudaMemcpyDeviceToDevice, c->stream));
+    }
     const int grid = c->num_sms * 8;
     if (ds->kind == ANNB_DS_STRINGS) {
         std::vector<int32_t> lens(ds->n);
@@ -445,6 +507,7 @@ ANNB_API int annb_dataset_free(annb_dataset *ds)
     }
     if (ds->offs) cudaFree(ds->offs);
     if (ds->lens) cudaFree(ds->lens);
+    if (ds->cost) cudaFree(ds->cost);
     delete ds;
     return ANNB_OK;
 }

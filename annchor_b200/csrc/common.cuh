@@ -149,6 +149,7 @@ struct annb_dataset {
     int32_t *lens = nullptr;  // strings: device length per string
     int sigma = 0;            // strings: alphabet size after remap
     int64_t max_len = 0;
+    double *cost = nullptr;   // hist, general Wasserstein: (d, d) ground-cost matrix; `data` then holds unit masses
     size_t pooled_cap = 0;    // > 0: `data` came from the device-buffer pool (annb_dataset_gather) and returns to it
 };
 

@@ -172,6 +172,198 @@ w1_pair_kernel(const double *__restrict__ C, int64_t nb, const int32_t *__restri
 }
 
 // ---------------------------------------------------------------------------------
+// General cost-matrix Wasserstein (annchor/utils.py:75-86: kantorovich(x, y, cost=M) of pynndescent
+// 0.5.13 -- zero bins dropped, both histograms normalised to unit mass, exact optimal transport).
+// One warp per pair solves the transportation problem exactly by successive shortest augmenting
+// paths with node potentials (multi-source Dijkstra on the dense residual graph, reduced costs >= 0):
+// every augmentation exhausts a supply, a demand or a flow arc.  Supports up to 64 bins (the
+// reference's 8 x 8 digits); flows, potentials and distances are float64 in shared memory.
+// ---------------------------------------------------------------------------------
+constexpr int OT_B = 64;
+struct OtWarp {
+    double f[OT_B * OT_B];  // flow on (source k, sink l), row pitch = n
+    double ds[OT_B], dt[OT_B], ps[OT_B], pt[OT_B], ra[OT_B], rb[OT_B];
+    int16_t si[OT_B], tj[OT_B], prev_s[OT_B], prev_t[OT_B];
+    uint8_t vis_s[OT_B], vis_t[OT_B];
+};
+
+__device__ __forceinline__ double shfl_xor_f64(double v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
+
+// mass: unit-sum histograms (n_items, nb); cost: (nb, nb) row-major; returns the optimal transport cost
+__device__ double ot_solve(OtWarp &W, const double *__restrict__ sC /* shared, nb x nb */, int nb,
+                           const double *__restrict__ x, const double *__restrict__ y, int lane)
+{
+    constexpr double EPS = 1e-13, TINY = 1e-15;
+    // 1. compress the supports
+    int m = 0, n = 0;
+    for (int b0 = 0; b0 < nb; b0 += 32) {
+        const int b = b0 + lane;
+        const double xv = b < nb ? x[b] : 0.0, yv = b < nb ? y[b] : 0.0;
+        const unsigned mx = __ballot_sync(0xffffffffu, xv > 0.0), my = __ballot_sync(0xffffffffu, yv > 0.0);
+        if (xv > 0.0) {
+            const int k = m + __popc(mx & ((1u << lane) - 1));
+            W.si[k] = (int16_t)b;
+            W.ra[k] = xv;
+        }
+        if (yv > 0.0) {
+            const int l = n + __popc(my & ((1u << lane) - 1));
+            W.tj[l] = (int16_t)b;
+            W.rb[l] = yv;
+        }
+        m += __popc(mx);
+        n += __popc(my);
+    }
+    __syncwarp();
+    if (m == 0 || n == 0) return 0.0;
+    for (int q = lane; q < m * n; q += 32) W.f[q] = 0.0;
+    for (int k = lane; k < m; k += 32) W.ps[k] = 0.0;
+    for (int l = lane; l < n; l += 32) {
+        double mn = INFINITY;
+        for (int k = 0; k < m; ++k) mn = fmin(mn, sC[W.si[k] * nb + W.tj[l]]);
+        W.pt[l] = mn;  // reduced cost C + ps - pt >= 0 on every forward arc
+    }
+    __syncwarp();
+    // 2. augment until all supply is shipped
+    for (int round = 0; round < 8 * (m + n) + 32; ++round) {
+        double rem = 0.0;
+        for (int k = lane; k < m; k += 32) rem += W.ra[k] > EPS ? W.ra[k] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) rem += shfl_xor_f64(rem, o);
+        if (!(rem > EPS)) break;
+        for (int k = lane; k < m; k += 32) {
+            W.ds[k] = W.ra[k] > EPS ? 0.0 : INFINITY;
+            W.prev_s[k] = -1;
+            W.vis_s[k] = 0;
+        }
+        for (int l = lane; l < n; l += 32) {
+            W.dt[l] = INFINITY;
+            W.prev_t[l] = -1;
+            W.vis_t[l] = 0;
+        }
+        __syncwarp();
+        int target = -1;
+        double dtar = INFINITY;
+        for (int it = 0; it < m + n; ++it) {
+            // closest unvisited node (sources: id k, sinks: id 64 + l)
+            double bv = INFINITY;
+            int bid = 1 << 20;
+            for (int k = lane; k < m; k += 32)
+                if (!W.vis_s[k] && W.ds[k] < bv) {
+                    bv = W.ds[k];
+                    bid = k;
+                }
+            for (int l = lane; l < n; l += 32)
+                if (!W.vis_t[l] && (W.dt[l] < bv)) {
+                    bv = W.dt[l];
+                    bid = OT_B + l;
+                }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = shfl_xor_f64(bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bid, o);
+                if (ov < bv || (ov == bv && oi < bid)) {
+                    bv = ov;
+                    bid = oi;
+                }
+            }
+            if (!(bv < INFINITY)) break;
+            if (bid >= OT_B) {
+                const int l = bid - OT_B;
+                if (lane == 0) W.vis_t[l] = 1;
+                if (W.rb[l] > EPS) {
+                    target = l;
+                    dtar = bv;
+                    break;
+                }
+                // backward arcs l -> k where flow can be withdrawn: cost -C, reduced -C + pt - ps
+                for (int k = lane; k < m; k += 32)
+                    if (!W.vis_s[k] && W.f[k * n + l] > TINY) {
+                        const double rc = fmax(W.pt[l] - W.ps[k] - sC[W.si[k] * nb + W.tj[l]], 0.0);
+                        if (bv + rc < W.ds[k]) {
+                            W.ds[k] = bv + rc;
+                            W.prev_s[k] = (int16_t)l;
+                        }
+                    }
+            } else {
+                const int k = bid;
+                if (lane == 0) W.vis_s[k] = 1;
+                for (int l = lane; l < n; l += 32)
+                    if (!W.vis_t[l]) {
+                        const double rc = fmax(sC[W.si[k] * nb + W.tj[l]] + W.ps[k] - W.pt[l], 0.0);
+                        if (bv + rc < W.dt[l]) {
+                            W.dt[l] = bv + rc;
+                            W.prev_t[l] = (int16_t)k;
+                        }
+                    }
+            }
+            __syncwarp();
+        }
+        __syncwarp();
+        if (target < 0) break;  // (cannot happen with positive remaining supply and demand)
+        // potentials: visited nodes move by their distance, the others by the target's
+        for (int k = lane; k < m; k += 32) W.ps[k] += W.vis_s[k] ? W.ds[k] : dtar;
+        for (int l = lane; l < n; l += 32) W.pt[l] += W.vis_t[l] ? W.dt[l] : dtar;
+        __syncwarp();
+        if (lane == 0) {
+            // bottleneck along target -> ... -> root (a source with remaining supply)
+            double amount = W.rb[target];
+            int l = target, k;
+            for (;;) {
+                k = W.prev_t[l];
+                if (W.prev_s[k] < 0) break;
+                const int l2 = W.prev_s[k];
+                amount = fmin(amount, W.f[k * n + l2]);
+                l = l2;
+            }
+            amount = fmin(amount, W.ra[k]);
+            const int root = k;
+            l = target;
+            for (;;) {
+                k = W.prev_t[l];
+                W.f[k * n + l] += amount;
+                if (W.prev_s[k] < 0) break;
+                const int l2 = W.prev_s[k];
+                const double r = W.f[k * n + l2] - amount;
+                W.f[k * n + l2] = r > TINY ? r : 0.0;
+                l = l2;
+            }
+            W.ra[root] -= amount;
+            W.rb[target] -= amount;
+        }
+        __syncwarp();
+    }
+    double cost = 0.0;
+    for (int q = lane; q < m * n; q += 32) cost += W.f[q] * sC[W.si[q / n] * nb + W.tj[q % n]];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cost += shfl_xor_f64(cost, o);
+    return cost;
+}
+
+constexpr int OT_WARPS = 4;
+template <typename OutT>
+__global__ void __launch_bounds__(OT_WARPS * 32)
+ot_pair_kernel(const double *__restrict__ mass, int nb, const double *__restrict__ cost,
+               const int32_t *__restrict__ I, const int32_t *__restrict__ J, const int32_t *__restrict__ anchor,
+               const int32_t *__restrict__ perm, int64_t n, OutT *__restrict__ out)
+{
+    extern __shared__ __align__(16) unsigned char ot_smem[];
+    double *sC = reinterpret_cast<double *>(ot_smem);
+    OtWarp *ws = reinterpret_cast<OtWarp *>(sC + OT_B * OT_B);
+    for (int q = threadIdx.x; q < nb * nb; q += blockDim.x) sC[q] = cost[q];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    OtWarp &W = ws[wib];
+    const int64_t warp = (int64_t)blockIdx.x * OT_WARPS + wib, nwarps = (int64_t)gridDim.x * OT_WARPS;
+    for (int64_t q = warp; q < n; q += nwarps) {
+        const int64_t p = perm ? (int64_t)__ldg(perm + q) : q;
+        const int64_t a = anchor ? *anchor : __ldg(I + p), b = anchor ? p : __ldg(J + p);
+        const double r = a == b ? 0.0 : ot_solve(W, sC, nb, mass + a * nb, mass + b * nb, lane);
+        if (lane == 0) out[p] = (OutT)r;
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // Levenshtein: Myers (1999) / Hyyro (2003) bit-parallel unit-cost edit distance, global
 // alignment, multi-word with +-1 horizontal carries between 64-row blocks.  One thread
 // per pair; the pattern's match bit-tables Peq[symbol][word] are built once per warp in
@@ -343,6 +535,18 @@ static int launch_lev(annb_ctx *c, const annb_dataset *ds, const int32_t *I, con
 }
 
 template <typename OutT>
+static int launch_ot(annb_ctx *c, const annb_dataset *ds, const int32_t *I, const int32_t *J, const int32_t *anchor,
+                     const int32_t *perm, int64_t n, OutT *out)
+{
+    const size_t smem = (size_t)OT_B * OT_B * 8 + (size_t)OT_WARPS * sizeof(OtWarp);
+    ANNB_CUDA(cudaFuncSetAttribute(ot_pair_kernel<OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = grid_for(c, n, OT_WARPS, 1);
+    ANNB_LAUNCH(ot_pair_kernel<OutT>, grid, OT_WARPS * 32, smem, c->stream, (const double *)ds->data, (int)ds->d,
+                ds->cost, I, J, anchor, perm, n, out);
+    return ANNB_OK;
+}
+
+template <typename OutT>
 static int pair_dists_any(annb_ctx *c, const annb_dataset *ds, int metric, const int32_t *I,
                           const int32_t *J, const int32_t *perm, int64_t n, OutT *out)
 {
@@ -361,6 +565,8 @@ static int pair_dists_any(annb_ctx *c, const annb_dataset *ds, int metric, const
                     I, J, (const int32_t *)nullptr, n, out);
         return ANNB_OK;
     }
+    case ANNB_WASSERSTEIN:
+        return launch_ot<OutT>(c, ds, I, J, nullptr, perm, n, out);
     }
     return ANNB_EINVAL;
 }
@@ -416,6 +622,8 @@ int anchor_row_f64(annb_ctx *c, const annb_dataset *ds, int metric, const int32_
                     ds->d, (const int32_t *)nullptr, (const int32_t *)nullptr, anchor, n, row);
         return ANNB_OK;
     }
+    case ANNB_WASSERSTEIN:
+        return launch_ot<double>(c, ds, nullptr, nullptr, anchor, nullptr, n, row);
     }
     return ANNB_EINVAL;
 }

@@ -74,6 +74,9 @@ __device__ __forceinline__ void load_point_tile(const View &V, int t, float *sD,
     }
     if (tid < TILE) cp_async16(sM + tid, V.meta + (int64_t)t * TILE + tid);
 }
+// __syncwarp() the compiler cannot elide: warp-level queues are written by one lane and read by another
+// (compute-sanitizer racecheck needs to see the barrier)
+__device__ __forceinline__ void warp_barrier() { asm volatile("bar.warp.sync 0xffffffff;" ::: "memory"); }
 __device__ __forceinline__ void cp_async4(void *smem, const void *gmem)
 {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);

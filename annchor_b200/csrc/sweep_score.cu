@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(256, 2) sample_sweep_kernel(const SampleArgs A
                 if (keep) queue[qn + __popc(mm & ((1u << lane) - 1))] = (uint32_t)li | ((uint32_t)lj << 8);
                 qn += __popc(mm);
             }
-            __syncwarp();
+            warp_barrier();
             for (int e0 = 0; e0 < qn; e0 += 32) {
                 const int e = e0 + lane;
                 bool emit = false;
@@ -444,7 +444,7 @@ __global__ void __launch_bounds__(256, 2) sample_sweep_kernel(const SampleArgs A
                     }
                 }
             }
-            __syncwarp();
+            warp_barrier();
         }
     }
 }

@@ -42,6 +42,7 @@ extern "C" {
 #define ANNB_COSINE 1        /* scipy.spatial.distance.cosine, annchor/utils.py:14,67 */
 #define ANNB_LEVENSHTEIN 2   /* annchor/distances.py:16-20 */
 #define ANNB_WASSERSTEIN1D 3 /* annchor/utils.py:75-86 with cost |a-b| (1-D) */
+#define ANNB_WASSERSTEIN 4   /* annchor/utils.py:75-86 with a general cost matrix (exact OT, <= 64 bins) */
 
 #define ANNB_F32 0
 #define ANNB_F64 1
@@ -84,6 +85,10 @@ int annb_dataset_hist(annb_ctx *ctx, const void *H, int64_t n, int64_t nbins, in
  * copied device to device; no counterpart in the reference (its arrays live in host memory) */
 int annb_dataset_gather(annb_ctx *ctx, const annb_dataset *ds, const int64_t *order, int64_t n,
                         annb_dataset **out);
+/* histograms + a general (nbins, nbins) ground-cost matrix for ANNB_WASSERSTEIN (annchor/utils.py:75-86:
+ * kantorovich(x, y, cost=M) -- zero bins dropped, unit mass, exact optimal transport); nbins <= 64 */
+int annb_dataset_hist_cost(annb_ctx *ctx, const void *H, int64_t n, int64_t nbins, int dtype,
+                           const double *cost, annb_dataset **out);
 int annb_dataset_free(annb_dataset *ds);
 int64_t annb_dataset_len(const annb_dataset *ds);
 

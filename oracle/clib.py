@@ -32,6 +32,8 @@ def lib():
         for nm in ("orc_euclid_pairs_f32", "orc_euclid_pairs_f64", "orc_cosine_pairs_f32",
                    "orc_cosine_pairs_f64", "orc_w1_pairs_f64"):
             getattr(L, nm).argtypes = [_P, _I, _P, _I, _P]
+        L.orc_ot_pairs_f64.argtypes = [_P, _I, _P, _P, _I, _P]
+        L.orc_ot_pairs_f64.restype = C.c_int
         L.orc_bounds_ijs.argtypes = [_P, _I, _P, _I, _P]
         L.orc_dad_ijs.argtypes = [_P, _I, _P, _I, _I, _P]
         L.orc_update_bounds.argtypes = [_P, _I, _P, _P, _P, _P]

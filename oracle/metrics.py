@@ -59,6 +59,17 @@ class PairMetric:
             self.X = np.ascontiguousarray(X, dtype=np.float64)
             nb = self.X.shape[1]
             self._call = lambda ij, n, out: L.orc_w1_pairs_f64(ptr(self.X), nb, ptr(ij), n, ptr(out))
+        elif name == "wasserstein":
+            # general ground cost (annchor/utils.py:75-86, kantorovich(x, y, cost=M)): exact OT
+            self.X = np.ascontiguousarray(X, dtype=np.float64)
+            nb = self.X.shape[1]
+            self.M = np.ascontiguousarray(kw["cost_matrix"], dtype=np.float64)
+            assert self.M.shape == (nb, nb)
+
+            def call(ij, n, out):
+                rc = L.orc_ot_pairs_f64(ptr(self.X), nb, ptr(self.M), ptr(ij), n, ptr(out))
+                assert rc == 0, "too many bins for the oracle's OT solver"
+            self._call = call
         else:
             raise ValueError("unknown oracle metric %r" % (name,))
 
@@ -76,3 +87,23 @@ def wasserstein1d_numpy(x, y):
     x = np.asarray(x, dtype=np.float64)
     y = np.asarray(y, dtype=np.float64)
     return float(np.abs(np.cumsum(x / x.sum()) - np.cumsum(y / y.sum())).sum())
+
+
+def kantorovich_lp(x, y, M):
+    """kantorovich(x, y, cost=M) (annchor/utils.py:82-84) as a linear programme (scipy HiGHS): an exact solver
+    independent of the augmenting-path one in oracle.c, used to pin it on a few pairs."""
+    from scipy.optimize import linprog
+    x = np.asarray(x, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    si, tj = np.nonzero(x > 0)[0], np.nonzero(y > 0)[0]
+    a, b = x[si] / x.sum(), y[tj] / y.sum()
+    m, n = len(si), len(tj)
+    c = np.asarray(M, dtype=np.float64)[np.ix_(si, tj)].ravel()
+    A = np.zeros((m + n, m * n))
+    for k in range(m):
+        A[k, k * n:(k + 1) * n] = 1.0
+    for l in range(n):
+        A[m + l, l::n] = 1.0
+    r = linprog(c, A_eq=A[:-1], b_eq=np.concatenate([a, b])[:-1], bounds=(0, None), method="highs")
+    assert r.status == 0, r.message
+    return float(r.fun)

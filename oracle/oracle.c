@@ -174,6 +174,150 @@ API void orc_w1_pairs_f64(const double *H, int64_t nb, const int64_t *ij, int64_
     }
 }
 
+/* 'wasserstein' with a general cost matrix (annchor/utils.py:75-86): kantorovich(x, y, cost=M) of
+ * pynndescent 0.5.13 (absent from /root/reference; its published algorithm: drop the empty bins,
+ * normalise both histograms to unit mass, solve the transportation problem exactly by network simplex and
+ * return the optimal cost).  The optimum is unique, so any exact solver restates it: this one is the
+ * textbook successive-shortest-path method (Dijkstra with node potentials on the dense bipartite residual
+ * graph), scalar float64.  Pinned against the reference's bundled digits 100-NN distances
+ * (tests/golden/digits.npz) and against an LP solver in tests/test_oracle.py. */
+#define OT_MAXB 256
+static double ot_pair(const double *x, const double *y, int64_t nb, const double *C)
+{
+    int si[OT_MAXB], tj[OT_MAXB], prev_s[OT_MAXB], prev_t[OT_MAXB];
+    char vs[OT_MAXB], vt[OT_MAXB];
+    double ra[OT_MAXB], rb[OT_MAXB], ps[OT_MAXB], pt[OT_MAXB], ds[OT_MAXB], dt[OT_MAXB];
+    static __thread double f[OT_MAXB * OT_MAXB];
+    const double EPS = 1e-13, TINY = 1e-15;
+    double sx = 0, sy = 0;
+    for (int64_t k = 0; k < nb; ++k) {
+        sx += x[k];
+        sy += y[k];
+    }
+    int m = 0, n = 0;
+    for (int64_t k = 0; k < nb; ++k) {
+        if (x[k] > 0) {
+            si[m] = (int)k;
+            ra[m++] = x[k] / sx;
+        }
+        if (y[k] > 0) {
+            tj[n] = (int)k;
+            rb[n++] = y[k] / sy;
+        }
+    }
+    if (m == 0 || n == 0) return 0.0;
+    for (int q = 0; q < m * n; ++q) f[q] = 0.0;
+    for (int k = 0; k < m; ++k) ps[k] = 0.0;
+    for (int l = 0; l < n; ++l) {
+        double mn = INFINITY;
+        for (int k = 0; k < m; ++k)
+            if (C[si[k] * nb + tj[l]] < mn) mn = C[si[k] * nb + tj[l]];
+        pt[l] = mn;
+    }
+    for (int round = 0; round < 8 * (m + n) + 32; ++round) {
+        double rem = 0;
+        for (int k = 0; k < m; ++k)
+            if (ra[k] > EPS) rem += ra[k];
+        if (!(rem > EPS)) break;
+        for (int k = 0; k < m; ++k) {
+            ds[k] = ra[k] > EPS ? 0.0 : INFINITY;
+            prev_s[k] = -1;
+            vs[k] = 0;
+        }
+        for (int l = 0; l < n; ++l) {
+            dt[l] = INFINITY;
+            prev_t[l] = -1;
+            vt[l] = 0;
+        }
+        int target = -1;
+        double dtar = INFINITY;
+        for (;;) {
+            double bv = INFINITY;
+            int bid = -1;
+            for (int k = 0; k < m; ++k)
+                if (!vs[k] && ds[k] < bv) {
+                    bv = ds[k];
+                    bid = k;
+                }
+            for (int l = 0; l < n; ++l)
+                if (!vt[l] && dt[l] < bv) {
+                    bv = dt[l];
+                    bid = OT_MAXB + l;
+                }
+            if (bid < 0) break;
+            if (bid >= OT_MAXB) {
+                const int l = bid - OT_MAXB;
+                vt[l] = 1;
+                if (rb[l] > EPS) {
+                    target = l;
+                    dtar = bv;
+                    break;
+                }
+                for (int k = 0; k < m; ++k)
+                    if (!vs[k] && f[k * n + l] > TINY) {
+                        double rc = pt[l] - ps[k] - C[si[k] * nb + tj[l]];
+                        if (rc < 0) rc = 0;
+                        if (bv + rc < ds[k]) {
+                            ds[k] = bv + rc;
+                            prev_s[k] = l;
+                        }
+                    }
+            } else {
+                const int k = bid;
+                vs[k] = 1;
+                for (int l = 0; l < n; ++l)
+                    if (!vt[l]) {
+                        double rc = C[si[k] * nb + tj[l]] + ps[k] - pt[l];
+                        if (rc < 0) rc = 0;
+                        if (bv + rc < dt[l]) {
+                            dt[l] = bv + rc;
+                            prev_t[l] = k;
+                        }
+                    }
+            }
+        }
+        if (target < 0) break;
+        for (int k = 0; k < m; ++k) ps[k] += vs[k] ? ds[k] : dtar;
+        for (int l = 0; l < n; ++l) pt[l] += vt[l] ? dt[l] : dtar;
+        double amount = rb[target];
+        int l = target, k;
+        for (;;) {
+            k = prev_t[l];
+            if (prev_s[k] < 0) break;
+            const int l2 = prev_s[k];
+            if (f[k * n + l2] < amount) amount = f[k * n + l2];
+            l = l2;
+        }
+        if (ra[k] < amount) amount = ra[k];
+        const int root = k;
+        l = target;
+        for (;;) {
+            k = prev_t[l];
+            f[k * n + l] += amount;
+            if (prev_s[k] < 0) break;
+            const int l2 = prev_s[k];
+            const double r = f[k * n + l2] - amount;
+            f[k * n + l2] = r > TINY ? r : 0.0;
+            l = l2;
+        }
+        ra[root] -= amount;
+        rb[target] -= amount;
+    }
+    double cost = 0;
+    for (int k = 0; k < m; ++k)
+        for (int l = 0; l < n; ++l) cost += f[k * n + l] * C[si[k] * nb + tj[l]];
+    return cost;
+}
+
+API int orc_ot_pairs_f64(const double *H, int64_t nb, const double *C, const int64_t *ij, int64_t n, double *out)
+{
+    if (nb > OT_MAXB) return -1;
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t p = 0; p < n; ++p)
+        out[p] = ij[2 * p] == ij[2 * p + 1] ? 0.0 : ot_pair(H + ij[2 * p] * nb, H + ij[2 * p + 1] * nb, nb, C);
+    return 0;
+}
+
 /* ------------------------------------------------------------------ */
 /* Bound / feature assembly (annchor/utils.py:274-301, 355-380)        */
 /* D is (nx, na) row-major here (the reference passes a transposed view) */

@@ -241,7 +241,27 @@ def gen_niters4():
     save("niters4", params=np.array([23, 15, 5000, 0.12, 42, 4]), **out)
 
 
-GENS = {"niters4": gen_niters4, "kat": gen_kat, "euclid_small": gen_euclid_small, "euclid_f32": gen_euclid_f32,
+def gen_digits():
+    """The reference's bundled UCI digits fixture (annchor/data/digits_data.npz, datasets.py:7-46): 1797 8x8
+    images as 64-bin histograms, the Euclidean pixel-grid cost matrix, and the first 30 columns of its exact
+    100-NN graph -- distances produced by the authors with the real pynndescent kantorovich (general cost
+    matrix, exact optimal transport), which is NOT importable here.  Known answers for the device OT kernel and
+    for the reference's test_digits / test_brute_force (annchor/tests/test_annchor.py:35-68, 216-245)."""
+    from annchor.datasets import load_digits
+    d = load_digits()
+    X = d["X"]
+    assert np.array_equal(X, np.round(X)) and X.min() >= 0 and X.max() <= 255
+    ng = d["neighbor_graph"]
+    # the sub-graph the reference's test_brute_force builds (tests/test_annchor.py:224-237): first 10 neighbours
+    # below 500 of each of the first 500 rows
+    small_idx = np.array([ng[0][i][ng[0][i] < 500][:10] for i in range(500)])
+    small_dist = np.array([ng[1][i][ng[0][i] < 500][:10] for i in range(500)])
+    save("digits", X=X.astype(np.uint8), y=d["y"].astype(np.int8), cost_matrix=d["cost_matrix"].astype(np.float64),
+         exact_idx=ng[0][:, :30].astype(np.int16), exact_dist=ng[1][:, :30].astype(np.float64),
+         small_idx=small_idx.astype(np.int16), small_dist=small_dist.astype(np.float64))
+
+
+GENS = {"digits": gen_digits, "niters4": gen_niters4, "kat": gen_kat, "euclid_small": gen_euclid_small, "euclid_f32": gen_euclid_f32,
         "blobs1000": gen_blobs1000, "strings": gen_strings, "w1": gen_w1, "cosine": gen_cosine}
 
 if __name__ == "__main__":

@@ -30,6 +30,12 @@ def _w1_case():
     return H, "wasserstein", dict(n_anchors=10, n_neighbors=10, n_samples=700, p_work=0.2), M
 
 
+def _digits_case():
+    g = load_golden("digits")  # general cost matrix: exact OT on the device (annchor/utils.py:75-86)
+    return g["X"][:700], "wasserstein", dict(n_anchors=25, n_neighbors=25, n_samples=3000, p_work=0.16), \
+        g["cost_matrix"]
+
+
 CASES = {
     "euclid_small": lambda: (load_golden("euclid_small")["X"], "euclidean",
                              dict(n_anchors=8, n_neighbors=8, n_samples=400, p_work=0.2), None),
@@ -40,6 +46,7 @@ CASES = {
                                  dict(n_anchors=30, n_neighbors=15, n_samples=1500, p_work=0.15, niters=3), None),
     "strings": lambda: (golden_strings()[0], "levenshtein", dict(n_neighbors=25, p_work=0.12), None),
     "w1": _w1_case,
+    "digits_ot": _digits_case,
     # very little work: rows are left with fewer than k-1 computed pairs and the final graph falls
     # back to predictions (annchor/utils.py:415-428)
     "low_p_work": lambda: (bench_blobs(1200, 16, 20, 3, np.float32), "euclidean",

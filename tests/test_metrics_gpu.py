@@ -83,8 +83,9 @@ def test_w1_pairs(gpu_ctx, dtype):
     M = np.abs(np.arange(H.shape[1])[:, None] - np.arange(H.shape[1])[None, :]).astype(float)
     got = ab.Dataset(gpu_ctx, H, "wasserstein", cost_matrix=M).pair_dists(IJ)
     np.testing.assert_allclose(got, PairMetric(H.astype(np.float64), "wasserstein1d")(IJ), rtol=1e-9)
-    with pytest.raises(NotImplementedError):
-        ab.Dataset(gpu_ctx, H, "wasserstein", cost_matrix=M * 2)
+    # any other ground cost goes to the exact OT kernel; 2*|a-b| must give exactly twice the closed form's value
+    got2 = ab.Dataset(gpu_ctx, H, "wasserstein", cost_matrix=M * 2).pair_dists(IJ[:500])
+    np.testing.assert_allclose(got2, 2.0 * got[:500], rtol=1e-9, atol=1e-12)
 
 
 def test_empty_and_bad_pairs(gpu_ctx):

@@ -12,6 +12,9 @@ from conftest import bench_blobs  # noqa: E402
 from annchor_b200.annchor import Annchor  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
-X = bench_blobs(n, 128, 100, 42, np.float32)
+if len(sys.argv) > 2 and sys.argv[2] == "hard":  # 100 well-separated blobs: empty sampler bins at small n
+    X = bench_blobs(n, 128, 100, 42, np.float32)
+else:
+    X = bench_blobs(n, 16, 40, 2, np.float32)
 a = Annchor(X, "euclidean", n_anchors=30, n_neighbors=15, n_samples=2000, p_work=0.1).fit()
 print("fit ok", a.evals, a.neighbor_graph[1][:2, :4])
