@@ -12,7 +12,9 @@
 //      (cp.async.bulk.tensor, 128B swizzle) of the K-blocks, one thread issues tcgen05.mma into a
 //      double-buffered TMEM accumulator (2 x 128 columns), four epilogue warps read the 128 x 128 tile
 //      back with tcgen05.ld and keep, per row, the CAND smallest approximate values with their ids
-//      (fused top-C: the N x N matrix never exists);
+//      (fused top-C: the N x N matrix never exists; a value costs one FMA and one compare against the
+//      row's cut-off, the rare survivors are appended to a shared-memory buffer that the warp prunes
+//      cooperatively with a bitonic network whenever it fills);
 //   3. the CAND candidates of every row are re-ranked with the exact metric kernel (metrics.cu, the
 //      same arithmetic as get_exact_ijs), and a row is accepted only if
 //        exact k-th value + 2 eps < smallest approximate value that was NOT kept,
@@ -33,9 +35,12 @@ namespace annb {
 namespace bf {
 
 constexpr int BM = 128, BN = 128, BK = 64;  // tile rows / columns / K elements (64 bf16 = one 128 B swizzle row)
-constexpr int STAGES = 3;                   // B pipeline depth (16 KB per stage)
+constexpr int STAGES = 2;                   // B pipeline depth (16 KB per stage; the tiles come from L2)
 constexpr int MAXKB = 6;                    // K-blocks: 3 * d_pad / 64 with d_pad <= 128
 constexpr int CAND = 64;                    // candidates kept per row
+constexpr int CAP = 92;                     // per-row survivor buffer: CAND kept + room for new survivors
+constexpr int CPITCH = CAP + 1;             // odd pitch: appends by 32 rows and reads along a row are conflict free
+constexpr int CHECK = 8;                    // columns between two overflow checks (a row gains <= CHECK entries)
 constexpr int TILE_BYTES = BM * BK * 2;     // 16 KB
 constexpr int THREADS = 192;                // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
 
@@ -177,11 +182,84 @@ struct GemmArgs {
     int64_t n, npad;
     int n_rb, n_ct, kb;  // row blocks, column tiles, K-blocks
     float scale;         // value = nx + ny - scale * (x . y): 2 (euclidean^2) or 1 (cosine, norms = 1/2)
+    int debug;           // ANNB_BF_DEBUG (timing experiments only): 1 = the epilogue drains TMEM without filtering,
+                         // 2 = filters but never keeps, 3 = no MMAs (TMA pipeline alone)
     const float *norm;
     int32_t *cand_id;    // [npad][CAND]
     float *cand_val;     // [npad][CAND]
     float *cand_tau;     // [npad] largest kept value = lower bound of everything that was dropped
 };
+
+// compare-exchange with the lane `stride` away: the lower lane of the pair keeps the smaller element when `asc`
+__device__ __forceinline__ void cx_shfl(float &v, int32_t &id, int stride, bool asc, int lane)
+{
+    const float pv = __shfl_xor_sync(0xffffffffu, v, stride);
+    const int32_t pid = __shfl_xor_sync(0xffffffffu, id, stride);
+    const bool keep_min = ((lane & stride) == 0) == asc;
+    const int take = ((int)(pv < v) & (int)keep_min) | ((int)(pv > v) & (int)!keep_min);  // no divergent branch
+    v = take ? pv : v;
+    id = take ? pid : id;
+}
+__device__ __forceinline__ void cx_reg(float &a, int32_t &ia, float &b, int32_t &ib)  // a <= b afterwards
+{
+    const bool sw = b < a;
+    const float lo = sw ? b : a, hi = sw ? a : b;
+    const int32_t ilo = sw ? ib : ia, ihi = sw ? ia : ib;
+    a = lo;
+    b = hi;
+    ia = ilo;
+    ib = ihi;
+}
+// Warp-cooperative: keep the CAND (= 64) smallest of a row's cnt (<= CAP) buffered entries in slots 0..63 (any order;
+// absent entries +inf / -1) and return the largest kept value.  128 slots as 4 registers per lane (slot = 32 k + lane):
+// the two halves are sorted ascending by a bitonic network, then min(A[i], B[63 - i]) are the 64 smallest of all.
+__device__ __forceinline__ float prune_row(float *rv, int32_t *ri, int cnt, int lane)
+{
+    float v[4];
+    int32_t id[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int e = k * 32 + lane;
+        v[k] = e < cnt ? rv[e] : INFINITY;
+        id[k] = e < cnt ? ri[e] : -1;
+    }
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1)
+#pragma unroll
+        for (int stride = size >> 1; stride >= 1; stride >>= 1) {
+            const bool asc = (lane & size) == 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) cx_shfl(v[k], id[k], stride, asc, lane);
+        }
+    // registers 1 and 3 descending, so that (0, 1) and (2, 3) are bitonic sequences of 64
+#pragma unroll
+    for (int k = 1; k < 4; k += 2) {
+        v[k] = __shfl_sync(0xffffffffu, v[k], 31 - lane);
+        id[k] = __shfl_sync(0xffffffffu, id[k], 31 - lane);
+    }
+    cx_reg(v[0], id[0], v[1], id[1]);
+    cx_reg(v[2], id[2], v[3], id[3]);
+#pragma unroll
+    for (int stride = 16; stride >= 1; stride >>= 1)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) cx_shfl(v[k], id[k], stride, true, lane);
+    // halves sorted ascending: A = (v0, v1), B = (v2, v3); B[63 - i] sits in the other register at lane 31 - lane
+    const float b1 = __shfl_sync(0xffffffffu, v[3], 31 - lane), b0 = __shfl_sync(0xffffffffu, v[2], 31 - lane);
+    const int32_t j1 = __shfl_sync(0xffffffffu, id[3], 31 - lane), j0 = __shfl_sync(0xffffffffu, id[2], 31 - lane);
+    const bool t0 = b1 < v[0], t1 = b0 < v[1];
+    v[0] = t0 ? b1 : v[0];
+    id[0] = t0 ? j1 : id[0];
+    v[1] = t1 ? b0 : v[1];
+    id[1] = t1 ? j0 : id[1];
+    rv[lane] = v[0];
+    ri[lane] = id[0];
+    rv[32 + lane] = v[1];
+    ri[32 + lane] = id[1];
+    float t = fmaxf(v[0], v[1]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, o));
+    return t;
+}
 
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_topc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
@@ -192,10 +270,10 @@ gemm_topc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char *sA = smem;                                   // [kb][128][64] bf16
     unsigned char *sB = sA + MAXKB * TILE_BYTES;                // [STAGES][128][64] bf16
-    float *lv = reinterpret_cast<float *>(sB + STAGES * TILE_BYTES);  // [CAND][128] candidate values (transposed)
-    int32_t *li = reinterpret_cast<int32_t *>(lv + CAND * BM);          // [CAND][128] candidate ids
-    float *sNy = reinterpret_cast<float *>(li + CAND * BM);             // [2][128] column norms, per accumulator stage
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sNy + 2 * BN);
+    float *cv = reinterpret_cast<float *>(sB + STAGES * TILE_BYTES);  // [128][CPITCH] survivor values per row
+    int32_t *ci = reinterpret_cast<int32_t *>(cv + BM * CPITCH);       // [128][CPITCH] survivor ids
+    float *sNy = reinterpret_cast<float *>(ci + BM * CPITCH);          // [4 warps][2 stages][128] column norms
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sNy + 8 * BN);
     uint64_t *full = bars, *empty = bars + STAGES, *a_full = bars + 2 * STAGES, *a_empty = a_full + 1;
     uint64_t *t_full = a_empty + 1, *t_empty = t_full + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(t_empty + 2);
@@ -261,7 +339,8 @@ gemm_topc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                         tc_fence_after();
 #pragma unroll
                         for (int kk = 0; kk < BK / 16; ++kk)
-                            tc_mma_bf16(tmem_base + acc * BN, smem_desc_sw128(sA + k * TILE_BYTES, kk * 16),
+                            if (G.debug != 3)
+                                tc_mma_bf16(tmem_base + acc * BN, smem_desc_sw128(sA + k * TILE_BYTES, kk * 16),
                                         smem_desc_sw128(sB + st * TILE_BYTES, kk * 16), idesc, (k | kk) != 0);
                         tc_commit(&empty[st]);  // frees the B stage once these MMAs have completed
                         if (++st == STAGES) {
@@ -280,46 +359,73 @@ gemm_topc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         }
     } else {
         // ===== epilogue: four warps, warp w reads TMEM lanes 32 * (w % 4) .. + 31 =====
+        // A thread owns one row.  Values below the row's cut-off tau are APPENDED to the row's buffer (rare after the
+        // first tiles); when a row has fewer than CHECK free slots the warp prunes it cooperatively to the CAND
+        // smallest entries (bitonic sort in registers) and lowers tau to the largest of them.  tau only ever
+        // decreases, so everything dropped -- at the filter or in a prune -- is >= the final tau.
         const int q = warp & 3;
         const int r = q * 32 + lane;      // tile row = TMEM lane
-        const int et = threadIdx.x - 64;  // 0..127 among the epilogue threads
         uint32_t acc = 0, pacc = 0;
         for (int rb = blockIdx.x; rb < G.n_rb; rb += gridDim.x) {
             const int64_t gi = (int64_t)rb * BM + r;
             const float nx = G.norm[gi];
-            for (int k = 0; k < CAND; ++k) {
-                lv[k * BM + r] = INFINITY;
-                li[k * BM + r] = -1;
-            }
-            float tau = INFINITY;
-            int pmax = 0;
+            float tau = G.debug == 2 ? -INFINITY : INFINITY;
+            int cnt = 0;
             for (int ct = 0; ct < G.n_ct; ++ct) {
-                sNy[acc * BN + et] = G.norm[(int64_t)ct * BN + et];
-                asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
+                // column norms of this tile: a private copy per warp and accumulator stage (no block barrier)
+                float *ny = sNy + (q * 2 + acc) * BN;
+                __syncwarp();
+                *reinterpret_cast<float4 *>(ny + lane * 4) =
+                    __ldg(reinterpret_cast<const float4 *>(G.norm + (int64_t)ct * BN) + lane);
+                __syncwarp();
                 mbar_wait(&t_full[acc], pacc);
                 tc_fence_after();
-                const float *ny = sNy + acc * BN;
 #pragma unroll 1
                 for (int c0 = 0; c0 < BN; c0 += 32) {
                     uint32_t v[32];
                     tc_ld_32x32(tmem_base + acc * BN + c0 + ((uint32_t)(q * 32) << 16), v);
+                    if (G.debug == 1) continue;
+                    // all 32 values first (independent FMAs, the column norms come as 8 x LDS.128), one compare mask;
+                    // the shared-memory appends happen only for the rare chunk that has a survivor
+                    float val[32];
+                    uint32_t mask = 0;
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        const float val = fmaf(-G.scale, __uint_as_float(v[c]), nx + ny[c0 + c]);
-                        if (val < tau) {
-                            const int64_t gj = (int64_t)ct * BN + c0 + c;
-                            if (gj != gi) {
-                                lv[pmax * BM + r] = val;
-                                li[pmax * BM + r] = (int32_t)gj;
-                                tau = -INFINITY;
-                                for (int k = 0; k < CAND; ++k) {
-                                    const float x = lv[k * BM + r];
-                                    if (x > tau) {
-                                        tau = x;
-                                        pmax = k;
+                    for (int c4 = 0; c4 < 32; c4 += 4) {
+                        const float4 y4 = *reinterpret_cast<const float4 *>(ny + c0 + c4);
+                        val[c4 + 0] = fmaf(-G.scale, __uint_as_float(v[c4 + 0]), nx + y4.x);
+                        val[c4 + 1] = fmaf(-G.scale, __uint_as_float(v[c4 + 1]), nx + y4.y);
+                        val[c4 + 2] = fmaf(-G.scale, __uint_as_float(v[c4 + 2]), nx + y4.z);
+                        val[c4 + 3] = fmaf(-G.scale, __uint_as_float(v[c4 + 3]), nx + y4.w);
+                    }
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) mask |= (val[c] < tau) ? (1u << c) : 0u;
+                    if (!__any_sync(0xffffffffu, mask != 0u)) continue;
+#pragma unroll
+                    for (int g = 0; g < 32; g += CHECK) {
+                        if ((mask >> g) & ((1u << CHECK) - 1u)) {
+#pragma unroll
+                            for (int c = g; c < g + CHECK; ++c)
+                                if (((mask >> c) & 1u) && val[c] < tau) {  // tau may have dropped in a prune since the mask
+                                    const int64_t gj = (int64_t)ct * BN + c0 + c;
+                                    if (gj != gi) {
+                                        cv[r * CPITCH + cnt] = val[c];
+                                        ci[r * CPITCH + cnt] = (int32_t)gj;
+                                        ++cnt;
                                     }
                                 }
+                        }
+                        unsigned need = __ballot_sync(0xffffffffu, cnt > CAP - CHECK);
+                        while (need) {
+                            const int src = __ffs(need) - 1;
+                            need &= need - 1;
+                            const int c_r = __shfl_sync(0xffffffffu, cnt, src);
+                            __syncwarp();
+                            const float t = prune_row(cv + (q * 32 + src) * CPITCH, ci + (q * 32 + src) * CPITCH, c_r, lane);
+                            if (lane == src) {
+                                cnt = CAND;
+                                tau = t;
                             }
+                            __syncwarp();
                         }
                     }
                 }
@@ -331,11 +437,21 @@ gemm_topc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     pacc ^= 1;
                 }
             }
-            for (int k = 0; k < CAND; ++k) {
-                G.cand_id[gi * CAND + k] = li[k * BM + r];
-                G.cand_val[gi * CAND + k] = lv[k * BM + r];
+            // final prune of every row, then the CAND slots go out (absent entries: id -1, value +inf)
+            for (int src = 0; src < 32; ++src) {
+                const int c_r = __shfl_sync(0xffffffffu, cnt, src);
+                __syncwarp();
+                const float t = prune_row(cv + (q * 32 + src) * CPITCH, ci + (q * 32 + src) * CPITCH, c_r, lane);
+                if (lane == src) tau = t;
+                __syncwarp();
+                const int64_t go = (int64_t)rb * BM + q * 32 + src;
+                for (int k = lane; k < CAND; k += 32) {
+                    G.cand_id[go * CAND + k] = ci[(q * 32 + src) * CPITCH + k];
+                    G.cand_val[go * CAND + k] = cv[(q * 32 + src) * CPITCH + k];
+                }
             }
             G.cand_tau[gi] = tau;
+            __syncwarp();
         }
     }
     tc_fence_before();
@@ -343,8 +459,9 @@ gemm_topc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
 }
 
-constexpr size_t GEMM_SMEM = 1024 + (size_t)(MAXKB + STAGES) * TILE_BYTES + (size_t)CAND * BM * 8 + 2 * BN * 4 +
+constexpr size_t GEMM_SMEM = 1024 + (size_t)(MAXKB + STAGES) * TILE_BYTES + (size_t)BM * CPITCH * 8 + 8 * BN * 4 +
                              (2 * STAGES + 6) * 8 + 64;
+static_assert(GEMM_SMEM <= 227 * 1024, "gemm_topc_kernel: shared memory budget");
 
 // cuTensorMapEncodeTiled through the runtime (libannb links cudart statically, not libcuda)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -543,6 +660,7 @@ ANNB_API int annb_bruteforce_knn(annb_ctx *c, const annb_dataset *ds, int metric
     G.n_ct = (int)(npad / bf::BN);
     G.kb = K / bf::BK;
     G.scale = cosine ? 1.0f : 2.0f;
+    G.debug = getenv("ANNB_BF_DEBUG") ? atoi(getenv("ANNB_BF_DEBUG")) : 0;
     G.norm = norm.as<float>();
     G.cand_id = cid.as<int32_t>();
     G.cand_val = cval.as<float>();
@@ -554,8 +672,18 @@ ANNB_API int annb_bruteforce_knn(annb_ctx *c, const annb_dataset *ds, int metric
         return ANNB_ECUDA;
     }
     const int grid = std::min(c->num_sms, G.n_rb);
+    if (g_trace) cudaEventRecord(c->ev0, c->stream);
     bf::gemm_topc_kernel<<<grid, bf::THREADS, bf::GEMM_SMEM, c->stream>>>(mapA, mapB, G);
     ++g_launches;
+    if (g_trace) {
+        cudaEventRecord(c->ev1, c->stream);
+        cudaEventSynchronize(c->ev1);
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+        const double flop = 2.0 * (double)npad * (double)npad * (double)K;
+        fprintf(stderr, "[annb-trace]   brute force gemm_topc_kernel: %.3f ms, %.1f TFLOP/s (bf16, K = %d), debug %d\n", ms,
+                flop / (ms * 1e-3) / 1e12, K, G.debug);
+    }
     // largest squared norm -> error bound of the approximate values
     std::vector<float> hnorm(n), htau(n);
     if (cudaMemcpyAsync(hnorm.data(), norm.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||

@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(256, 2) sample_sweep_kernel(const SampleArgs A
         for (int r = 0; r < 8; ++r) {
             const int li = micro_off(ty, r);
             const uint32_t gi = (uint32_t)(ti * TILE + li);
-            int qn = 0;
+            uint32_t km = 0;  // columns of this row step that take part
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 const int lj = micro_off(tx, c);
@@ -405,10 +405,21 @@ __global__ void __launch_bounds__(256, 2) sample_sweep_kernel(const SampleArgs A
                     for (int k = 1; k < A.nb; ++k) b += dad >= A.edge[k];
                     keep = A.bthr[b] != 0u && h <= A.bthr[b];
                 }
-                const unsigned mm = __ballot_sync(0xffffffffu, keep);
-                if (keep) queue[qn + __popc(mm & ((1u << lane) - 1))] = (uint32_t)li | ((uint32_t)lj << 8);
-                qn += __popc(mm);
+                km |= keep ? (1u << c) : 0u;
             }
+            // compact the kept (row, column) pairs of the warp into its queue: exclusive scan of the lanes' counts
+            const int mine = __popc(km);
+            int incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const int qn = __shfl_sync(0xffffffffu, incl, 31);
+            int pos = incl - mine;
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                if ((km >> c) & 1u) queue[pos++] = (uint32_t)li | ((uint32_t)micro_off(tx, c) << 8);
             warp_barrier();
             for (int e0 = 0; e0 < qn; e0 += 32) {
                 const int e = e0 + lane;
