@@ -1525,6 +1525,7 @@ ANNB_API int annb_index_create(annb_ctx *c, const annb_dataset *ds, int metric,
     }
     ANNB_CUDA(cudaMemsetAsync(ix->tl_ptr.p, 0, (size_t)(ix->NT + 1) * 8, c->stream));  // every tile list empty
     ix->cull_enabled = getenv("ANNB_NO_CULL") == nullptr;  // test knob: sweeps without tile-level pruning
+    ix->reduced_enabled = getenv("ANNB_NO_REDUCED") == nullptr;  // test knob: pruning without the reduced tile mode
     ANNB_TRY(hash_alloc(ix, 1 << 16));
     *out = ix;
     return ANNB_OK;
@@ -1967,7 +1968,53 @@ static int run_thresh(annb_index *ix, int k2)
         P.R = R;
         P.rank = ix->P.rank;
         P.world = ix->P.world;
+        P.counters = nullptr;
+        P.reduced = (P.V.cull && ix->reduced_enabled) ? 1 : 0;
+        if (const char *dump = getenv("ANNB_DUMP_TILES")) {
+            // debug: what the tile test of this sweep sees (analysed offline, tools/tile_prune_replay.py)
+            static int dump_no = 0;
+            char path[512];
+            snprintf(path, sizeof path, "%s.%d.bin", dump, dump_no++);
+            ANNB_CUDA(cudaStreamSynchronize(c->stream));
+            const View V = ix->view();
+            const int64_t T = V.T;
+            std::vector<float> lo((size_t)T * kMaxAnchors), hi((size_t)T * kMaxAnchors), c1(ix->npad), c2(ix->npad, 0.0f);
+            std::vector<uint64_t> cm(T);
+            std::vector<long long> tl((size_t)ix->NT + 1);
+            cudaMemcpy(lo.data(), V.tb_lo, lo.size() * 4, cudaMemcpyDeviceToHost);
+            cudaMemcpy(hi.data(), V.tb_hi, hi.size() * 4, cudaMemcpyDeviceToHost);
+            cudaMemcpy(cm.data(), V.tb_cm, cm.size() * 8, cudaMemcpyDeviceToHost);
+            cudaMemcpy(c1.data(), P.cut1, c1.size() * 4, cudaMemcpyDeviceToHost);
+            if (P.cut2) cudaMemcpy(c2.data(), P.cut2, c2.size() * 4, cudaMemcpyDeviceToHost);
+            cudaMemcpy(tl.data(), V.tl_ptr, tl.size() * 8, cudaMemcpyDeviceToHost);
+            if (FILE *f = fopen(path, "wb")) {
+                const int64_t hdr[6] = {T, kMaxAnchors, V.na, ix->npad, P.cut2 ? 1 : 0, (int64_t)sizeof(Model)};
+                fwrite(hdr, 8, 6, f);
+                fwrite(&ix->model, sizeof(Model), 1, f);
+                fwrite(lo.data(), 4, lo.size(), f);
+                fwrite(hi.data(), 4, hi.size(), f);
+                fwrite(cm.data(), 8, cm.size(), f);
+                fwrite(c1.data(), 4, c1.size(), f);
+                fwrite(c2.data(), 4, c2.size(), f);
+                // store entries per tile as a byte (0 / 1) in upper-triangular order
+                std::vector<uint8_t> he((size_t)ix->NT);
+                for (int64_t t = 0; t < ix->NT; ++t) he[t] = tl[t + 1] > tl[t];
+                fwrite(he.data(), 1, he.size(), f);
+                fclose(f);
+            }
+        }
+        if (g_trace) {
+            ANNB_CUDA(cudaMemsetAsync(ix->counters.p, 0, 64, c->stream));
+            P.counters = ix->counters.as<unsigned long long>();
+        }
         ANNB_TRY(launch_thresh_pairs(c, P));
+        if (g_trace) {
+            unsigned long long tc[4];
+            ANNB_CUDA(cudaMemcpyAsync(tc, ix->counters.p, 32, cudaMemcpyDeviceToHost, c->stream));
+            ANNB_CUDA(cudaStreamSynchronize(c->stream));
+            fprintf(stderr, "[annb-trace]   thresh pair sweep: tiles pruned %llu, reduced %llu, computed in full %llu (with store entries %llu) of %lld\n",
+                    tc[0], tc[3], tc[2], tc[1], (long long)ix->NT);
+        }
         ix->pairs_swept += n * (n - 1) / 2 / ix->P.world;
         ix->sweeps += 1;
         // 3. per-row selection (per-rank partial lists when the tiles are split)
@@ -2164,7 +2211,7 @@ static void fill_efloor(const annb_index *ix, int floor_level, float *efloor, fl
 }
 
 static int run_score(annb_index *ix, int floor_level, uint64_t floor_mix_thr, int stride, bool emit,
-                     int64_t emit_cap, std::vector<uint64_t> &hist, unsigned long long cnt[6])
+                     int64_t emit_cap, std::vector<uint64_t> &hist, unsigned long long cnt[8])
 {
     annb_ctx *c = ix->ctx;
     ANNB_TRY(tile_lists_rebuild(ix));
@@ -2204,6 +2251,7 @@ static int run_score(annb_index *ix, int floor_level, uint64_t floor_mix_thr, in
     A.q_stride = stride;
     A.rank = ix->P.rank;
     A.world = ix->P.world;
+    A.reduced = (A.V.cull && ix->reduced_enabled) ? 1 : 0;
     ANNB_CUDA(cudaMemsetAsync(ix->hist.p, 0, (size_t)ix->nlevels * 4, c->stream));
     ANNB_CUDA(cudaMemsetAsync(ix->counters.p, 0, 64, c->stream));
     ANNB_CUDA(cudaEventRecord(c->ev0, c->stream));
@@ -2211,12 +2259,12 @@ static int run_score(annb_index *ix, int floor_level, uint64_t floor_mix_thr, in
     ANNB_CUDA(cudaEventRecord(c->ev1, c->stream));
     std::vector<uint32_t> h32(ix->nlevels);
     ANNB_CUDA(cudaMemcpyAsync(h32.data(), ix->hist.p, (size_t)ix->nlevels * 4, cudaMemcpyDeviceToHost, c->stream));
-    ANNB_CUDA(cudaMemcpyAsync(cnt, ix->counters.p, 48, cudaMemcpyDeviceToHost, c->stream));
+    ANNB_CUDA(cudaMemcpyAsync(cnt, ix->counters.p, 56, cudaMemcpyDeviceToHost, c->stream));
     ANNB_CUDA(cudaStreamSynchronize(c->stream));
     hist.assign(h32.begin(), h32.end());
     if (g_trace)
-        fprintf(stderr, "[annb-trace]   score sweep: stride %d floor %d pairs-in-phase2 %llu (flagged %llu) not-computed %llu emitted %llu, tiles pruned %llu\n",
-                stride, floor_level, cnt[3], cnt[4], cnt[1], cnt[0], cnt[5]);
+        fprintf(stderr, "[annb-trace]   score sweep: stride %d floor %d pairs-in-phase2 %llu (flagged %llu) not-computed %llu emitted %llu, tiles pruned %llu, reduced %llu, pairs computed %llu\n",
+                stride, floor_level, cnt[3], cnt[4], cnt[1], cnt[0], cnt[5], cnt[6], cnt[2]);
     ANNB_TRY(ix->reduce(hist.data(), (int64_t)hist.size(), ANNB_RED_U64));  // global level counts
     float ms = 0;
     ANNB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
@@ -2314,7 +2362,7 @@ ANNB_API int annb_index_select(annb_index *ix, int64_t n_refine, int64_t lookahe
     int64_t tot_target = want1 >= n_nc ? n_nc : std::min<int64_t>(want2, n_nc);
 
     std::vector<uint64_t> h1, h2;
-    unsigned long long c1v[6] = {0, 0, 0, 0, 0, 0}, c2v[6] = {0, 0, 0, 0, 0, 0};
+    unsigned long long c1v[8] = {0, 0, 0, 0, 0, 0, 0, 0}, c2v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     // Level 0 is probability 0.  On small problems it takes part like any other level (the
     // reference's argpartition then picks arbitrary probability-0 pairs).  On large problems
     // emitting the probability-0 bulk is pointless and Theta(N^2): the cut never goes below level 1,

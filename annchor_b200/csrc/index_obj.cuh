@@ -113,6 +113,7 @@ struct annb_index {
         return V;
     }
     bool cull_enabled = true;
+    bool reduced_enabled = true;  // reduced tile mode of the sweeps (sweep.cuh); ANNB_NO_REDUCED turns it off
     int64_t n_not_computed() const { return n_candidates - n_anchor_pairs - n_known; }
 };
 

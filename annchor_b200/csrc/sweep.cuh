@@ -489,6 +489,99 @@ __device__ __forceinline__ bool tile_can_pass(const View &V, const Model &M, int
     return any;
 }
 
+// ---- reduced tile mode -------------------------------------------------------------------------
+// A tile's cut-offs are not uniform: a few rows (points whose neighbourhood the pre-pass missed, rows
+// without enough candidates: cut = +inf) sit far above the rest, and the tile-level test against the LARGEST
+// cut of 128 rows then keeps alive a tile pair that only those rows can use.  So a tile pair that survives
+// the test is examined per row: tile_can_pass with the row's OWN cut tells whether any pair of that row can
+// pass phase 1 through the row's cut (a pair passes through max(cut_i, cut_j), i.e. through one of its two
+// rows).  When at most MAXO rows of either tile can, the sweep computes only (those rows x all columns),
+// (all rows x those columns) and the pairs with a store entry -- a few hundred pairs instead of 16 384 --
+// with the same per-pair arithmetic and the same phase 2.
+constexpr int MAXO = 16;
+struct Outliers {  // shared memory
+    uint32_t mi[4], mj[4];   // rows of the row tile / the column tile that can pass, as bit masks
+    int n_i, n_j;
+    uint8_t oi[MAXO], oj[MAXO];
+};
+// Every thread calls this with `mine` = "my row can pass" (threads 0..127: rows of the row tile, 128..255: rows of the
+// column tile).  Returns true, with the index lists filled, if both tiles have at most MAXO such rows.  Block-wide.
+__device__ __forceinline__ bool collect_outliers(Outliers *o, bool mine)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned bal = __ballot_sync(0xffffffffu, mine);
+    if (lane == 0 && warp < 8) (warp < 4 ? o->mi[warp] : o->mj[warp - 4]) = bal;
+    __syncthreads();
+    const int n_i = __popc(o->mi[0]) + __popc(o->mi[1]) + __popc(o->mi[2]) + __popc(o->mi[3]);
+    const int n_j = __popc(o->mj[0]) + __popc(o->mj[1]) + __popc(o->mj[2]) + __popc(o->mj[3]);
+    const bool ok = n_i <= MAXO && n_j <= MAXO;
+    if (ok && warp < 2) {  // warp 0 lists the rows, warp 1 the columns: lane l takes the l-th set bit
+        const uint32_t *m = warp == 0 ? o->mi : o->mj;
+        int k = lane, idx = -1;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const int c = __popc(m[w]);
+            if (idx < 0) {
+                if (k < c) idx = w * 32 + (int)__fns(m[w], 0, k + 1);
+                else k -= c;
+            }
+        }
+        if (lane < (warp == 0 ? n_i : n_j)) (warp == 0 ? o->oi : o->oj)[lane] = (uint8_t)idx;
+        if (lane == 0) (warp == 0 ? o->n_i : o->n_j) = warp == 0 ? n_i : n_j;
+    }
+    __syncthreads();
+    return ok;
+}
+// no row can pass on its own: only the store entries of the tile are left
+__device__ __forceinline__ void no_outliers(Outliers *o)
+{
+    if (threadIdx.x < 4) {
+        o->mi[threadIdx.x] = 0u;
+        o->mj[threadIdx.x] = 0u;
+    }
+    if (threadIdx.x == 0) o->n_i = o->n_j = 0;
+    __syncthreads();
+}
+// bounds of ONE pair from the staged anchor-distance tiles: one rounded subtraction / addition per anchor and
+// exact max / min, i.e. bit-identical to what bounds_half leaves for the same pair
+__device__ __forceinline__ void bounds_pair(const float *__restrict__ sDi, const float *__restrict__ sDj, int na, int li,
+                                            int lj, float &lb, float &ub)
+{
+    lb = 0.0f;
+    ub = INFINITY;
+    for (int a = 0; a < na; ++a) {
+        const float x = sDi[a * SROW + li], y = sDj[a * SROW + lj];
+        lb = fmaxf(lb, fabsf(x - y));
+        ub = fminf(ub, x + y);
+    }
+}
+// item `idx` of a reduced tile: [0, 128 n_i) outlier rows x columns | [.., + 128 n_j) rows x outlier columns (rows
+// that are outliers themselves are covered by the first group) | entries of the store (not in an outlier row /
+// column).  Returns false for an index that is not a pair of its own.
+__device__ __forceinline__ bool reduced_item(const View &V, const Outliers *o, const TileDesc *dp, const uint32_t *codes,
+                                             int idx, int &li, int &lj)
+{
+    const int na_ = o->n_i * TILE, nb_ = o->n_j * TILE;
+    if (idx < na_) {
+        li = o->oi[idx >> 7];
+        lj = idx & 127;
+        return true;
+    }
+    if (idx < na_ + nb_) {
+        const int k = idx - na_;
+        lj = o->oj[k >> 7];
+        li = k & 127;
+        return ((o->mi[li >> 5] >> (li & 31)) & 1u) == 0u;
+    }
+    const long long e = idx - na_ - nb_;
+    const long long cnt = dp->end - dp->base;
+    if (e >= cnt) return false;
+    const uint32_t code = cnt <= TL_CAP ? codes[e] : __ldg(V.tl_code + dp->base + e);
+    li = code >> 9;
+    lj = (code >> 2) & 127;
+    return ((o->mi[li >> 5] >> (li & 31)) & 1u) == 0u && ((o->mj[lj >> 5] >> (lj & 31)) & 1u) == 0u;
+}
+
 // largest of 128 shared-memory values (every warp computes it)
 __device__ __forceinline__ float tile_max128(const float *v)
 {

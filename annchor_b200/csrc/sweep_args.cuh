@@ -36,6 +36,9 @@ struct ThreshPairArgs {
     int R;
     int rank, world;
     int qcap;
+    unsigned long long *counters;  // trace (may be nullptr): [0] tiles pruned, [1] tiles with store entries, [2] tiles
+                                   // computed in full, [3] tiles in reduced mode
+    int reduced;         // reduced tile mode on (sweep.cuh)
 };
 
 struct ScoreArgs {
@@ -64,6 +67,7 @@ struct ScoreArgs {
     int64_t q_begin, q_end;   // range of this rank's tile sequence
     int q_stride;             // 1 = every tile; s > 1 = pilot over every s-th tile
     int rank, world;
+    int reduced;              // reduced tile mode on (sweep.cuh)
 };
 
 struct SampleArgs {

@@ -100,8 +100,9 @@ __global__ void __launch_bounds__(SWT, 1) score_sweep_kernel(const __grid_consta
     // sequence, and a contiguous slice per CTA would leave most SMs idle while a few finish
     const int64_t nq = (A.q_end - A.q_begin + A.q_stride - 1) / A.q_stride;
     const int64_t m0 = 0, m1 = (nq - (int64_t)blockIdx.x + gridDim.x - 1) / gridDim.x;
-    unsigned long long n_nc = 0, n_swept = 0, n_staged = 0, n_flagged = 0;
-    int n_culled = 0;
+    unsigned n_nc = 0, n_swept = 0, n_staged = 0, n_flagged = 0;  // per lane: < 2^32 (widened when reduced)
+    int n_culled = 0, n_reduced = 0;
+    __shared__ Outliers s_out;
     int en = 0;  // staged emissions of this warp
 
     auto tile_no = [&](int64_t m) {
@@ -154,15 +155,137 @@ __global__ void __launch_bounds__(SWT, 1) score_sweep_kernel(const __grid_consta
         // tile-level pruning: no store entry in the tile and even the smallest possible prediction
         // cannot reach the floor level for the largest threshold of the two tiles (the same test
         // `cut - pred > margin` phase 1 applies per pair, at the tile's extremes)
-        if (V.cull && A.ef_min > -INFINITY && sDesc[(m - m0) & 3].end == sDesc[(m - m0) & 3].base && ti != tj) {
+        const bool has_entries = sDesc[(m - m0) & 3].end != sDesc[(m - m0) & 3].base;
+        bool reduced = false;
+        if (V.cull && A.ef_min > -INFINITY && ti != tj) {
             const float cutmax = fmaxf(tile_max128(tI), tile_max128(tJ));
-            if (!tile_can_pass<0>(V, M, ti, tj, cutmax, A.efloor)) {
+            const bool can = tile_can_pass<0>(V, M, ti, tj, cutmax, A.efloor);
+            if (!can && !has_entries) {
                 n_culled += 1;
                 continue;
+            }
+            if (A.reduced) {  // reduced tile mode (sweep.cuh): which rows can reach the floor level through their own threshold?
+                if (can) {
+                    const int l = tid & (TILE - 1);
+                    const float myc = tid < TILE ? tI[l] : tJ[l];
+                    const bool mine = tile_can_pass<0>(V, M, ti, tj, myc, A.efloor) && tid < 2 * TILE;
+                    reduced = collect_outliers(&s_out, mine);
+                } else {
+                    no_outliers(&s_out);
+                    reduced = true;
+                }
             }
         }
         build_tile_store(V, ts, &sDesc[(m - m0) & 3], sCode + buf * TL_CAP, sBm, 0);
         const uint32_t *bm = sBm;
+        // ---- phase 2: drain the warp's queue, one survivor per lane ----
+        auto drain = [&](int qn) {
+            if (lane == 0) n_staged += qn;
+            for (int e0 = 0; e0 < qn; e0 += 32) {
+                if (en > EMIT_CAP - 32) flush_emit(A, ek, el, en, lane);
+                const int e = e0 + lane;
+                int lvl = -1;
+                uint64_t key = 0;
+                if (e < qn) {
+                    const Survivor s = queue[e];
+                    const int li2 = s.ids & 0xff, lj = s.ids >> 8;
+                    const int gi = ti * TILE + li2, gj = tj * TILE + lj;
+                    if (gj < V.n && s.lb < INFINITY) {  // gi < gj by construction (diagonal masked to +inf)
+                        const PointMeta pi = sMi[li2], pj = sMj[lj];
+                        if (is_candidate(pi, pj)) {
+                            const bool fl = flag_bit(bm, li2, lj);
+                            n_flagged += fl ? 1 : 0;
+                            const PairVal pv = pair_value(V, ts, tm, M, s.lb, s.ub, li2, lj, gi, gj, li2, lj, pi, pj,
+                                                          sDi, sDj, fl);
+                            if (!pv.computed) {
+                                ++n_nc;
+                                const float p = fmaxf(tI[li2], tJ[lj]) - pv.v;
+                                const int label = err_label2(M, pv.dad);
+                                if (p > A.efloor[label]) {
+                                    int l = A.floor_level;
+                                    if (p > A.efloor_hi[label]) {  // above the floor level: rank it
+                                        const float *er = errs + M.eoff[label];
+                                        int lo = 0, hi = M.eoff[label + 1] - M.eoff[label];
+                                        while (lo < hi) {  // np.searchsorted(errs[label], p, 'left')
+                                            const int mid = (lo + hi) >> 1;
+                                            if (er[mid] < p) lo = mid + 1;
+                                            else hi = mid;
+                                        }
+                                        l = ranktab[M.eoff[label] + label + lo];
+                                    }
+                                    if (l >= A.floor_level) {
+                                        key = pair_key((uint32_t)gi, (uint32_t)gj);
+                                        if (l > A.floor_level ||
+                                            tie_key((uint32_t)gi, (uint32_t)gj, A.tie_salt) <= A.floor_mix_thr) {
+                                            lvl = l;
+                                            atomicAdd(&sHist[l], 1u);  // at the floor level: emitted pairs only
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+                if (A.emit_key) {
+                    const unsigned mm = __ballot_sync(0xffffffffu, lvl >= 0);
+                    if (lvl >= 0) {
+                        const int pos = en + __popc(mm & ((1u << lane) - 1));
+                        ek[pos] = key;
+                        el[pos] = (uint16_t)lvl;
+                    }
+                    en += __popc(mm);
+                    __syncwarp();
+                }
+            }
+            __syncwarp();
+            if (lane == 0) *qcnt = 0;
+            __syncwarp();
+        };
+        if (reduced) {
+            // outlier rows / columns and store entries only, one pair per thread and round; the per-pair test is the
+            // one phase 1 of the full tile applies (same expressions, same rounding)
+            const TileDesc *dp = &sDesc[(m - m0) & 3];
+            const int n_items = (s_out.n_i + s_out.n_j) * TILE + (int)(dp->end - dp->base);
+            const uint32_t thr_hi_r = (uint32_t)(A.floor_mix_thr >> 32);
+            for (int base = 0; base < n_items; base += SWT) {
+                int li = 0, lj = 0;
+                bool keep = false;
+                Survivor sv;
+                if (base + tid < n_items && reduced_item(V, &s_out, dp, sCode + buf * TL_CAP, base + tid, li, lj)) {
+                    n_swept += 1;
+                    bounds_pair(sDi, sDj, na, li, lj, sv.lb, sv.ub);
+                    const float s2 = sDi[sMj[lj].cA * SROW + li] + sDj[sMi[li].cA * SROW + lj];
+                    int bin;
+                    const float y = predict_clip2(tm, M, sv.lb, sv.ub, s2, bin);
+                    const float4 mx = tm->mx[bin];
+                    const bool eq = s2 == tm->en[bin];
+                    const float cut = fmaxf(tI[li], tJ[lj]);
+                    if (!A.wide_floor) {
+                        keep = cut - y > (eq ? mx.y : mx.x);
+                    } else {
+                        const uint32_t h = hash_pair32((uint32_t)(ti * TILE + li), (uint32_t)(tj * TILE + lj),
+                                                       (uint32_t)A.tie_salt);
+                        keep = (cut - y > (eq ? mx.w : mx.z)) || ((cut - y > (eq ? mx.y : mx.x)) && h <= thr_hi_r);
+                    }
+                    keep = keep || flag_bit(bm, li, lj);
+                }
+                const unsigned mm = __ballot_sync(0xffffffffu, keep);
+                int qn = *reinterpret_cast<volatile int *>(qcnt);
+                if (keep) {
+                    sv.ids = (uint32_t)li | ((uint32_t)lj << 8);
+                    sv.pad = 0;
+                    queue[qn + __popc(mm & ((1u << lane) - 1u))] = sv;
+                }
+                qn += __popc(mm);
+                __syncwarp();
+                if (lane == 0) *qcnt = qn;
+                __syncwarp();
+                if (qn > A.qcap - 32) drain(qn);
+            }
+            drain(*reinterpret_cast<volatile int *>(qcnt));
+            n_reduced += 1;
+            continue;
+        }
         // ---- phase 1: bounds + clipped prediction; keep (pred < cut-off) | flagged ----
         float cj[8];
         int cAj[8];
@@ -237,67 +360,7 @@ __global__ void __launch_bounds__(SWT, 1) score_sweep_kernel(const __grid_consta
             __syncwarp();
             const int qn = *reinterpret_cast<volatile int *>(qcnt);
             if (pass < SW_PASSES - 1 && qn <= A.qcap - QROW) continue;  // room for another row step
-            // ---- phase 2: drain the queue, one survivor per lane ----
-            if (lane == 0) n_staged += qn;
-            for (int e0 = 0; e0 < qn; e0 += 32) {
-                if (en > EMIT_CAP - 32) flush_emit(A, ek, el, en, lane);
-                const int e = e0 + lane;
-                int lvl = -1;
-                uint64_t key = 0;
-                if (e < qn) {
-                    const Survivor s = queue[e];
-                    const int li2 = s.ids & 0xff, lj = s.ids >> 8;
-                    const int gi = ti * TILE + li2, gj = tj * TILE + lj;
-                    if (gj < V.n && s.lb < INFINITY) {  // gi < gj by construction (diagonal masked to +inf)
-                        const PointMeta pi = sMi[li2], pj = sMj[lj];
-                        if (is_candidate(pi, pj)) {
-                            const bool fl = flag_bit(bm, li2, lj);
-                            n_flagged += fl ? 1 : 0;
-                            const PairVal pv = pair_value(V, ts, tm, M, s.lb, s.ub, li2, lj, gi, gj, li2, lj, pi, pj,
-                                                          sDi, sDj, fl);
-                            if (!pv.computed) {
-                                ++n_nc;
-                                const float p = fmaxf(tI[li2], tJ[lj]) - pv.v;
-                                const int label = err_label2(M, pv.dad);
-                                if (p > A.efloor[label]) {
-                                    int l = A.floor_level;
-                                    if (p > A.efloor_hi[label]) {  // above the floor level: rank it
-                                        const float *er = errs + M.eoff[label];
-                                        int lo = 0, hi = M.eoff[label + 1] - M.eoff[label];
-                                        while (lo < hi) {  // np.searchsorted(errs[label], p, 'left')
-                                            const int mid = (lo + hi) >> 1;
-                                            if (er[mid] < p) lo = mid + 1;
-                                            else hi = mid;
-                                        }
-                                        l = ranktab[M.eoff[label] + label + lo];
-                                    }
-                                    if (l >= A.floor_level) {
-                                        key = pair_key((uint32_t)gi, (uint32_t)gj);
-                                        if (l > A.floor_level ||
-                                            tie_key((uint32_t)gi, (uint32_t)gj, A.tie_salt) <= A.floor_mix_thr) {
-                                            lvl = l;
-                                            atomicAdd(&sHist[l], 1u);  // at the floor level: emitted pairs only
-                                        }
-                                    }
-                                }
-                            }
-                        }
-                    }
-                }
-                if (A.emit_key) {
-                    const unsigned mm = __ballot_sync(0xffffffffu, lvl >= 0);
-                    if (lvl >= 0) {
-                        const int pos = en + __popc(mm & ((1u << lane) - 1));
-                        ek[pos] = key;
-                        el[pos] = (uint16_t)lvl;
-                    }
-                    en += __popc(mm);
-                    __syncwarp();
-                }
-            }
-            __syncwarp();
-            if (lane == 0) *qcnt = 0;
-            __syncwarp();
+            drain(qn);
         }
         n_swept += 32 * SW_HALVES;
     }
@@ -305,18 +368,22 @@ __global__ void __launch_bounds__(SWT, 1) score_sweep_kernel(const __grid_consta
     __syncthreads();
     for (int k = tid; k < A.nlevels; k += blockDim.x)
         if (sHist[k]) atomicAdd(&A.hist[k], sHist[k]);
+    unsigned long long w_nc = n_nc, w_swept = n_swept, w_flagged = n_flagged;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        n_nc += __shfl_xor_sync(0xffffffffu, n_nc, o);
-        n_swept += __shfl_xor_sync(0xffffffffu, n_swept, o);
-        n_flagged += __shfl_xor_sync(0xffffffffu, n_flagged, o);
+        w_nc += __shfl_xor_sync(0xffffffffu, w_nc, o);
+        w_swept += __shfl_xor_sync(0xffffffffu, w_swept, o);
+        w_flagged += __shfl_xor_sync(0xffffffffu, w_flagged, o);
     }
     if (lane == 0) {
-        atomicAdd(&A.counters[1], n_nc);
-        atomicAdd(&A.counters[2], n_swept);
-        atomicAdd(&A.counters[3], n_staged);   // phase-1 survivors handed to phase 2
-        atomicAdd(&A.counters[4], n_flagged);  // of which carried a flag bit (known / tightened / forced)
-        if (warp == 0) atomicAdd(&A.counters[5], (unsigned long long)n_culled);  // tiles skipped by the tile-level bound
+        atomicAdd(&A.counters[1], w_nc);
+        atomicAdd(&A.counters[2], w_swept);
+        atomicAdd(&A.counters[3], (unsigned long long)n_staged);  // phase-1 survivors handed to phase 2
+        atomicAdd(&A.counters[4], w_flagged);  // of which carried a flag bit (known / tightened / forced)
+        if (warp == 0) {
+            atomicAdd(&A.counters[5], (unsigned long long)n_culled);   // tiles skipped by the tile-level bound
+            atomicAdd(&A.counters[6], (unsigned long long)n_reduced);  // tiles computed in reduced mode
+        }
     }
 }
 
@@ -416,10 +483,11 @@ __global__ void __launch_bounds__(256, 2) sample_sweep_kernel(const SampleArgs A
                 if (lane >= o) incl += t;
             }
             const int qn = __shfl_sync(0xffffffffu, incl, 31);
+            uint32_t *qr = queue + (r & 1) * (QCAP / 2);  // row steps alternate between the halves (<= 256 entries each)
             int pos = incl - mine;
 #pragma unroll
             for (int c = 0; c < 8; ++c)
-                if ((km >> c) & 1u) queue[pos++] = (uint32_t)li | ((uint32_t)micro_off(tx, c) << 8);
+                if ((km >> c) & 1u) qr[pos++] = (uint32_t)li | ((uint32_t)micro_off(tx, c) << 8);
             warp_barrier();
             for (int e0 = 0; e0 < qn; e0 += 32) {
                 const int e = e0 + lane;
@@ -427,7 +495,7 @@ __global__ void __launch_bounds__(256, 2) sample_sweep_kernel(const SampleArgs A
                 uint64_t key = 0;
                 float dad = 0.0f;
                 if (e < qn) {
-                    const uint32_t ids = queue[e];
+                    const uint32_t ids = qr[e];
                     const int li2 = ids & 0xff, lj = ids >> 8;
                     const int gi2 = ti * TILE + li2, gj = tj * TILE + lj;
                     const PointMeta pi = sMi[li2], pj = sMj[lj];

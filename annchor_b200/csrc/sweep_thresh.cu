@@ -343,6 +343,8 @@ __global__ void __launch_bounds__(SWT, 1) thresh_pairs_kernel(const __grid_const
     const bool l2on = A.cut2 != nullptr;
     build_tile_model(M, tm);
     if (lane == 0) *qcnt = 0;
+    unsigned n_culled = 0, n_with_entries = 0, n_computed = 0, n_reduced = 0;
+    __shared__ Outliers s_out;
 
     const int64_t NT = (int64_t)V.T * (V.T + 1) / 2;
     const int64_t nq = (NT - A.rank + A.world - 1) / A.world;
@@ -397,12 +399,94 @@ __global__ void __launch_bounds__(SWT, 1) thresh_pairs_kernel(const __grid_const
         const float *k2I = c2I + buf * TILE, *k2J = c2J + buf * TILE;
         // tile-level pruning: no store entry in the tile and even the smallest possible prediction
         // exceeds every cut of the two tiles (phase 1 keeps a pair iff pred <= max(cut_i, cut_j))
-        if (V.cull && V.is_metric && sDesc[(m - m0) & 3].end == sDesc[(m - m0) & 3].base && ti != tj) {
+        const bool has_entries = sDesc[(m - m0) & 3].end != sDesc[(m - m0) & 3].base;
+        bool reduced = false;
+        if (V.cull && V.is_metric && ti != tj) {
             const float cutmax = fmaxf(fmaxf(tile_max128(k1I), tile_max128(k2I)), fmaxf(tile_max128(k1J), tile_max128(k2J)));
-            if (!tile_can_pass<1>(V, M, ti, tj, cutmax, nullptr)) continue;
+            const bool can = tile_can_pass<1>(V, M, ti, tj, cutmax, nullptr);
+            if (!can && !has_entries) {
+                ++n_culled;
+                continue;
+            }
+            if (A.reduced) {  // reduced tile mode (sweep.cuh): which rows can pass through their own cut?
+                if (can) {
+                    const int l = tid & (TILE - 1);
+                    const float myc = tid < TILE ? fmaxf(k1I[l], k2I[l]) : fmaxf(k1J[l], k2J[l]);
+                    const bool mine = tile_can_pass<1>(V, M, ti, tj, myc, nullptr) && tid < 2 * TILE;
+                    reduced = collect_outliers(&s_out, mine);
+                } else {
+                    no_outliers(&s_out);
+                    reduced = true;
+                }
+            }
         }
+        if (has_entries) ++n_with_entries;
+        if (reduced) ++n_reduced;
+        else ++n_computed;
         build_tile_store(V, ts, &sDesc[(m - m0) & 3], sCode + buf * TL_CAP, sBm, 0);
         const uint32_t *bm = sBm;
+        // ---- phase 2: drain the warp's queue, one survivor per lane ----
+        auto drain = [&](int qn) {
+            for (int e0 = 0; e0 < qn; e0 += 32) {
+                const int e = e0 + lane;
+                if (e < qn) {
+                    const Survivor s = queue[e];
+                    const int li2 = s.ids & 0xff, lj = s.ids >> 8;
+                    const int gi = ti * TILE + li2, gj = tj * TILE + lj;
+                    if (gj < V.n && s.lb < INFINITY) {
+                        const PointMeta pi = sMi[li2], pj = sMj[lj];
+                        if (is_candidate(pi, pj)) {
+                            const PairVal pv = pair_value(V, ts, tm, M, s.lb, s.ub, li2, lj, gi, gj, li2, lj, pi, pj, sDi,
+                                                          sDj, flag_bit(bm, li2, lj));
+                            const float v = pv.v;
+                            const uint32_t cflag = pv.computed ? 0x80000000u : 0u;
+                            if (v <= k1I[li2] || (!pv.computed && v <= k2I[li2])) {
+                                const int pos = atomicAdd(&A.cnt[gi], 1);
+                                if (pos < A.R) A.rec[(int64_t)gi * A.R + pos] = make_uint2(__float_as_uint(v), (uint32_t)gj | cflag);
+                            }
+                            if (v <= k1J[lj] || (!pv.computed && v <= k2J[lj])) {
+                                const int pos = atomicAdd(&A.cnt[gj], 1);
+                                if (pos < A.R) A.rec[(int64_t)gj * A.R + pos] = make_uint2(__float_as_uint(v), (uint32_t)gi | cflag);
+                            }
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) *qcnt = 0;
+            __syncwarp();
+        };
+        if (reduced) {
+            // outlier rows / columns and store entries only, one pair per thread and round (sweep.cuh)
+            const TileDesc *dp = &sDesc[(m - m0) & 3];
+            const int n_items = (s_out.n_i + s_out.n_j) * TILE + (int)(dp->end - dp->base);
+            for (int base = 0; base < n_items; base += SWT) {
+                int li = 0, lj = 0;
+                bool keep = false;
+                Survivor sv;
+                if (base + tid < n_items && reduced_item(V, &s_out, dp, sCode + buf * TL_CAP, base + tid, li, lj)) {
+                    bounds_pair(sDi, sDj, na, li, lj, sv.lb, sv.ub);
+                    const float s2 = sDi[sMj[lj].cA * SROW + li] + sDj[sMi[li].cA * SROW + lj];
+                    int bin;
+                    const float y = predict_clip2(tm, M, sv.lb, sv.ub, s2, bin);
+                    keep = flag_bit(bm, li, lj) || y <= fmaxf(fmaxf(k1I[li], k2I[li]), fmaxf(k1J[lj], k2J[lj]));
+                }
+                const unsigned mm = __ballot_sync(0xffffffffu, keep);
+                int qn = *reinterpret_cast<volatile int *>(qcnt);
+                if (keep) {
+                    sv.ids = (uint32_t)li | ((uint32_t)lj << 8);
+                    sv.pad = 0;
+                    queue[qn + __popc(mm & ((1u << lane) - 1u))] = sv;
+                }
+                qn += __popc(mm);
+                __syncwarp();
+                if (lane == 0) *qcnt = qn;
+                __syncwarp();
+                if (qn > A.qcap - 32) drain(qn);
+            }
+            drain(*reinterpret_cast<volatile int *>(qcnt));
+            continue;
+        }
         float cj[8];
         int cAj[8];
 #pragma unroll
@@ -446,35 +530,14 @@ __global__ void __launch_bounds__(SWT, 1) thresh_pairs_kernel(const __grid_const
             __syncwarp();
             const int qn = *reinterpret_cast<volatile int *>(qcnt);
             if (pass < SW_PASSES - 1 && qn <= A.qcap - QROW) continue;
-            for (int e0 = 0; e0 < qn; e0 += 32) {
-                const int e = e0 + lane;
-                if (e < qn) {
-                    const Survivor s = queue[e];
-                    const int li2 = s.ids & 0xff, lj = s.ids >> 8;
-                    const int gi = ti * TILE + li2, gj = tj * TILE + lj;
-                    if (gj < V.n && s.lb < INFINITY) {
-                        const PointMeta pi = sMi[li2], pj = sMj[lj];
-                        if (is_candidate(pi, pj)) {
-                            const PairVal pv = pair_value(V, ts, tm, M, s.lb, s.ub, li2, lj, gi, gj, li2, lj, pi, pj, sDi,
-                                                          sDj, flag_bit(bm, li2, lj));
-                            const float v = pv.v;
-                            const uint32_t cflag = pv.computed ? 0x80000000u : 0u;
-                            if (v <= k1I[li2] || (!pv.computed && v <= k2I[li2])) {
-                                const int pos = atomicAdd(&A.cnt[gi], 1);
-                                if (pos < A.R) A.rec[(int64_t)gi * A.R + pos] = make_uint2(__float_as_uint(v), (uint32_t)gj | cflag);
-                            }
-                            if (v <= k1J[lj] || (!pv.computed && v <= k2J[lj])) {
-                                const int pos = atomicAdd(&A.cnt[gj], 1);
-                                if (pos < A.R) A.rec[(int64_t)gj * A.R + pos] = make_uint2(__float_as_uint(v), (uint32_t)gi | cflag);
-                            }
-                        }
-                    }
-                }
-            }
-            __syncwarp();
-            if (lane == 0) *qcnt = 0;
-            __syncwarp();
+            drain(qn);
         }
+    }
+    if (A.counters && tid == 0) {
+        atomicAdd(&A.counters[0], (unsigned long long)n_culled);
+        atomicAdd(&A.counters[1], (unsigned long long)n_with_entries);
+        atomicAdd(&A.counters[2], (unsigned long long)n_computed);
+        atomicAdd(&A.counters[3], (unsigned long long)n_reduced);
     }
 }
 
@@ -482,7 +545,8 @@ int launch_thresh_pairs(annb_ctx *c, ThreshPairArgs &A)
 {
     const size_t lim = 227 * 1024;
     const size_t base = (size_t)4 * A.V.na * SROW * 4 + 4 * TILE * sizeof(PointMeta) + TS_BYTES +
-                        2 * TL_CAP * 4 + 4 * sizeof(TileDesc) + 8 * TILE * 4 + sizeof(TileModel) + SWW * 4 + 64;
+                        2 * TL_CAP * 4 + 4 * sizeof(TileDesc) + 8 * TILE * 4 + sizeof(TileModel) + SWW * 4 + 64 +
+                        sizeof(Outliers) + 64;  // (+ the static shared variables of the kernel)
     ANNB_REQUIRE(base + (size_t)SWW * (QROW + 32) * sizeof(Survivor) <= lim, ANNB_ERANGE,
                  "threshold pair sweep needs %zu bytes of shared memory (n_anchors=%d)",
                  base + (size_t)SWW * (QROW + 32) * sizeof(Survivor), A.V.na);

@@ -271,11 +271,17 @@ def test_tile_pruning_is_exact(monkeypatch, kind):
     monkeypatch.setenv("ANNB_NO_CULL", "1")
     b = Annchor(X, metric, **kw).fit()
     monkeypatch.delenv("ANNB_NO_CULL")
-    assert a.evals == b.evals and a.n_forced == b.n_forced and a.n_tightened == b.n_tightened
-    assert np.array_equal(a.neighbor_graph[0], b.neighbor_graph[0])
-    assert np.array_equal(a.neighbor_graph[1], b.neighbor_graph[1])
-    assert np.array_equal(a.A, b.A)
-    np.testing.assert_array_equal(a.D, b.D)
+    # ... and with whole-tile pruning only (no reduced tile mode: outlier rows / store entries of a tile whose
+    # bulk cannot pass are computed alone)
+    monkeypatch.setenv("ANNB_NO_REDUCED", "1")
+    c = Annchor(X, metric, **kw).fit()
+    monkeypatch.delenv("ANNB_NO_REDUCED")
+    for o in (b, c):
+        assert a.evals == o.evals and a.n_forced == o.n_forced and a.n_tightened == o.n_tightened
+        assert np.array_equal(a.neighbor_graph[0], o.neighbor_graph[0])
+        assert np.array_equal(a.neighbor_graph[1], o.neighbor_graph[1])
+        assert np.array_equal(a.A, o.A)
+        np.testing.assert_array_equal(a.D, o.D)
 
 
 def test_spatial_renumbering_keeps_the_result_quality(monkeypatch):
