@@ -89,6 +89,7 @@ _SIGS = {
     "annb_index_export_tightened": [_P, _P, _P, _P, _P, _I64, C.POINTER(_I64)],
     "annb_index_import_dev": [_P, _I32, _P, _P, _P, _P, _I64],
     "annb_bruteforce_knn": [_P, _P, _I32, _I64, _P, _P],
+    "annb_nearest_enemies": [_P, _P, _I32, _P, _I64, _P, _P],
     "annb_pair_dists_query": [_P, _P, _I32, _I64, _P, _I64, _P],
     "annb_index_query": [_P, _P, _I64, _I64, C.c_double, _P, _P, C.POINTER(_I64)],
     "annb_numba_rng_new": [C.c_uint32, _PP],

@@ -499,6 +499,58 @@ class Annchor:
         _, first = np.unique(r * np.int64(n) + c, return_index=True)
         return coo_matrix((v[first], (r[first], c[first])), shape=(n, n)).todok()
 
+    def get_nearest_enemies(self, y, nn=3, loc_min=100):
+        """Nearest-enemy graph (annchor/annchor.py:685-786): for every point the ``nn`` nearest points carrying a
+        different label, stored in ``self.nearest_enemy_graph = (ngi int64 (nx, nn), ngd float64 (nx, nn))``.
+
+        The reference approximates this graph from its materialised candidate state (enemy locality ``loc_min``,
+        regression predictions, the 50 best candidates per row evaluated exactly).  The streaming index keeps no
+        per-pair state, so the graph is computed EXACTLY here, by exhaustive evaluation with the metric kernels
+        (annb_nearest_enemies) -- an O(nx^2) pass meant for the data-set sizes the reference's own O(nx^2)-memory
+        implementation can handle.  ``loc_min`` is accepted for signature compatibility."""
+        y = np.asarray(y)
+        nx = self.nx
+        assert len(y) == nx, "Label dimension mismatch: len(y)=%d, len(X)=%d" % (len(y), nx)
+        labels, inv, counts = np.unique(y, return_inverse=True, return_counts=True)
+        assert len(labels) > 1, "Data must have more than one label"
+        assert np.all(counts >= nn), "At least one label occurs fewer times than specified nn=%d" % nn
+        self.nearest_enemy_graph = self._dataset.nearest_enemies(inv.astype(np.int32), nn)
+        self.evals += nx * (nx - 1) // 2
+        return self.nearest_enemy_graph
+
+    def alpha_rss(self, y, dne=None, alpha=0):
+        """annchor/annchor.py:921-940: greedy relaxed selective subset -- visit the points by increasing nearest
+        enemy distance and keep a point unless an already kept point is closer than dne / (1 + alpha).  The
+        distances to the kept points are evaluated on the device in blocks (same decisions as the reference's
+        one-point-at-a-time loop: a block member only ever needs the kept points and earlier block members)."""
+        if dne is None:
+            if not hasattr(self, "nearest_enemy_graph"):
+                self.get_nearest_enemies(y)
+            dne = self.nearest_enemy_graph[1][:, 0]
+        dne = np.asarray(dne, dtype=np.float64)
+        ix = np.argsort(dne)
+        alpha_dne = dne / (1 + alpha)
+        rss = [int(ix[0])]
+        self.rssDs = {}
+        B = 256
+        for b0 in range(0, len(ix), B):
+            blk = ix[b0:b0 + B]
+            old = np.array(rss, dtype=np.int64)
+            both = np.concatenate([old, blk])
+            IJ = np.stack([np.repeat(blk, both.shape[0]), np.tile(both, blk.shape[0])], 1)
+            Dm = self._dataset.pair_dists(IJ).reshape(blk.shape[0], both.shape[0])
+            self.evals += IJ.shape[0]
+            pos_in_both = {int(v): old.shape[0] + q for q, v in enumerate(blk)}
+            cols = list(range(old.shape[0]))  # columns of Dm that are kept points
+            for q, i in enumerate(blk):
+                ds = Dm[q, cols]
+                self.rssDs[int(i)] = ds
+                dnn = np.min(ds)
+                if (dnn > alpha_dne[i]) or np.isclose(dnn, alpha_dne[i]):
+                    rss.append(int(i))
+                    cols.append(pos_in_both[int(i)])
+        return np.array(rss)
+
     def query(self, Q, nn=15, p_work=0.3, get_exact_query_ijs=None):
         """Query new data against the fitted index (annchor/annchor.py:643-683): returns
         (ngi int64 (len(Q), nn), ngd float64 (len(Q), nn)), the nn approximate nearest points of X per

@@ -139,6 +139,17 @@ class Dataset:
                                       ptr(out)))
         return out
 
+    def nearest_enemies(self, labels, nn):
+        """Exact nearest-enemy graph (annb_nearest_enemies): the nn nearest items with a different label."""
+        lab = as_c(np.asarray(labels), np.int32)
+        if lab.shape != (self.n,):
+            raise ValueError("labels must have one entry per item")
+        idx = np.empty((self.n, int(nn)), dtype=np.int64)
+        dist = np.empty((self.n, int(nn)), dtype=np.float64)
+        check(self._L.annb_nearest_enemies(self.ctx.handle, self.handle, self.metric, ptr(lab), int(nn), ptr(idx),
+                                           ptr(dist)))
+        return idx, dist
+
     def gather(self, order):
         """A new Dataset holding the items in the given order (device to device, annb_dataset_gather)."""
         order = as_c(order, np.int64)

@@ -539,8 +539,9 @@ void emit_row(int64_t row, std::vector<Cand> &c, int64_t k, int64_t *idx, double
 }
 
 // exact brute force of a set of rows through the pair kernels, in chunks of rows
+// labels != nullptr: nearest ENEMIES -- only columns with another label take part, k columns, no self column
 int exact_rows(annb_ctx *c, const annb_dataset *ds, int metric, const std::vector<int64_t> &rows, bool contiguous,
-               int64_t k, int64_t *idx, double *dist)
+               int64_t k, int64_t *idx, double *dist, const int32_t *labels = nullptr)
 {
     const int64_t n = ds->n;
     const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>((int64_t)rows.size(), (1 << 25) / n));
@@ -578,6 +579,17 @@ int exact_rows(annb_ctx *c, const annb_dataset *ds, int metric, const std::vecto
         for (int64_t q = 0; q < m; ++q) {
             const int64_t row = rows[r0 + q];
             cand.clear();
+            if (labels) {
+                for (int64_t j = 0; j < n; ++j)
+                    if (labels[j] != labels[row]) cand.push_back({h[(size_t)q * n + j], j});
+                const size_t want = (size_t)std::min<int64_t>(k, (int64_t)cand.size());
+                std::partial_sort(cand.begin(), cand.begin() + want, cand.end());
+                for (int64_t t = 0; t < k; ++t) {
+                    idx[row * k + t] = (size_t)t < want ? cand[t].id : -1;
+                    dist[row * k + t] = (size_t)t < want ? cand[t].d : INFINITY;
+                }
+                continue;
+            }
             for (int64_t j = 0; j < n; ++j)
                 if (j != row) cand.push_back({h[(size_t)q * n + j], j});
             emit_row(row, cand, k, idx, dist);
@@ -597,6 +609,21 @@ int exact_rows(annb_ctx *c, const annb_dataset *ds, int metric, const std::vecto
 static double bf_error_bound(double m2, int K, double scale)
 {
     return scale * m2 * (std::ldexp(1.0, -15) + K * std::ldexp(1.0, -22)) + 4.0 * m2 * std::ldexp(1.0, -22);
+}
+
+// Exact nearest-enemy graph (annchor/annchor.py:685-786 computes an approximation of it from the fitted state): for
+// every item the nn nearest items carrying a DIFFERENT label, by exhaustive evaluation with the metric kernels.
+ANNB_API int annb_nearest_enemies(annb_ctx *c, const annb_dataset *ds, int metric, const int32_t *labels, int64_t nn,
+                                  int64_t *idx, double *dist)
+{
+    TraceScope _ts("annb_nearest_enemies");
+    ANNB_REQUIRE(c && ds && labels && idx && dist, ANNB_EINVAL, "NULL argument");
+    ANNB_TRY(check_metric(ds, metric));
+    ANNB_REQUIRE(nn >= 1 && nn < ds->n, ANNB_EINVAL, "nn=%lld outside [1, n)", (long long)nn);
+    ANNB_CUDA(cudaSetDevice(c->device));
+    std::vector<int64_t> rows(ds->n);
+    std::iota(rows.begin(), rows.end(), 0);
+    return exact_rows(c, ds, metric, rows, true, nn, idx, dist, labels);
 }
 
 ANNB_API int annb_bruteforce_knn(annb_ctx *c, const annb_dataset *ds, int metric, int64_t k, int64_t *idx,

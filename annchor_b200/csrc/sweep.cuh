@@ -427,6 +427,33 @@ __device__ __forceinline__ void tile_from_index(int64_t t, int T, int &ti, int &
 // MODE 1 (pair thresholds): pred <= cut; MODE 2 (row thresholds): pred < cut -- with cut <= cutmax and
 // pred >= the bound below.  The bound and the margin are taken per regression bin the tile pair's s2
 // interval overlaps (the error label of a pair is its bin b, or b + 1 when s2 sits exactly on the edge).
+// per regression bin the interval [s_lo, s_hi] of 2 * dad overlaps: lower bound of the clipped prediction from the
+// interval ends the coefficient signs select, compared with the cut the way phase 1 compares a pair
+template <int MODE>
+__device__ __forceinline__ bool bins_can_pass(const Model &M, float lbmin, float lbmax, float ubmin, float ubmax,
+                                              float s_lo, float s_hi, float cutmax, const float *margin)
+{
+    bool any = false;
+    for (int b = 0; b < M.nb; ++b) {
+        // bin b holds e2[b] < s2 <= e2[b+1]  (e2[0] = -inf, e2[nb] = +inf; reg_bin2)
+        const float blo = b == 0 ? -INFINITY : M.e2[b], bhi = b + 1 < M.nb ? M.e2[b + 1] : INFINITY;
+        if (!(s_hi > blo && s_lo <= bhi)) continue;
+        const float c0 = M.c0[b], c1 = M.c1[b], cz = 0.5f * M.c2[b];
+        const float y = fmaf(c0 >= 0.0f ? lbmin : lbmax, c0,
+                             fmaf(c1 >= 0.0f ? ubmin : ubmax, c1, fmaf(cz >= 0.0f ? s_lo : s_hi, cz, M.ic[b])));
+        const float p = fminf(fmaxf(y, lbmin), ubmin);  // lower bound of the clipped prediction in this bin
+        if (MODE == 0) {
+            const float mg = fminf(margin[b], margin[b + 1 < M.nb ? b + 1 : b]);
+            any |= !(cutmax - p <= mg);  // (NaN counts as "can pass")
+        } else if (MODE == 1) {
+            any |= !(p > cutmax);
+        } else {
+            any |= !(p >= cutmax);
+        }
+    }
+    return any;
+}
+
 template <int MODE>
 __device__ __forceinline__ bool tile_can_pass(const View &V, const Model &M, int ti, int tj, float cutmax,
                                               const float *margin /* [MAX_BINS], MODE 0 */)
@@ -467,26 +494,33 @@ __device__ __forceinline__ bool tile_can_pass(const View &V, const Model &M, int
         sjLo = fminf(sjLo, __shfl_xor_sync(0xffffffffu, sjLo, o));
         sjHi = fmaxf(sjHi, __shfl_xor_sync(0xffffffffu, sjHi, o));
     }
-    const float s_lo = siLo + sjLo, s_hi = siHi + sjHi;
-    bool any = false;
-    for (int b = 0; b < M.nb; ++b) {
-        // bin b holds e2[b] < s2 <= e2[b+1]  (e2[0] = -inf, e2[nb] = +inf; reg_bin2)
-        const float blo = b == 0 ? -INFINITY : M.e2[b], bhi = b + 1 < M.nb ? M.e2[b + 1] : INFINITY;
-        if (!(s_hi > blo && s_lo <= bhi)) continue;
-        const float c0 = M.c0[b], c1 = M.c1[b], cz = 0.5f * M.c2[b];
-        const float y = fmaf(c0 >= 0.0f ? lbmin : lbmax, c0,
-                             fmaf(c1 >= 0.0f ? ubmin : ubmax, c1, fmaf(cz >= 0.0f ? s_lo : s_hi, cz, M.ic[b])));
-        const float p = fminf(fmaxf(y, lbmin), ubmin);  // lower bound of the clipped prediction in this bin
-        if (MODE == 0) {
-            const float mg = fminf(margin[b], margin[b + 1 < M.nb ? b + 1 : b]);
-            any |= !(cutmax - p <= mg);  // (NaN counts as "can pass")
-        } else if (MODE == 1) {
-            any |= !(p > cutmax);
-        } else {
-            any |= !(p >= cutmax);
+    return bins_can_pass<MODE>(M, lbmin, lbmax, ubmin, ubmax, siLo + sjLo, siHi + sjHi, cutmax, margin);
+}
+
+// The same question for ONE point (local row l of a staged tile, anchor distances in shared memory) against
+// a whole tile t: can any pair (point, member of t) pass phase 1 through a cut <= `cut`?  Per-thread, no
+// shuffles; the bounds of the point's own coordinates are exact, so this is much sharper than the tile-tile test.
+template <int MODE>
+__device__ __forceinline__ bool point_can_pass(const View &V, const Model &M, const float *__restrict__ sD, int l,
+                                               int cA_l, int t, float cut, const float *margin)
+{
+    const float *lo = V.tb_lo + (int64_t)t * kMaxAnchors, *hi = V.tb_hi + (int64_t)t * kMaxAnchors;
+    const uint64_t cm = V.tb_cm[t];
+    float lbmin = 0.0f, lbmax = 0.0f, ubmin = INFINITY, ubmax = INFINITY, siLo = INFINITY, siHi = -INFINITY;
+    for (int a = 0; a < V.na; ++a) {
+        const float d = sD[a * SROW + l], lj = __ldg(lo + a), hj = __ldg(hi + a);
+        lbmin = fmaxf(lbmin, fmaxf(d - hj, lj - d));
+        lbmax = fmaxf(lbmax, fmaxf(hj - d, d - lj));
+        ubmin = fminf(ubmin, d + lj);
+        ubmax = fminf(ubmax, d + hj);
+        if ((cm >> a) & 1ull) {  // D[point, cA(j)] for the closest anchors that occur in t
+            siLo = fminf(siLo, d);
+            siHi = fmaxf(siHi, d);
         }
     }
-    return any;
+    // D[j, cA(point)]: the tile's interval on the point's own closest anchor
+    const float sjLo = __ldg(lo + cA_l), sjHi = __ldg(hi + cA_l);
+    return bins_can_pass<MODE>(M, lbmin, lbmax, ubmin, ubmax, siLo + sjLo, siHi + sjHi, cut, margin);
 }
 
 // ---- reduced tile mode -------------------------------------------------------------------------

@@ -168,7 +168,10 @@ __global__ void __launch_bounds__(SWT, 1) score_sweep_kernel(const __grid_consta
                 if (can) {
                     const int l = tid & (TILE - 1);
                     const float myc = tid < TILE ? tI[l] : tJ[l];
-                    const bool mine = tile_can_pass<0>(V, M, ti, tj, myc, A.efloor) && tid < 2 * TILE;
+                    // ... and, for those, the sharper test of the point itself against the other tile
+                    const bool mine = tile_can_pass<0>(V, M, ti, tj, myc, A.efloor) && tid < 2 * TILE &&
+                                      (tid < TILE ? point_can_pass<0>(V, M, sDi, l, sMi[l].cA, tj, myc, A.efloor)
+                                                  : point_can_pass<0>(V, M, sDj, l, sMj[l].cA, ti, myc, A.efloor));
                     reduced = collect_outliers(&s_out, mine);
                 } else {
                     no_outliers(&s_out);

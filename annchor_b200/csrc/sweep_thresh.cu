@@ -412,7 +412,10 @@ __global__ void __launch_bounds__(SWT, 1) thresh_pairs_kernel(const __grid_const
                 if (can) {
                     const int l = tid & (TILE - 1);
                     const float myc = tid < TILE ? fmaxf(k1I[l], k2I[l]) : fmaxf(k1J[l], k2J[l]);
-                    const bool mine = tile_can_pass<1>(V, M, ti, tj, myc, nullptr) && tid < 2 * TILE;
+                    // ... and, for those, the sharper test of the point itself against the other tile
+                    const bool mine = tile_can_pass<1>(V, M, ti, tj, myc, nullptr) && tid < 2 * TILE &&
+                                      (tid < TILE ? point_can_pass<1>(V, M, sDi, l, sMi[l].cA, tj, myc, nullptr)
+                                                  : point_can_pass<1>(V, M, sDj, l, sMj[l].cA, ti, myc, nullptr));
                     reduced = collect_outliers(&s_out, mine);
                 } else {
                     no_outliers(&s_out);

@@ -359,6 +359,11 @@ def run_ours(args, w):
                      "frac": issue_achieved / issue_peak, "traffic": traffic,
                      "kernel": "score_sweep_kernel", "pairs_per_launch": sw_pairs, "ms_per_launch": sw_ms,
                      "algorithmic_ops_per_pair": ops_per_pair,
+                     "pairs_covered_per_launch": w["N"] * (w["N"] - 1) / 2.0 / world,
+                     "note": "pairs_per_launch counts only the pairs whose bounds / prediction were computed; the "
+                             "launch also decides, per tile pair, that the rest of pairs_covered_per_launch cannot "
+                             "pass (tile-level bounds, DESIGN.md section 3) -- that time is inside ms_per_launch, so "
+                             "frac understates the bounds loop itself (ncu: 44 % issue-active)",
                      "peak_source": "148 SMs x 128 FP32 lanes x SM clock under load (%.0f MHz): one lane-op per "
                                     "lane and clock; FADD / FMNMX have no 2x FMA credit" % (sm_clk / 1e6),
                      "launches_averaged": n_sw,

@@ -282,6 +282,11 @@ int annb_index_import_dev(annb_index *ix, int kind, const int32_t *i_dev, const 
 int annb_bruteforce_knn(annb_ctx *ctx, const annb_dataset *ds, int metric, int64_t k,
                         int64_t *idx, double *dist);
 
+/* exact nearest-enemy graph (annchor/annchor.py:685-786 approximates it from the fitted state): the nn nearest
+ * items with a different label, idx int64 (n,nn), dist float64 (n,nn); -1 / +inf where fewer enemies exist */
+int annb_nearest_enemies(annb_ctx *ctx, const annb_dataset *ds, int metric, const int32_t *labels, int64_t nn,
+                         int64_t *idx, double *dist);
+
 /* host helper: numba's in-@njit np.random.seed + np.random.choice(replace=False)
  * (annchor/utils.py:555-557,572) so the materialised sampler reproduces the reference's draw */
 int annb_numba_rng_new(uint32_t seed, void **state);
