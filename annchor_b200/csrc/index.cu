@@ -1526,6 +1526,7 @@ ANNB_API int annb_index_create(annb_ctx *c, const annb_dataset *ds, int metric,
     ANNB_CUDA(cudaMemsetAsync(ix->tl_ptr.p, 0, (size_t)(ix->NT + 1) * 8, c->stream));  // every tile list empty
     ix->cull_enabled = getenv("ANNB_NO_CULL") == nullptr;  // test knob: sweeps without tile-level pruning
     ix->reduced_enabled = getenv("ANNB_NO_REDUCED") == nullptr;  // test knob: pruning without the reduced tile mode
+    ix->scan_enabled = getenv("ANNB_NO_SCAN") == nullptr;        // test knob: pruning decided tile by tile, after the loads
     ANNB_TRY(hash_alloc(ix, 1 << 16));
     *out = ix;
     return ANNB_OK;
@@ -1548,7 +1549,7 @@ ANNB_API int annb_index_destroy(annb_index *ix)
     if (!ix) return ANNB_OK;
     cudaSetDevice(ix->ctx->device);
     cudaStreamSynchronize(ix->ctx->stream);
-    DevBuf *all[] = {&ix->A_dev, &ix->D64, &ix->D32, &ix->Dpm, &ix->meta, &ix->scratch, &ix->htab, &ix->tl_ptr, &ix->tl_cnt, &ix->tl_code, &ix->tl_a, &ix->tl_b, &ix->scan_tmp, &ix->tb_lo, &ix->tb_hi, &ix->tb_cm, &ix->order_dev,
+    DevBuf *all[] = {&ix->A_dev, &ix->D64, &ix->D32, &ix->Dpm, &ix->meta, &ix->scratch, &ix->htab, &ix->tl_ptr, &ix->tl_cnt, &ix->tl_code, &ix->tl_a, &ix->tl_b, &ix->scan_tmp, &ix->tb_lo, &ix->tb_hi, &ix->tb_cm, &ix->tb_cutmax, &ix->order_dev,
                      &ix->errs_dev, &ix->rank_dev, &ix->thresh, &ix->l2val, &ix->l2id, &ix->hist,
                      &ix->counters, &ix->emit_key, &ix->emit_lvl, &ix->sel_i, &ix->sel_j, &ix->nxt_i,
                      &ix->nxt_j, &ix->tiehist, &ix->tiekeys, &ix->pool_key, &ix->pool_dad, &ix->t0,
@@ -1970,6 +1971,12 @@ static int run_thresh(annb_index *ix, int k2)
         P.world = ix->P.world;
         P.counters = nullptr;
         P.reduced = (P.V.cull && ix->reduced_enabled) ? 1 : 0;
+        P.tcmax = nullptr;
+        if (P.V.cull && ix->scan_enabled) {
+            ANNB_TRY(ix->tb_cutmax.ensure((size_t)P.V.T * 4));
+            ANNB_TRY(launch_tile_cutmax(c, P.cut1, P.cut2, P.V.T, ix->tb_cutmax.as<float>()));
+            P.tcmax = ix->tb_cutmax.as<float>();
+        }
         if (const char *dump = getenv("ANNB_DUMP_TILES")) {
             // debug: what the tile test of this sweep sees (analysed offline, tools/tile_prune_replay.py)
             static int dump_no = 0;
@@ -2009,11 +2016,11 @@ static int run_thresh(annb_index *ix, int k2)
         }
         ANNB_TRY(launch_thresh_pairs(c, P));
         if (g_trace) {
-            unsigned long long tc[4];
-            ANNB_CUDA(cudaMemcpyAsync(tc, ix->counters.p, 32, cudaMemcpyDeviceToHost, c->stream));
+            unsigned long long tc[6];
+            ANNB_CUDA(cudaMemcpyAsync(tc, ix->counters.p, 48, cudaMemcpyDeviceToHost, c->stream));
             ANNB_CUDA(cudaStreamSynchronize(c->stream));
-            fprintf(stderr, "[annb-trace]   thresh pair sweep: tiles pruned %llu, reduced %llu, computed in full %llu (with store entries %llu) of %lld\n",
-                    tc[0], tc[3], tc[2], tc[1], (long long)ix->NT);
+            fprintf(stderr, "[annb-trace]   thresh pair sweep: tiles pruned %llu, reduced %llu (%llu with nothing to do, %llu rows), computed in full %llu (with store entries %llu) of %lld\n",
+                    tc[0], tc[3], tc[4], tc[5], tc[2], tc[1], (long long)ix->NT);
         }
         ix->pairs_swept += n * (n - 1) / 2 / ix->P.world;
         ix->sweeps += 1;
@@ -2252,6 +2259,12 @@ static int run_score(annb_index *ix, int floor_level, uint64_t floor_mix_thr, in
     A.rank = ix->P.rank;
     A.world = ix->P.world;
     A.reduced = (A.V.cull && ix->reduced_enabled) ? 1 : 0;
+    A.tcmax = nullptr;
+    if (A.V.cull && ix->scan_enabled) {
+        ANNB_TRY(ix->tb_cutmax.ensure((size_t)A.V.T * 4));
+        ANNB_TRY(launch_tile_cutmax(c, A.thresh, nullptr, A.V.T, ix->tb_cutmax.as<float>()));
+        A.tcmax = ix->tb_cutmax.as<float>();
+    }
     ANNB_CUDA(cudaMemsetAsync(ix->hist.p, 0, (size_t)ix->nlevels * 4, c->stream));
     ANNB_CUDA(cudaMemsetAsync(ix->counters.p, 0, 64, c->stream));
     ANNB_CUDA(cudaEventRecord(c->ev0, c->stream));

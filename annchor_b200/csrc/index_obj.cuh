@@ -27,6 +27,7 @@ struct annb_index {
     // per-tile entry lists derived from the hash map (rebuilt lazily before a sweep)
     DevBuf tl_ptr, tl_cnt, tl_code, tl_a, tl_b, scan_tmp;
     // per-tile anchor-distance intervals and closest-anchor sets (tile-level pruning in the sweeps)
+    DevBuf tb_cutmax;  // [T] largest cut per tile of the sweep about to run (scan-ahead)
     DevBuf tb_lo, tb_hi, tb_cm, order_dev;  // order_dev[new] = old id (int32) when the index is renumbered
     bool ordered = false;  // the points were renumbered by annb_index_spatial_order (coherent tiles)
     bool tl_dirty = false;
@@ -114,6 +115,7 @@ struct annb_index {
     }
     bool cull_enabled = true;
     bool reduced_enabled = true;  // reduced tile mode of the sweeps (sweep.cuh); ANNB_NO_REDUCED turns it off
+    bool scan_enabled = true;     // scan-ahead over the tile sequence; ANNB_NO_SCAN turns it off
     int64_t n_not_computed() const { return n_candidates - n_anchor_pairs - n_known; }
 };
 

@@ -142,6 +142,13 @@ __device__ __forceinline__ void load_tile_codes(const View &V, const TileDesc *d
     for (int e = threadIdx.x; e < (int)cnt; e += blockDim.x) cp_async4(codes + e, V.tl_code + base + e);
 }
 
+__device__ __forceinline__ void load_tile_codes(const View &V, long long base, long long end, uint32_t *codes)
+{
+    const long long cnt = end - base;
+    if (cnt > TL_CAP) return;
+    for (int e = threadIdx.x; e < (int)cnt; e += blockDim.x) cp_async4(codes + e, V.tl_code + base + e);
+}
+
 // `bf` is the flag bitmap phase 1 reads.  Upper-triangle sweeps pass bf == ts.bm (mode 0).  A row sweep
 // keeps a separate row-oriented copy: mode 1 = transposed (row tile below the column tile), 2 = both
 // orientations (diagonal tile), 3 = same orientation (row tile above the column tile).
@@ -507,6 +514,7 @@ __device__ __forceinline__ bool point_can_pass(const View &V, const Model &M, co
     const float *lo = V.tb_lo + (int64_t)t * kMaxAnchors, *hi = V.tb_hi + (int64_t)t * kMaxAnchors;
     const uint64_t cm = V.tb_cm[t];
     float lbmin = 0.0f, lbmax = 0.0f, ubmin = INFINITY, ubmax = INFINITY, siLo = INFINITY, siHi = -INFINITY;
+#pragma unroll 6
     for (int a = 0; a < V.na; ++a) {
         const float d = sD[a * SROW + l], lj = __ldg(lo + a), hj = __ldg(hi + a);
         lbmin = fmaxf(lbmin, fmaxf(d - hj, lj - d));

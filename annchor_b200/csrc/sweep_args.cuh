@@ -39,6 +39,7 @@ struct ThreshPairArgs {
     unsigned long long *counters;  // trace (may be nullptr): [0] tiles pruned, [1] tiles with store entries, [2] tiles
                                    // computed in full, [3] tiles in reduced mode
     int reduced;         // reduced tile mode on (sweep.cuh)
+    const float *tcmax;  // [T] largest cut of each tile (launch_tile_cutmax) or nullptr: no scan-ahead
 };
 
 struct ScoreArgs {
@@ -68,6 +69,7 @@ struct ScoreArgs {
     int q_stride;             // 1 = every tile; s > 1 = pilot over every s-th tile
     int rank, world;
     int reduced;              // reduced tile mode on (sweep.cuh)
+    const float *tcmax;       // [T] largest threshold of each tile or nullptr: no scan-ahead
 };
 
 struct SampleArgs {
@@ -89,6 +91,7 @@ struct SampleArgs {
 
 int launch_thresh_sweep(annb_ctx *c, ThreshArgs &A);
 int launch_thresh_pairs(annb_ctx *c, ThreshPairArgs &A);
+int launch_tile_cutmax(annb_ctx *c, const float *cutA, const float *cutB, int T, float *out);
 int launch_thresh_select(annb_ctx *c, const uint2 *rec, const int32_t *cnt, int R, int64_t n, int k1, int k2,
                          int n_src, float *thresh, float *l1out, float *l2val, int32_t *l2id);
 int launch_score_sweep(annb_ctx *c, ScoreArgs &A);

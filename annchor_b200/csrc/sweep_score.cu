@@ -111,51 +111,92 @@ __global__ void __launch_bounds__(SWT, 1) score_sweep_kernel(const __grid_consta
     auto tile_of = [&](int64_t m, int &ti, int &tj) { tile_from_index(tile_no(m), V.T, ti, tj); };
     TileStore ts;
     ts.init(sTS);
-    if (m0 < m1) {
-        // descriptors of the first two tiles directly, everything later through cp.async one tile ahead
-        if (tid < 2 && m0 + tid < m1) {
-            const int64_t t = tile_no(m0 + tid);
-            sDesc[tid].base = V.tl_ptr[t];
-            sDesc[tid].end = V.tl_ptr[t + 1];
+    // Scan-ahead (see thresh_pairs_kernel): the tile sequence is filtered before anything is loaded -- no store
+    // entry and the tile-level test fails for the largest threshold of the two tiles (A.tcmax) => skipped without
+    // touching the tile's anchor-distance rows; eight candidates are tested at a time, one per warp.
+    __shared__ unsigned char s_flag[2][SWW];
+    int scan_round = 0;
+    const bool scan_on = V.cull && A.ef_min > -INFINITY && A.tcmax != nullptr;
+    auto next_surviving = [&](int64_t start) -> int64_t {
+        if (!scan_on) return start;
+        for (int64_t base = start; base < m1; base += SWW, ++scan_round) {
+            const int64_t cnd = base + warp;
+            bool surv = false;
+            if (cnd < m1) {
+                int ci, cj;
+                const int64_t t = tile_no(cnd);
+                tile_from_index(t, V.T, ci, cj);
+                surv = ci == cj || V.tl_ptr[t + 1] > V.tl_ptr[t] ||
+                       tile_can_pass<0>(V, M, ci, cj, fmaxf(A.tcmax[ci], A.tcmax[cj]), A.efloor);
+            }
+            if (lane == 0) s_flag[scan_round & 1][warp] = surv ? 1 : 0;
+            __syncthreads();
+            int first = -1;
+#pragma unroll
+            for (int w = SWW - 1; w >= 0; --w)
+                if (s_flag[scan_round & 1][w]) first = w;
+            if (first >= 0) {
+                n_culled += first;
+                ++scan_round;
+                return base + first;
+            }
+            n_culled += (int)min((int64_t)SWW, m1 - base);
         }
-        __syncthreads();
+        return m1;
+    };
+    // m = the tile being computed, mnext = the one being prefetched, mnn = found while mnext's loads are in flight
+    int64_t m = next_surviving(m0), mnext = m < m1 ? next_surviving(m + 1) : m1, mnn = m1;
+    int k = 0;  // surviving tiles so far: buffer and descriptor slot
+    if (m < m1) {
+        const int64_t t = tile_no(m);
+        const long long e0 = V.tl_ptr[t], e1 = V.tl_ptr[t + 1];
+        if (tid == 0) {
+            sDesc[0].base = e0;
+            sDesc[0].end = e1;
+        }
         int ti, tj;
-        tile_of(m0, ti, tj);
+        tile_from_index(t, V.T, ti, tj);
         load_point_tile(V, ti, sD0i, sM0i);
         load_point_tile(V, tj, sD0j, sM0j);
-        load_tile_codes(V, &sDesc[0], sCode);
+        load_tile_codes(V, e0, e1, sCode);
         if (tid < TILE) {
             thI[tid] = A.thresh[(int64_t)ti * TILE + tid];
             thJ[tid] = A.thresh[(int64_t)tj * TILE + tid];
         }
         cp_async_commit();
     }
-    for (int64_t m = m0; m < m1; ++m) {
-        const int buf = (int)((m - m0) & 1);
+    for (; m < m1; m = mnext, mnext = mnn, ++k) {
+        const int buf = k & 1;
         int ti, tj;
         tile_of(m, ti, tj);
         cp_async_wait_all();
         __syncthreads();
-        if (m + 1 < m1) {
+        if (mnext < m1) {
             int ni, nj;
-            tile_of(m + 1, ni, nj);
+            const int64_t t = tile_no(mnext);
+            tile_from_index(t, V.T, ni, nj);
+            const long long e0 = V.tl_ptr[t], e1 = V.tl_ptr[t + 1];
+            if (tid == 0) {
+                sDesc[(k + 1) & 3].base = e0;
+                sDesc[(k + 1) & 3].end = e1;
+            }
             load_point_tile(V, ni, buf ? sD0i : sD1i, buf ? sM0i : sM1i);
             load_point_tile(V, nj, buf ? sD0j : sD1j, buf ? sM0j : sM1j);
-            load_tile_codes(V, &sDesc[(m + 1 - m0) & 3], sCode + (buf ^ 1) * TL_CAP);
-            if (m + 2 < m1) load_tile_desc(V, tile_no(m + 2), &sDesc[(m + 2 - m0) & 3]);
+            load_tile_codes(V, e0, e1, sCode + (buf ^ 1) * TL_CAP);
             if (tid < TILE) {
                 thI[(buf ^ 1) * TILE + tid] = A.thresh[(int64_t)ni * TILE + tid];
                 thJ[(buf ^ 1) * TILE + tid] = A.thresh[(int64_t)nj * TILE + tid];
             }
             cp_async_commit();
         }
+        mnn = mnext < m1 ? next_surviving(mnext + 1) : m1;
         const float *sDi = buf ? sD1i : sD0i, *sDj = buf ? sD1j : sD0j;
         const PointMeta *sMi = buf ? sM1i : sM0i, *sMj = buf ? sM1j : sM0j;
         const float *tI = thI + buf * TILE, *tJ = thJ + buf * TILE;
         // tile-level pruning: no store entry in the tile and even the smallest possible prediction
         // cannot reach the floor level for the largest threshold of the two tiles (the same test
         // `cut - pred > margin` phase 1 applies per pair, at the tile's extremes)
-        const bool has_entries = sDesc[(m - m0) & 3].end != sDesc[(m - m0) & 3].base;
+        const bool has_entries = sDesc[k & 3].end != sDesc[k & 3].base;
         bool reduced = false;
         if (V.cull && A.ef_min > -INFINITY && ti != tj) {
             const float cutmax = fmaxf(tile_max128(tI), tile_max128(tJ));
@@ -179,7 +220,7 @@ __global__ void __launch_bounds__(SWT, 1) score_sweep_kernel(const __grid_consta
                 }
             }
         }
-        build_tile_store(V, ts, &sDesc[(m - m0) & 3], sCode + buf * TL_CAP, sBm, 0);
+        build_tile_store(V, ts, &sDesc[k & 3], sCode + buf * TL_CAP, sBm, 0);
         const uint32_t *bm = sBm;
         // ---- phase 2: drain the warp's queue, one survivor per lane ----
         auto drain = [&](int qn) {
@@ -247,7 +288,7 @@ __global__ void __launch_bounds__(SWT, 1) score_sweep_kernel(const __grid_consta
         if (reduced) {
             // outlier rows / columns and store entries only, one pair per thread and round; the per-pair test is the
             // one phase 1 of the full tile applies (same expressions, same rounding)
-            const TileDesc *dp = &sDesc[(m - m0) & 3];
+            const TileDesc *dp = &sDesc[k & 3];
             const int n_items = (s_out.n_i + s_out.n_j) * TILE + (int)(dp->end - dp->base);
             const uint32_t thr_hi_r = (uint32_t)(A.floor_mix_thr >> 32);
             for (int base = 0; base < n_items; base += SWT) {

@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(SWT, 1) thresh_pairs_kernel(const __grid_const
     const bool l2on = A.cut2 != nullptr;
     build_tile_model(M, tm);
     if (lane == 0) *qcnt = 0;
-    unsigned n_culled = 0, n_with_entries = 0, n_computed = 0, n_reduced = 0;
+    unsigned n_culled = 0, n_with_entries = 0, n_computed = 0, n_reduced = 0, n_reduced_empty = 0, n_reduced_rows = 0;
     __shared__ Outliers s_out;
 
     const int64_t NT = (int64_t)V.T * (V.T + 1) / 2;
@@ -362,44 +362,86 @@ __global__ void __launch_bounds__(SWT, 1) thresh_pairs_kernel(const __grid_const
     };
     TileStore ts;
     ts.init(sTS);
-    if (m0 < m1) {
-        if (tid < 2 && m0 + tid < m1) {
-            const int64_t t = tile_no(m0 + tid);
-            sDesc[tid].base = V.tl_ptr[t];
-            sDesc[tid].end = V.tl_ptr[t + 1];
+    // Scan-ahead: the tile sequence is filtered BEFORE anything is loaded.  A tile pair that holds no store entry and
+    // fails the tile-level test against the largest cut of its two tiles (A.tcmax, one value per tile) is skipped
+    // without touching its anchor-distance rows; the eight warps test eight consecutive candidates at a time.
+    __shared__ unsigned char s_flag[2][SWW];
+    int scan_round = 0;
+    const bool scan_on = V.cull && V.is_metric && A.tcmax != nullptr;
+    auto next_surviving = [&](int64_t start) -> int64_t {
+        if (!scan_on) return start;
+        for (int64_t base = start; base < m1; base += SWW, ++scan_round) {
+            const int64_t cnd = base + warp;
+            bool surv = false;
+            if (cnd < m1) {
+                int ci, cj;
+                const int64_t t = tile_no(cnd);
+                tile_from_index(t, V.T, ci, cj);
+                surv = ci == cj || V.tl_ptr[t + 1] > V.tl_ptr[t] ||
+                       tile_can_pass<1>(V, M, ci, cj, fmaxf(A.tcmax[ci], A.tcmax[cj]), nullptr);
+            }
+            if (lane == 0) s_flag[scan_round & 1][warp] = surv ? 1 : 0;
+            __syncthreads();
+            int first = -1;
+#pragma unroll
+            for (int w = SWW - 1; w >= 0; --w)
+                if (s_flag[scan_round & 1][w]) first = w;
+            if (first >= 0) {
+                n_culled += first;
+                ++scan_round;
+                return base + first;
+            }
+            n_culled += (unsigned)min((int64_t)SWW, m1 - base);
         }
-        __syncthreads();
+        return m1;
+    };
+    // m = the tile being computed, mnext = the one being prefetched, mnn = found while mnext's loads are in flight
+    int64_t m = next_surviving(m0), mnext = m < m1 ? next_surviving(m + 1) : m1, mnn = m1;
+    int k = 0;  // surviving tiles so far: buffer and descriptor slot
+    if (m < m1) {
+        const int64_t t = tile_no(m);
+        const long long e0 = V.tl_ptr[t], e1 = V.tl_ptr[t + 1];
+        if (tid == 0) {
+            sDesc[0].base = e0;
+            sDesc[0].end = e1;
+        }
         int ti, tj;
-        tile_from_index(tile_no(m0), V.T, ti, tj);
+        tile_from_index(t, V.T, ti, tj);
         load_point_tile(V, ti, sD0i, sM0i);
         load_point_tile(V, tj, sD0j, sM0j);
-        load_tile_codes(V, &sDesc[0], sCode);
+        load_tile_codes(V, e0, e1, sCode);
         stage_cuts(ti, tj, 0);
         cp_async_commit();
     }
-    for (int64_t m = m0; m < m1; ++m) {
-        const int buf = (int)((m - m0) & 1);
+    for (; m < m1; m = mnext, mnext = mnn, ++k) {
+        const int buf = k & 1;
         int ti, tj;
         tile_from_index(tile_no(m), V.T, ti, tj);
         cp_async_wait_all();
         __syncthreads();
-        if (m + 1 < m1) {
+        if (mnext < m1) {
             int ni, nj;
-            tile_from_index(tile_no(m + 1), V.T, ni, nj);
+            const int64_t t = tile_no(mnext);
+            tile_from_index(t, V.T, ni, nj);
+            const long long e0 = V.tl_ptr[t], e1 = V.tl_ptr[t + 1];
+            if (tid == 0) {
+                sDesc[(k + 1) & 3].base = e0;
+                sDesc[(k + 1) & 3].end = e1;
+            }
             load_point_tile(V, ni, buf ? sD0i : sD1i, buf ? sM0i : sM1i);
             load_point_tile(V, nj, buf ? sD0j : sD1j, buf ? sM0j : sM1j);
-            load_tile_codes(V, &sDesc[(m + 1 - m0) & 3], sCode + (buf ^ 1) * TL_CAP);
-            if (m + 2 < m1) load_tile_desc(V, tile_no(m + 2), &sDesc[(m + 2 - m0) & 3]);
+            load_tile_codes(V, e0, e1, sCode + (buf ^ 1) * TL_CAP);
             stage_cuts(ni, nj, buf ^ 1);
             cp_async_commit();
         }
+        mnn = mnext < m1 ? next_surviving(mnext + 1) : m1;
         const float *sDi = buf ? sD1i : sD0i, *sDj = buf ? sD1j : sD0j;
         const PointMeta *sMi = buf ? sM1i : sM0i, *sMj = buf ? sM1j : sM0j;
         const float *k1I = c1I + buf * TILE, *k1J = c1J + buf * TILE;
         const float *k2I = c2I + buf * TILE, *k2J = c2J + buf * TILE;
         // tile-level pruning: no store entry in the tile and even the smallest possible prediction
         // exceeds every cut of the two tiles (phase 1 keeps a pair iff pred <= max(cut_i, cut_j))
-        const bool has_entries = sDesc[(m - m0) & 3].end != sDesc[(m - m0) & 3].base;
+        const bool has_entries = sDesc[k & 3].end != sDesc[k & 3].base;
         bool reduced = false;
         if (V.cull && V.is_metric && ti != tj) {
             const float cutmax = fmaxf(fmaxf(tile_max128(k1I), tile_max128(k2I)), fmaxf(tile_max128(k1J), tile_max128(k2J)));
@@ -426,7 +468,7 @@ __global__ void __launch_bounds__(SWT, 1) thresh_pairs_kernel(const __grid_const
         if (has_entries) ++n_with_entries;
         if (reduced) ++n_reduced;
         else ++n_computed;
-        build_tile_store(V, ts, &sDesc[(m - m0) & 3], sCode + buf * TL_CAP, sBm, 0);
+        build_tile_store(V, ts, &sDesc[k & 3], sCode + buf * TL_CAP, sBm, 0);
         const uint32_t *bm = sBm;
         // ---- phase 2: drain the warp's queue, one survivor per lane ----
         auto drain = [&](int qn) {
@@ -461,8 +503,10 @@ __global__ void __launch_bounds__(SWT, 1) thresh_pairs_kernel(const __grid_const
         };
         if (reduced) {
             // outlier rows / columns and store entries only, one pair per thread and round (sweep.cuh)
-            const TileDesc *dp = &sDesc[(m - m0) & 3];
+            const TileDesc *dp = &sDesc[k & 3];
             const int n_items = (s_out.n_i + s_out.n_j) * TILE + (int)(dp->end - dp->base);
+            if (n_items == 0) ++n_reduced_empty;
+            n_reduced_rows += s_out.n_i + s_out.n_j;
             for (int base = 0; base < n_items; base += SWT) {
                 int li = 0, lj = 0;
                 bool keep = false;
@@ -541,7 +585,34 @@ __global__ void __launch_bounds__(SWT, 1) thresh_pairs_kernel(const __grid_const
         atomicAdd(&A.counters[1], (unsigned long long)n_with_entries);
         atomicAdd(&A.counters[2], (unsigned long long)n_computed);
         atomicAdd(&A.counters[3], (unsigned long long)n_reduced);
+        atomicAdd(&A.counters[4], (unsigned long long)n_reduced_empty);
+        atomicAdd(&A.counters[5], (unsigned long long)n_reduced_rows);
     }
+}
+
+// per tile: the largest of max(cutA, cutB) over its 128 points (what tile_max128 gives a sweep for the staged
+// cuts); one warp per tile.  Lets a sweep test a tile pair before it loads anything of it.
+__global__ void __launch_bounds__(256)
+tile_cutmax_kernel(const float *__restrict__ cutA, const float *__restrict__ cutB, int T, float *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int t = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+    if (t >= T) return;
+    float m = -INFINITY;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int64_t g = (int64_t)t * TILE + q * 32 + lane;
+        m = fmaxf(m, cutB ? fmaxf(cutA[g], cutB[g]) : cutA[g]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) out[t] = m;
+}
+
+int launch_tile_cutmax(annb_ctx *c, const float *cutA, const float *cutB, int T, float *out)
+{
+    ANNB_LAUNCH(tile_cutmax_kernel, (T * 32 + 255) / 256, 256, 0, c->stream, cutA, cutB, T, out);
+    return ANNB_OK;
 }
 
 int launch_thresh_pairs(annb_ctx *c, ThreshPairArgs &A)

@@ -276,7 +276,11 @@ def test_tile_pruning_is_exact(monkeypatch, kind):
     monkeypatch.setenv("ANNB_NO_REDUCED", "1")
     c = Annchor(X, metric, **kw).fit()
     monkeypatch.delenv("ANNB_NO_REDUCED")
-    for o in (b, c):
+    # ... and with the tile test made after the loads instead of by the scan-ahead over the tile sequence
+    monkeypatch.setenv("ANNB_NO_SCAN", "1")
+    d = Annchor(X, metric, **kw).fit()
+    monkeypatch.delenv("ANNB_NO_SCAN")
+    for o in (b, c, d):
         assert a.evals == o.evals and a.n_forced == o.n_forced and a.n_tightened == o.n_tightened
         assert np.array_equal(a.neighbor_graph[0], o.neighbor_graph[0])
         assert np.array_equal(a.neighbor_graph[1], o.neighbor_graph[1])
