@@ -91,6 +91,8 @@ __global__ void __launch_bounds__(SWT, 1) thresh_sweep_kernel(const __grid_const
     if (lane == 0) *qcnt = 0;
     TileStore ts;
     ts.init(sTS);
+    __shared__ unsigned char s_flag[2][SWW];
+    int scan_round = 0;
     const int n_rb = A.rb_list ? A.n_rb : V.T;
     for (int rq = blockIdx.x * A.world + A.rank; rq < n_rb; rq += gridDim.x * A.world) {
         const int rb = A.rb_list ? A.rb_list[rq] : rq;
@@ -123,41 +125,75 @@ __global__ void __launch_bounds__(SWT, 1) thresh_sweep_kernel(const __grid_const
             }
             return tc < V.T ? tc : -1;
         };
-        __syncthreads();  // the previous row block is done with the descriptors
-        if (tid < 2 && col_at(tid) >= 0) {
-            const int64_t t = canon(col_at(tid));
-            sDesc[tid].base = V.tl_ptr[t];
-            sDesc[tid].end = V.tl_ptr[t + 1];
-        }
-        __syncthreads();
+        __syncthreads();  // the previous row block is done with the descriptors and the cuts are initialised
+        // scan-ahead over the column tile sequence (see thresh_pairs_kernel): a column tile without store entries that
+        // fails the tile test against the largest CURRENT cut of the 128 rows is skipped before it is loaded (cuts
+        // only ever decrease, so a test made ahead of time is conservative)
+        const bool cullable = V.cull && filter;
+        auto next_step = [&](int start) -> int {
+            if (!cullable) return start;
+            for (int base = start;; base += SWW, ++scan_round) {
+                if (col_at(base) < 0) return base;
+                const int tc = col_at(base + warp);
+                bool surv = false;
+                if (tc >= 0) {
+                    const int64_t t = canon(tc);
+                    surv = tc == rb || V.tl_ptr[t + 1] > V.tl_ptr[t] ||
+                           tile_can_pass<2>(V, M, rb, tc, tile_max128(cut), nullptr);
+                }
+                if (lane == 0) s_flag[scan_round & 1][warp] = surv ? 1 : 0;
+                __syncthreads();
+                int first = -1;
+#pragma unroll
+                for (int w = SWW - 1; w >= 0; --w)
+                    if (s_flag[scan_round & 1][w]) first = w;
+                if (first >= 0) {
+                    ++scan_round;
+                    return base + first;
+                }
+            }
+        };
+        int step_no = next_step(0), step_next = col_at(step_no) >= 0 ? next_step(step_no + 1) : step_no, step_nn = 0;
         load_point_tile(V, rb, sDi, sMi);
-        if (col_at(0) >= 0) {
-            load_point_tile(V, col_at(0), sDj0, sMj0);
-            load_tile_codes(V, &sDesc[0], sCode);
+        if (col_at(step_no) >= 0) {
+            const int64_t t = canon(col_at(step_no));
+            const long long e0 = V.tl_ptr[t], e1 = V.tl_ptr[t + 1];
+            if (tid == 0) {
+                sDesc[0].base = e0;
+                sDesc[0].end = e1;
+            }
+            load_point_tile(V, col_at(step_no), sDj0, sMj0);
+            load_tile_codes(V, e0, e1, sCode);
         }
         cp_async_commit();
 
-        int par = 0;  // buffer parity
-        for (int step_no = 0; col_at(step_no) >= 0; par ^= 1, ++step_no) {
+        for (int k = 0; col_at(step_no) >= 0; step_no = step_next, step_next = step_nn, ++k) {
+            const int par = k & 1;  // buffer parity
             const int tc = col_at(step_no);
             const float *sDj = par ? sDj1 : sDj0;
             const PointMeta *sMj = par ? sMj1 : sMj0;
             cp_async_wait_all();
             __syncthreads();
-            if (col_at(step_no + 1) >= 0) {  // prefetch the next column tile into the other buffer
-                load_point_tile(V, col_at(step_no + 1), par ? sDj0 : sDj1, par ? sMj0 : sMj1);
-                load_tile_codes(V, &sDesc[(step_no + 1) & 3], sCode + (par ^ 1) * TL_CAP);
-                if (col_at(step_no + 2) >= 0) load_tile_desc(V, canon(col_at(step_no + 2)), &sDesc[(step_no + 2) & 3]);
+            if (col_at(step_next) >= 0) {  // prefetch the next surviving column tile into the other buffer
+                const int64_t t = canon(col_at(step_next));
+                const long long e0 = V.tl_ptr[t], e1 = V.tl_ptr[t + 1];
+                if (tid == 0) {
+                    sDesc[(k + 1) & 3].base = e0;
+                    sDesc[(k + 1) & 3].end = e1;
+                }
+                load_point_tile(V, col_at(step_next), par ? sDj0 : sDj1, par ? sMj0 : sMj1);
+                load_tile_codes(V, e0, e1, sCode + (par ^ 1) * TL_CAP);
                 cp_async_commit();
             }
+            step_nn = col_at(step_next) >= 0 ? next_step(step_next + 1) : step_next;
             // entries are stored once per pair, in the tile of (lo, hi): the flags phase 1 reads are
             // re-oriented so that bit (row, col) of sBF is the flag of (this CTA's row point, column point)
             // tile-level pruning (metrics only: the phase-1 filter `pred < cut[row]` is on): no store entry
             // and the smallest possible prediction is not below the largest current cut of the 128 rows
-            if (V.cull && filter && sDesc[step_no & 3].end == sDesc[step_no & 3].base && tc != rb) {
+            if (V.cull && filter && sDesc[k & 3].end == sDesc[k & 3].base && tc != rb) {
                 if (!tile_can_pass<2>(V, M, rb, tc, tile_max128(cut), nullptr)) continue;
             }
-            build_tile_store(V, ts, &sDesc[step_no & 3], sCode + par * TL_CAP, sBF, tc < rb ? 1 : (tc == rb ? 2 : 3));
+            build_tile_store(V, ts, &sDesc[k & 3], sCode + par * TL_CAP, sBF, tc < rb ? 1 : (tc == rb ? 2 : 3));
             // ---- phase 1: bounds + clipped prediction, two passes of 4 x 8 pairs per thread ----
             int cAj[8];
 #pragma unroll

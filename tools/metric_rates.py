@@ -49,3 +49,10 @@ Xe = bench_blobs(1_000_000, 128, 100, 42, np.float32)
 ds = ab.Dataset(ctx, Xe, "euclidean")
 t, _, _ = rate(ds, len(Xe), 50_000_000)
 print("euclidean d=128 f32 (N=1M rows, random pairs): %.3e pairs/s, %.0f GB/s (1036 B per pair)" % (5e7 / t, 5e7 * 1036 / t / 1e9))
+# general cost-matrix Wasserstein (exact OT per pair, one warp per pair): the reference's digits fixture
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from conftest import load_golden  # noqa: E402
+g = load_golden("digits")
+ds = ab.Dataset(ctx, g["X"], "wasserstein", cost_matrix=g["cost_matrix"])
+t, _, _ = rate(ds, g["X"].shape[0], 2_000_000, reps=3)
+print("wasserstein (8x8 digits, general cost matrix, exact OT): %.3e pairs/s" % (2e6 / t))
