@@ -541,6 +541,7 @@ __device__ __forceinline__ bool point_can_pass(const View &V, const Model &M, co
 // (all rows x those columns) and the pairs with a store entry -- a few hundred pairs instead of 16 384 --
 // with the same per-pair arithmetic and the same phase 2.
 constexpr int MAXO = 16;
+constexpr int REDUCED_MAX_ITEMS = 3072;  // pairs of a reduced tile (outlier rows x 128 + store entries) above which the full tile is cheaper
 struct Outliers {  // shared memory
     uint32_t mi[4], mj[4];   // rows of the row tile / the column tile that can pass, as bit masks
     int n_i, n_j;

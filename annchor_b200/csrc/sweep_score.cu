@@ -218,6 +218,9 @@ __global__ void __launch_bounds__(SWT, 1) score_sweep_kernel(const __grid_consta
                     no_outliers(&s_out);
                     reduced = true;
                 }
+                // one pair per thread is ~3x less efficient than the vectorised tile: not worth it beyond ~3000 pairs
+                if (reduced && (s_out.n_i + s_out.n_j) * TILE + (long long)(sDesc[k & 3].end - sDesc[k & 3].base) > REDUCED_MAX_ITEMS)
+                    reduced = false;
             }
         }
         build_tile_store(V, ts, &sDesc[k & 3], sCode + buf * TL_CAP, sBm, 0);

@@ -499,6 +499,9 @@ __global__ void __launch_bounds__(SWT, 1) thresh_pairs_kernel(const __grid_const
                     no_outliers(&s_out);
                     reduced = true;
                 }
+                // one pair per thread is ~3x less efficient than the vectorised tile: not worth it beyond ~3000 pairs
+                if (reduced && (s_out.n_i + s_out.n_j) * TILE + (long long)(sDesc[k & 3].end - sDesc[k & 3].base) > REDUCED_MAX_ITEMS)
+                    reduced = false;
             }
         }
         if (has_entries) ++n_with_entries;
