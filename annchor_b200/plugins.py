@@ -183,22 +183,26 @@ class SimpleStratifiedSampler:
         if n_samples == 0:
             raise NothingToSample()
         bin_size, rem = n_samples // self.n_partitions, n_samples % self.n_partitions
-        indices = np.arange(sf.shape[0])
+        P = self.n_partitions
+        inner = bins[1:-1]
         rng = NumbaRNG(seed) if exact else None
-        if not exact:
+        bidx = np.digitize(sf, inner)  # sampler bin of every pool pair: bins[b] <= sf < bins[b + 1] (utils.py:547-549)
+
+        def priorities(ijs):
             # order-independent priorities (the pool arrives in atomic order): splitmix64 of the pair
             key = (ijs[:, 0].astype(np.uint64) << np.uint64(32)) | ijs[:, 1].astype(np.uint64)
             with np.errstate(over="ignore"):
                 z = key + np.uint64((seed * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF)
                 z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
                 z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
-                prio = z ^ (z >> np.uint64(31))
+                return z ^ (z >> np.uint64(31))
+
         if not exact:
             # bins the uniform pool left short are re-sampled at their own rate over all tiles (the
             # reference draws per bin from the materialised pair list, so a rare dad range is as well
             # represented as a common one)
-            want_b = n_samples // self.n_partitions + 1
-            cnt = np.array([np.count_nonzero((sf >= bins[b]) & (sf < bins[b + 1])) for b in range(self.n_partitions)])
+            want_b = n_samples // P + 1
+            cnt = np.bincount(bidx, minlength=P)
             short = cnt < want_b
             if short.any():
                 frac = max(n_pool / float(n_nc), 1e-12)
@@ -206,20 +210,18 @@ class SimpleStratifiedSampler:
                 n2 = ix.sample_pool_bins(seed, bins, rate, self.pool_size)
                 if n2 > 0:
                     ijs2, dad2 = ix.get_pool()
-                    keep = ~np.isin(np.digitize(sf, bins[1:-1]), np.nonzero(short)[0])
+                    keep = ~short[bidx]
                     ijs = np.concatenate([ijs[keep], ijs2])
                     sf = np.concatenate([sf[keep], dad2])
-                    key = (ijs[:, 0].astype(np.uint64) << np.uint64(32)) | ijs[:, 1].astype(np.uint64)
-                    with np.errstate(over="ignore"):
-                        z = key + np.uint64((seed * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF)
-                        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
-                        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
-                        prio = z ^ (z >> np.uint64(31))
-                    indices = np.arange(sf.shape[0])
+                    bidx = np.concatenate([bidx[keep], np.digitize(dad2, inner)])
+            prio = priorities(ijs)
         self.loop_num += 1
+        # members of every bin in increasing pool index (what indices[mask] would give)
+        by_bin = np.argsort(bidx, kind="stable")
+        starts = np.searchsorted(bidx[by_bin], np.arange(P + 1))
         parts = []
-        for b in range(self.n_partitions):
-            ixmask = indices[(sf >= bins[b]) & (sf < bins[b + 1])]
+        for b in range(P):
+            ixmask = by_bin[starts[b]:starts[b + 1]]
             want = bin_size + (b < rem)
             if ixmask.shape[0] < want:
                 parts.append(ixmask)
