@@ -186,7 +186,16 @@ class SimpleStratifiedSampler:
         P = self.n_partitions
         inner = bins[1:-1]
         rng = NumbaRNG(seed) if exact else None
-        bidx = np.digitize(sf, inner)  # sampler bin of every pool pair: bins[b] <= sf < bins[b + 1] (utils.py:547-549)
+
+        def bin_of(v):
+            # sampler bin of every pool pair: bins[b] <= v < bins[b + 1] (utils.py:547-549) = number of inner edges
+            # <= v (what np.digitize returns, without its per-element binary search)
+            out = np.zeros(v.shape[0], dtype=np.int8)
+            for e in inner:
+                out += v >= e
+            return out
+
+        bidx = bin_of(sf)
 
         def priorities(ijs):
             # order-independent priorities (the pool arrives in atomic order): splitmix64 of the pair
@@ -213,15 +222,12 @@ class SimpleStratifiedSampler:
                     keep = ~short[bidx]
                     ijs = np.concatenate([ijs[keep], ijs2])
                     sf = np.concatenate([sf[keep], dad2])
-                    bidx = np.concatenate([bidx[keep], np.digitize(dad2, inner)])
+                    bidx = np.concatenate([bidx[keep], bin_of(dad2)])
             prio = priorities(ijs)
         self.loop_num += 1
-        # members of every bin in increasing pool index (what indices[mask] would give)
-        by_bin = np.argsort(bidx, kind="stable")
-        starts = np.searchsorted(bidx[by_bin], np.arange(P + 1))
         parts = []
         for b in range(P):
-            ixmask = by_bin[starts[b]:starts[b + 1]]
+            ixmask = np.flatnonzero(bidx == b)  # members of the bin in increasing pool index
             want = bin_size + (b < rem)
             if ixmask.shape[0] < want:
                 parts.append(ixmask)
