@@ -107,6 +107,15 @@ class NumbaRNG:
             pass
 
 
+def bin_of(v, inner):
+    """Sampler bin of every value: bins[b] <= v < bins[b + 1] (annchor/utils.py:547-549) = the number of inner edges
+    <= v -- what np.digitize(v, inner) returns, without its per-element binary search (int8: at most 8 bins)."""
+    out = np.zeros(v.shape[0], dtype=np.int8)
+    for e in inner:
+        out += v >= e
+    return out
+
+
 def host_features(D, ijs):
     """[lb, ub, dad] of explicit pairs in float64 from the host copy of D (annchor/utils.py:274-301,
     355-380) -- used for the (<= n_samples) sample pairs only."""
@@ -186,16 +195,7 @@ class SimpleStratifiedSampler:
         P = self.n_partitions
         inner = bins[1:-1]
         rng = NumbaRNG(seed) if exact else None
-
-        def bin_of(v):
-            # sampler bin of every pool pair: bins[b] <= v < bins[b + 1] (utils.py:547-549) = number of inner edges
-            # <= v (what np.digitize returns, without its per-element binary search)
-            out = np.zeros(v.shape[0], dtype=np.int8)
-            for e in inner:
-                out += v >= e
-            return out
-
-        bidx = bin_of(sf)
+        bidx = bin_of(sf, inner)
 
         def priorities(ijs):
             # order-independent priorities (the pool arrives in atomic order): splitmix64 of the pair
@@ -222,7 +222,7 @@ class SimpleStratifiedSampler:
                     keep = ~short[bidx]
                     ijs = np.concatenate([ijs[keep], ijs2])
                     sf = np.concatenate([sf[keep], dad2])
-                    bidx = np.concatenate([bidx[keep], bin_of(dad2)])
+                    bidx = np.concatenate([bidx[keep], bin_of(dad2, inner)])
             prio = priorities(ijs)
         self.loop_num += 1
         parts = []

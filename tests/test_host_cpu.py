@@ -122,3 +122,17 @@ def test_device_specs_reject_opaque_plugins():
         plugins.regression_device_spec(Opaque(), list(plugins.FEATURE_NAMES))
     with pytest.raises(NotImplementedError):
         plugins.error_device_spec(Opaque())
+
+
+def test_sampler_bins_are_the_half_open_intervals_of_the_reference():
+    """bin_of == np.digitize == the reference's (lo <= x) & (x < hi) masks (annchor/utils.py:547-549), values on the
+    edges and +-inf edges included."""
+    from annchor_b200.plugins import bin_of
+    rng = np.random.default_rng(0)
+    bins = np.hstack([-np.inf, np.linspace(0.2, 0.8, 6), np.inf])
+    v = np.concatenate([rng.random(5000), bins[1:-1], bins[1:-1] - 1e-12, [0.0, 1.0, -3.0, 7.0]]).astype(np.float32)
+    got = bin_of(v, bins[1:-1])
+    assert got.dtype == np.int8
+    assert np.array_equal(got, np.digitize(v, bins[1:-1]))
+    for b in range(7):
+        assert np.array_equal(np.flatnonzero(got == b), np.flatnonzero((v >= bins[b]) & (v < bins[b + 1])))
