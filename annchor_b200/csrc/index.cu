@@ -2956,8 +2956,9 @@ ANNB_API int annb_index_sample_pool(annb_index *ix, uint64_t seed, int64_t max_p
     double frac = all ? 1.0 : 0.8 * (double)max_pool / (double)n_nc;
     for (int attempt = 0;; ++attempt) {
         ANNB_REQUIRE(attempt < 4, ANNB_ESTATE, "sampler pool did not fit");
-        // sparse samples visit 1 tile in 64 and take pairs there at 64x the rate
-        const double tile_frac = frac < 1.0 / 8192.0 ? 1.0 / 64.0 : 1.0;
+        // sparse samples visit a fraction of the tiles and take pairs there at a correspondingly higher rate: about 16
+        // pairs per visited tile, between 1 tile in 64 and 1 in 4096 (N = 1M: 2*10^4 of 3*10^7 tiles)
+        const double tile_frac = frac < 1.0 / 8192.0 ? std::min(1.0 / 64.0, std::max(1.0 / 4096.0, 1024.0 * frac)) : 1.0;
         A.tile_thr = tile_frac >= 1.0 ? 0xffffffffu : (uint32_t)(tile_frac * 4294967295.0);
         const double pfrac = frac / tile_frac;
         A.thr = pfrac >= 1.0 ? 0xffffffffu : (uint32_t)(pfrac * 4294967295.0);
@@ -3013,10 +3014,10 @@ ANNB_API int annb_index_sample_pool_bins(annb_index *ix, uint64_t seed, const do
     // that the sweep's cost follows the largest rate instead of being a full pass over all pairs
     double rmax = 0.0;
     for (int b = 0; b < nb; ++b) rmax = std::max(rmax, rate[b]);
-    // ... and at most ~10^6 tiles are visited (bounded cost at N = 1M, where a full pass is 3*10^7 tiles):
-    // a very rare bin then gets fewer pairs than asked for, still far more than the uniform pool held
-    double tile_frac = std::min(1.0, std::max(1.0 / 64.0, 8.0 * rmax));
-    tile_frac = std::min(tile_frac, std::max(1.0 / 64.0, 1.0e6 / (double)ix->NT));
+    // (in-tile rate <= 1/2) ... and at most ~2.5*10^5 tiles are visited (bounded cost at N = 1M, where a full pass is
+    // 3*10^7 tiles): a very rare bin then gets fewer pairs than asked for, still far more than the uniform pool held
+    double tile_frac = std::min(1.0, std::max(1.0 / 4096.0, 2.0 * rmax));
+    tile_frac = std::min(tile_frac, std::max(1.0 / 4096.0, 2.5e5 / (double)ix->NT));
     A.tile_thr = tile_frac >= 1.0 ? 0xffffffffu : (uint32_t)(tile_frac * 4294967295.0);
     A.thr = 0;
     for (int b = 0; b < MAX_BINS; ++b) {
