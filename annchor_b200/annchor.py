@@ -551,6 +551,14 @@ class Annchor:
                     cols.append(pos_in_both[int(i)])
         return np.array(rss)
 
+    def annchor_selective_subset(self, y, dne=None, alpha=0):
+        """annchor/annchor.py:788-919.  Not available: the reference's algorithm walks, for every point, the sorted
+        list of ALL its candidate pairs with their RefineApprox / upper-bound values -- materialised per-pair state
+        the streaming index does not keep.  ``alpha_rss`` (the greedy relaxed selective subset built on exact metric
+        evaluations) and ``get_nearest_enemies`` are available."""
+        raise NotImplementedError("annchor_selective_subset needs the reference's materialised per-pair state; "
+                                  "use alpha_rss(y, dne, alpha), which evaluates the metric on the device")
+
     def query(self, Q, nn=15, p_work=0.3, get_exact_query_ijs=None):
         """Query new data against the fitted index (annchor/annchor.py:643-683): returns
         (ngi int64 (len(Q), nn), ngd float64 (len(Q), nn)), the nn approximate nearest points of X per
